@@ -1,0 +1,157 @@
+"""TEST INFRASTRUCTURE ONLY -- run the reference's own renderer source without TensorFlow.
+
+The reference (TF 1.12 graph code) cannot be imported here: TensorFlow and
+tensorpack are absent and un-installable.  But the hot path is ~120 lines of
+pure tensor algebra that use ~25 ``tf.*`` names.  This module
+
+1. provides ``tf``: a namespace with exactly those names, each mapped onto the
+   torch op with the same semantics (shapes, axis conventions, dtypes), and
+2. ``load_reference_functions(path, names, K)``: parses a reference file with
+   ``ast``, compiles ONLY the named top-level ``def``s (nothing else in the file
+   is executed -- the module-level tensorpack imports never run) and binds them
+   to a namespace holding the shim, ``np`` and the module global ``nb_landmarks``
+   the functions read (mask/mask_gen_dynamic.py:126-128, 259-264).
+
+The reference source is read from ``/root/reference`` at call time and is never
+copied into this repository.  Used by ``tests/golden/make_golden.py`` to create
+the committed golden vectors and by ``tests/test_oracle_pinning.py`` (skipped
+when ``/root/reference`` is absent, e.g. on the GPU box).
+
+What this pins and what it does not: op ORDER, transposes, gather indices,
+broadcast shapes, sign flips and cast boundaries are the reference's own.  The
+primitive kernels (inv, det, matmul, exp) are torch's, not TF/Eigen's; float32
+``cos``/``sin`` and the float32 3x3 ``matmul`` are pinned to the definitions in
+``reference_port`` (correctly rounded trig, fixed summation order).
+"""
+from __future__ import annotations
+
+import ast
+import contextlib
+import types
+from typing import Dict, Iterable
+
+import numpy as np
+import torch
+
+from .reference_port import cos_f32, matmul3_f32, sin_f32, tf_linspace_f32
+
+
+def _dt(d):
+    return d
+
+
+def _stack(values, axis=0, name=None):
+    return torch.stack([torch.as_tensor(v) for v in values], dim=axis)
+
+
+def _matmul(a, b, transpose_a=False, transpose_b=False, name=None):
+    if transpose_a:
+        a = a.transpose(-1, -2)
+    if transpose_b:
+        b = b.transpose(-1, -2)
+    if a.dtype == torch.float32 and a.shape[-2:] == (3, 3) and b.shape[-2:] == (3, 3):
+        return matmul3_f32(a, b)      # pinned evaluation order, see reference_port.matmul3_f32
+    return torch.matmul(a, b)
+
+
+def _constant(value, dtype=None, name=None):
+    return torch.tensor(np.asarray(value), dtype=dtype)
+
+
+def _gather(params, indices, axis=0, name=None):
+    idx = torch.as_tensor(indices, dtype=torch.long)
+    return torch.index_select(params, axis, idx)
+
+
+def _linspace(start, stop, num, name=None):
+    assert float(start) == -1.0 and float(stop) == 1.0, "shim only models the call the path makes"
+    return torch.from_numpy(tf_linspace_f32(int(num)))
+
+
+def _meshgrid(x, y, indexing="xy"):
+    assert indexing == "xy"
+    X = x.view(1, -1).expand(y.numel(), x.numel())
+    Y = y.view(-1, 1).expand(y.numel(), x.numel())
+    return [X, Y]
+
+
+def _reshape(t, shape, name=None):
+    return t.reshape([int(s) for s in shape])
+
+
+def _reduce_sum(t, axis=None, keepdims=False, name=None):
+    return t.sum(dim=axis, keepdim=keepdims) if axis is not None else t.sum()
+
+
+def _reduce_max(t, axis=None, keepdims=False, name=None):
+    if isinstance(t, (list, tuple)):
+        t = torch.stack(list(t), dim=0)
+    return t.max(dim=axis, keepdim=keepdims).values if axis is not None else t.max()
+
+
+def _zeros(shape, dtype=torch.float32, name=None):
+    return torch.zeros([int(s) for s in shape], dtype=dtype)
+
+
+def _squeeze(t, axis=None, name=None):
+    return t.squeeze(axis) if axis is not None else t.squeeze()
+
+
+def _transpose(t, perm=None, name=None):
+    return t.permute(*perm) if perm is not None else t.t()
+
+
+def _tile(t, multiples, name=None):
+    return t.repeat(*[int(m) for m in multiples])
+
+
+@contextlib.contextmanager
+def _name_scope(*a, **k):
+    yield
+
+
+def make_tf() -> types.SimpleNamespace:
+    """Build the ``tf`` stand-in.  Only names used on the path exist; anything else raises."""
+    linalg = types.SimpleNamespace(
+        inv=lambda a, name=None: torch.linalg.inv(a),
+        det=lambda a, name=None: torch.linalg.det(a),
+        matmul=_matmul,
+    )
+    tf = types.SimpleNamespace(
+        float32=torch.float32, float64=torch.float64, newaxis=None,
+        zeros_like=lambda t, name=None: torch.zeros_like(torch.as_tensor(t)),
+        ones_like=lambda t, name=None: torch.ones_like(torch.as_tensor(t)),
+        zeros=_zeros, stack=_stack, cos=cos_f32, sin=sin_f32, exp=torch.exp,
+        matmul=_matmul, constant=_constant, reshape=_reshape,
+        shape=lambda t: tuple(t.shape),
+        cast=lambda t, dtype, name=None: t.to(dtype),
+        to_float=lambda t, name=None: t.to(torch.float32),
+        identity=lambda t, name=None: t,
+        transpose=_transpose, gather=_gather, squeeze=_squeeze, tile=_tile,
+        expand_dims=lambda t, axis, name=None: t.unsqueeze(axis),
+        linspace=_linspace, meshgrid=_meshgrid, reduce_sum=_reduce_sum, reduce_max=_reduce_max,
+        name_scope=_name_scope, linalg=linalg,
+    )
+    return tf
+
+
+def load_reference_functions(path: str, names: Iterable[str], nb_landmarks: int,
+                             extra_globals: Dict | None = None) -> Dict[str, object]:
+    """Compile the named top-level functions of reference file ``path`` against the shim."""
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    wanted = set(names)
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    # a file may define a name more than once (never the case for the path, but be strict)
+    seen = [n.name for n in picked]
+    missing = wanted - set(seen)
+    if missing:
+        raise KeyError(f"{path}: no top-level def for {sorted(missing)}")
+    if len(seen) != len(set(seen)):
+        raise ValueError(f"{path}: duplicate definitions among {seen}")
+    mod = ast.Module(body=picked, type_ignores=[])
+    ns: Dict[str, object] = {"tf": make_tf(), "np": np, "nb_landmarks": int(nb_landmarks)}
+    if extra_globals:
+        ns.update(extra_globals)
+    exec(compile(mod, path, "exec"), ns)  # noqa: S102 -- executing the read-only reference, on purpose
+    return {n: ns[n] for n in wanted}

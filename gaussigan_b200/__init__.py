@@ -1,0 +1,14 @@
+"""gaussigan_b200 -- B200-native (sm_100a) drop-in for GaussiGAN's splat-to-silhouette renderer.
+
+Only the reference's data-parallel hot path lives here: the renderer
+``get_landmarks`` / ``get_gaussian_maps_2d`` and its backward, as hand-written CUDA kernels behind a
+C ABI (``include/gaussigan.h``), with this package as the host-side mirror of the reference's Python
+interface.  Importing it loads ``lib/libgaussigan_sm100.so`` and fails loudly if it is missing.
+"""
+from ._lib import GaussiganError, lib as _capi  # noqa: F401  (import = load the shared library)
+from .renderer import (REFERENCE_SIZES, get_gaussian_maps_2d, get_landmarks, get_landmarks_infer,
+                       get_landmarks_with_mask, project, render_silhouette)
+
+__all__ = ["REFERENCE_SIZES", "GaussiganError", "get_gaussian_maps_2d", "get_landmarks", "get_landmarks_infer",
+           "get_landmarks_with_mask", "project", "render_silhouette"]
+__version__ = "0.1.0"

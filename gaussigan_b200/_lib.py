@@ -1,0 +1,76 @@
+"""ctypes binding of ``libgaussigan_sm100.so`` (the C ABI in ``include/gaussigan.h``).
+
+There is NO fallback: if the shared library is missing the import raises, and every entry point that
+returns a negative status raises ``GaussiganError`` with ``gg_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+GG_PARAM_STRIDE = 8
+GG_MOMENTS = 5
+GG_MAX_SCALES = 4
+LAYOUT_NHWC = 0
+LAYOUT_NCHW = 1
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libgaussigan_sm100.so"
+
+
+class GaussiganError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+def _load() -> C.CDLL:
+    path = Path(os.environ.get("GAUSSIGAN_LIB", _LIB_PATH))
+    if not path.exists():
+        raise ImportError(
+            f"{path} not found: build it with `python -m gaussigan_b200.build` "
+            "(nvcc, sm_100a). gaussigan_b200 has no CPU or PyTorch fallback.")
+    return C.CDLL(str(path))
+
+
+lib = _load()
+
+_vp, _i, _d = C.c_void_p, C.c_int, C.c_double
+_ip = C.POINTER(C.c_int)
+_pp = C.POINTER(C.c_void_p)
+
+#: name -> (restype, argtypes); mirrors include/gaussigan.h one to one
+SIGNATURES = {
+    "gg_version": (_i, []),
+    "gg_last_error": (C.c_char_p, []),
+    "gg_project_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "gg_project_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _vp, _i, _vp, _vp,
+                            _vp, _vp, _vp, _i, _vp]),
+    "gg_conic_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "gg_conic_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    "gg_splat_fwd": (_i, [_vp, _i, _i, _i, _ip, _pp, _pp, _i, _i, _vp]),
+    "gg_splat_bwd_tiles": (_i, [_i, _i, _ip, _ip, _ip, _i]),
+    "gg_splat_bwd": (_i, [_vp, _i, _i, _i, _ip, _pp, _pp, _i, _vp, _i, _i, _vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header and library disagree
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return (lib.gg_last_error() or b"").decode()
+
+
+def check(status: int, what: str) -> int:
+    if status < 0:
+        raise GaussiganError(f"{what} failed ({status}): {last_error()}")
+    return status
+
+
+def int_array(values):
+    return (C.c_int * len(values))(*[int(v) for v in values])
+
+
+def ptr_array(ptrs):
+    """Host array of device pointers; ``None``/0 entries become NULL."""
+    return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) if p else None for p in ptrs])

@@ -1,0 +1,79 @@
+"""Build libgaussigan_sm100.so in-tree with nvcc for sm_100a (B200).
+
+``python -m gaussigan_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles without a
+GPU.  The library lands in ``gaussigan_b200/lib/`` (git-ignored, shipped to the GPU box by gpurun).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIBDIR = PKG / "lib"
+LIBNAME = "libgaussigan_sm100.so"
+SOURCES = ["gg_capi.cu", "gg_project.cu", "gg_splat.cu", "gg_fused.cu", "gg_geometry.cu", "gg_host.cu"]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden",
+    "--expt-relaxed-constexpr",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libgaussigan_sm100.so cannot be built")
+
+
+def _sources() -> list[Path]:
+    return [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    files = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
+                   + [PKG.parent / "include" / "gaussigan.h"])
+    for f in files:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def lib_path() -> Path:
+    return LIBDIR / LIBNAME
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    LIBDIR.mkdir(exist_ok=True)
+    out = lib_path()
+    stamp = LIBDIR / (LIBNAME + ".sha256")
+    fp = _fingerprint()
+    if not force and out.exists() and stamp.exists() and stamp.read_text().strip() == fp:
+        return out
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(out), *map(str, _sources())]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr, file=sys.stderr)
+    stamp.write_text(fp)
+    return out
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

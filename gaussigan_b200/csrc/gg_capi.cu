@@ -1,0 +1,170 @@
+// gg_capi.cu -- the extern "C" surface declared in include/gaussigan.h: argument validation,
+// device selection, error reporting.  No compute here.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "gg_common.cuh"
+#include "gg_launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char *where) {
+  return fail(GG_E_CUDA, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int set_device(int device) {
+  thread_local int current = -1;
+  if (device != current) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    current = device;
+  }
+  return GG_OK;
+}
+
+int check_bk(int B, int K) {
+  if (B < 0 || K <= 0) return fail(GG_E_SHAPE, "B must be >= 0 and K > 0 (got B=%d, K=%d)", B, K);
+  if ((long long)B * K > (1ll << 30)) return fail(GG_E_SHAPE, "B*K too large (%lld)", (long long)B * K);
+  return GG_OK;
+}
+
+int check_scales(int K, int nscales, const int *sizes) {
+  if (nscales < 1 || nscales > GG_MAX_SCALES)
+    return fail(GG_E_SHAPE, "nscales must be in 1..%d (got %d)", GG_MAX_SCALES, nscales);
+  if (!sizes) return fail(GG_E_NULL, "sizes_host is NULL");
+  for (int i = 0; i < nscales; ++i)
+    if (sizes[i] < 1 || sizes[i] > 16384) return fail(GG_E_SHAPE, "scale %d: n=%d out of range 1..16384", i, sizes[i]);
+  if (K > 1536) return fail(GG_E_SHAPE, "K=%d exceeds the staged-parameter shared-memory budget (1536)", K);
+  return GG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gg_version(void) { return GG_VERSION; }
+
+const char *gg_last_error(void) { return g_err; }
+
+int gg_project_fwd(const float *mus, const void *sigma, int sigma_is_f64, const float *rotx, const float *roty,
+                   const float *rotz, double tx, double ty, double tz, double focal, int B, int K, double *mu2d,
+                   double *sigma2d, float *params, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (B == 0) return GG_OK;
+  if (!mus || !sigma || !rotx || !roty || !rotz || !params) return fail(GG_E_NULL, "gg_project_fwd: NULL input");
+  if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_project_fwd: params must be 16-byte aligned");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_project_fwd(mus, sigma, sigma_is_f64, rotx, roty, rotz, tx, ty, tz, focal, B, K, mu2d,
+                                         sigma2d, params, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_project_fwd");
+}
+
+int gg_project_bwd(const float *mus, const void *sigma, int sigma_is_f64, const float *rotx, const float *roty,
+                   const float *rotz, double tx, double ty, double tz, double focal, int B, int K,
+                   const float *partials, int T, const double *gmu2d, const double *gsigma2d, float *dmus,
+                   double *dsigma, float *drot, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (B == 0) return GG_OK;
+  if (!mus || !sigma || !rotx || !roty || !rotz) return fail(GG_E_NULL, "gg_project_bwd: NULL input");
+  if (T < 0 || (T > 0 && !partials)) return fail(GG_E_WORKSPACE, "gg_project_bwd: T=%d but partials is NULL", T);
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_project_bwd(mus, sigma, sigma_is_f64, rotx, roty, rotz, tx, ty, tz, focal, B, K,
+                                         partials, T, gmu2d, gsigma2d, dmus, dsigma, drot, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_project_bwd");
+}
+
+int gg_conic_fwd(const void *mu2d, const void *sigma2d, int is_f64, int B, int K, float *params, int device,
+                 void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (B == 0) return GG_OK;
+  if (!mu2d || !sigma2d || !params) return fail(GG_E_NULL, "gg_conic_fwd: NULL input");
+  if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_conic_fwd: params must be 16-byte aligned");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_conic_fwd(mu2d, sigma2d, is_f64, B * K, params, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_conic_fwd");
+}
+
+int gg_conic_bwd(const void *mu2d, const void *sigma2d, int is_f64, int B, int K, const float *partials, int T,
+                 double *dmu2d, double *dsigma2d, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (B == 0) return GG_OK;
+  if (!mu2d || !sigma2d) return fail(GG_E_NULL, "gg_conic_bwd: NULL input");
+  if (T <= 0 || !partials) return fail(GG_E_WORKSPACE, "gg_conic_bwd: needs T > 0 partials (T=%d)", T);
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_conic_bwd(mu2d, sigma2d, is_f64, B, K, partials, T, dmu2d, dsigma2d,
+                                       (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_conic_bwd");
+}
+
+int gg_splat_fwd(const float *params, int B, int K, int nscales, const int *sizes_host, float *const *maps_host,
+                 float *const *masks_host, int layout, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (int r = check_scales(K, nscales, sizes_host)) return r;
+  if (layout != GG_LAYOUT_NHWC && layout != GG_LAYOUT_NCHW) return fail(GG_E_SHAPE, "unknown layout %d", layout);
+  if (B == 0) return GG_OK;
+  if (!params) return fail(GG_E_NULL, "gg_splat_fwd: params is NULL");
+  if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_splat_fwd: params must be 16-byte aligned");
+  bool any = false;
+  for (int i = 0; i < nscales; ++i) {
+    float *m = maps_host ? maps_host[i] : nullptr;
+    float *k = masks_host ? masks_host[i] : nullptr;
+    if (m || k) any = true;
+    if ((m && !aligned16(m)) || (k && !aligned16(k)))
+      return fail(GG_E_ALIGN, "gg_splat_fwd: scale %d output not 16-byte aligned", i);
+    if ((long long)B * sizes_host[i] * sizes_host[i] > (1ll << 40)) return fail(GG_E_SHAPE, "scale %d too large", i);
+  }
+  if (!any) return fail(GG_E_NULL, "gg_splat_fwd: no output requested");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_splat_fwd(params, B, K, nscales, sizes_host, maps_host, masks_host, layout,
+                                       (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_splat_fwd");
+}
+
+int gg_splat_bwd_tiles(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,
+                       const int *has_gmasks_host, int layout) {
+  if (K <= 0) return fail(GG_E_SHAPE, "K must be > 0");
+  if (int r = check_scales(K, nscales, sizes_host)) return r;
+  if (layout != GG_LAYOUT_NHWC && layout != GG_LAYOUT_NCHW) return fail(GG_E_SHAPE, "unknown layout %d", layout);
+  return gg::plan_bwd_tiles(K, nscales, sizes_host, has_gmaps_host, has_gmasks_host, layout);
+}
+
+int gg_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes_host,
+                 const float *const *gmaps_host, const float *const *gmasks_host, int layout, float *partials, int T,
+                 int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (int r = check_scales(K, nscales, sizes_host)) return r;
+  if (layout != GG_LAYOUT_NHWC && layout != GG_LAYOUT_NCHW) return fail(GG_E_SHAPE, "unknown layout %d", layout);
+  if (B == 0) return GG_OK;
+  if (!params || !partials) return fail(GG_E_NULL, "gg_splat_bwd: params/partials is NULL");
+  if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_splat_bwd: params must be 16-byte aligned");
+  int hm[GG_MAX_SCALES], hk[GG_MAX_SCALES];
+  for (int i = 0; i < nscales; ++i) {
+    const float *m = gmaps_host ? gmaps_host[i] : nullptr;
+    const float *k = gmasks_host ? gmasks_host[i] : nullptr;
+    hm[i] = m != nullptr;
+    hk[i] = k != nullptr;
+    if ((m && !aligned16(m)) || (k && !aligned16(k)))
+      return fail(GG_E_ALIGN, "gg_splat_bwd: scale %d gradient not 16-byte aligned", i);
+  }
+  int need = gg::plan_bwd_tiles(K, nscales, sizes_host, hm, hk, layout);
+  if (need != T || T <= 0)
+    return fail(GG_E_WORKSPACE, "gg_splat_bwd: T=%d but this configuration writes %d partial tiles", T, need);
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_splat_bwd(params, B, K, nscales, sizes_host, gmaps_host, gmasks_host, layout, partials,
+                                       T, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_splat_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// gg_common.cuh -- shared device helpers and host-side launch descriptors (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gaussigan.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgaussigan_sm100 is written for sm_100a (B200) only"
+#endif
+
+namespace gg {
+
+constexpr int kThreads = 256;          // CTA size of every splat kernel (8 warps)
+constexpr int kWarps = kThreads / 32;
+constexpr int kStrip = 8;              // pixels per thread-strip along x (two 128-bit accesses)
+constexpr int kKBlock = 64;            // Gaussians handled per CTA along grid.z in the backward
+
+// Staged per-Gaussian record, GG_PARAM_STRIDE floats, written by the projection kernels:
+//   [0] mu_x  [1] mu_y  [2] nA = -a*log2(e)  [3] nr = -(b/a)  [4] nE = -(c - b*b/a)*log2(e)
+//   [5..7] a, b, c (kept for debugging / future use)
+// so that  g(x, y) = exp2( nA * t^2 + nE * dy^2 ),  dy = y - mu_y,  t = x - (mu_x + nr*dy)
+// which is exp(-(a dx^2 + 2 b dx dy + c dy^2)) after completing the square along x.
+struct ScaleDesc {
+  int n;           // image side
+  int spr;         // strips per row            = ceil(n / kStrip)
+  int sprc;        // strips per row per chunk  = min(spr, kThreads)
+  int rpp;         // rows per pass of one CTA  = max(1, kThreads / spr)
+  int chunks;      // column chunks             = ceil(spr / kThreads)
+  int rows_per_tile;
+  int tile_begin;  // first tile index of this scale inside the launch
+  int tiles;       // tiles of this scale per batch element
+  float step;      // float32 (2 / (n-1)), TF 1.12 LinSpace step (mask_gen_dynamic.py:121-122)
+  float *maps;     // forward outputs / backward upstream gradients (const in the backward)
+  float *mask;
+};
+
+struct SplatArgs {
+  const float *params;   // [B,K,GG_PARAM_STRIDE]
+  float *partials;       // backward: [B,T,K,GG_MOMENTS]
+  int B, K;
+  int T;                 // tiles per batch element in THIS launch (splits blockIdx.x)
+  int slots;             // backward: total partial slots per batch element (partials stride)
+  int nscales;
+  int layout;
+  int tile_offset;       // backward: first partial slot written by this launch
+  ScaleDesc sc[GG_MAX_SCALES];
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Pixel-centre coordinate exactly as TF 1.12 LinSpace evaluates it in float32:
+// out[j] = start + step * j, product and sum each rounded (no FMA contraction).
+__device__ __forceinline__ float grid_coord(int j, float step) {
+  return __fadd_rn(-1.0f, __fmul_rn(step, (float)j));
+}
+
+__device__ __forceinline__ void st_f4(float *p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+
+}  // namespace gg

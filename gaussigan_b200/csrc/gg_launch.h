@@ -1,0 +1,25 @@
+// gg_launch.h -- host-side launchers implemented in gg_project.cu / gg_splat.cu, called by gg_capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gg {
+
+cudaError_t launch_project_fwd(const float *mus, const void *sigma, int f64, const float *rx, const float *ry,
+                               const float *rz, double tx, double ty, double tz, double focal, int B, int K,
+                               double *mu2d, double *sigma2d, float *params, cudaStream_t st);
+cudaError_t launch_project_bwd(const float *mus, const void *sigma, int f64, const float *rx, const float *ry,
+                               const float *rz, double tx, double ty, double tz, double focal, int B, int K,
+                               const float *partials, int T, const double *gmu2d, const double *gsigma2d,
+                               float *dmus, double *dsigma, float *drot, cudaStream_t st);
+cudaError_t launch_conic_fwd(const void *mu2d, const void *sigma2d, int f64, int N, float *params, cudaStream_t st);
+cudaError_t launch_conic_bwd(const void *mu2d, const void *sigma2d, int f64, int B, int K, const float *partials,
+                             int T, double *dmu2d, double *dsigma2d, cudaStream_t st);
+
+int plan_bwd_tiles(int K, int nscales, const int *sizes, const int *has_gmaps, const int *has_gmasks, int layout);
+cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, const int *sizes, float *const *maps,
+                             float *const *masks, int layout, cudaStream_t st);
+cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes,
+                             const float *const *gmaps, const float *const *gmasks, int layout, float *partials,
+                             int T, cudaStream_t st);
+
+}  // namespace gg

@@ -1,0 +1,634 @@
+// gg_splat.cu -- the per-pixel kernels: evaluate K projected Gaussians at every pixel (forward) and
+// reduce per-pixel upstream gradients into five moments per Gaussian (backward).
+//
+// Replaces get_gaussian_maps_2d's raster, the float32 cast, the 4-scale loop and the sum composite
+// (mask/mask_gen_dynamic.py:121-141, 315-319, 785-786) and their tf.gradients.
+//
+// Arithmetic.  With the conic completed along x (see gg_common.cuh),
+//     g = exp2(nA * t^2 + nE * dy^2),   dy = y - mu_y,   t = x - (mu_x + nr * dy)
+// so a thread that owns a strip of 8 pixels of one row pays ~4 instructions per (row, Gaussian) for
+// (dy, shift, nE*dy^2) and then FADD + FMUL + FFMA + MUFU.EX2 (+ FADD into the mask) per pixel:
+// 5 issue slots per (pixel, Gaussian) instead of the 9 of the textbook form.  The backward
+// accumulates sum(w), sum(w t), sum(w t^2) along the strip (w = g * Gbar) and folds them into the
+// five moments {t^2, t dy, dy^2, t, dy} per row; the projection adjoint converts the sheared moments
+// back (gg_project.cu: conic_adjoint).  No tensor cores: nothing here is a contraction.
+//
+// Two thread mappings:
+//   strip kernels  -- thread = 8 consecutive pixels of a row, loop over K.  Used for mask-only
+//                     output/gradient and for NCHW maps (128-bit stores along W); also the generic
+//                     NHWC fallback for K that is not 4 * 2^m.
+//   quad kernels   -- NHWC maps: thread = (pixel, 4 consecutive Gaussians), one 128-bit access per
+//                     pixel-quad, consecutive lanes -> consecutive 16-byte chunks (fully coalesced).
+//
+// Backward reduction: per-thread registers -> per-warp transpose through padded shared memory
+// (5 STS per Gaussian, conflict-free) -> 32-term serial sums by 30 lanes -> fixed-order sum over the
+// 8 warps -> one [K,5] partial per CTA written to its own slot.  No atomics, no zero-fill,
+// bit-reproducible; the O(T) sum over slots happens in float64 in the projection adjoint.
+#include <cstdlib>
+#include "gg_common.cuh"
+
+namespace gg {
+
+namespace {
+
+constexpr int kKC = 6;                      // Gaussians staged per warp-flush (5*kKC <= 32 columns)
+constexpr int kStageCols = kKC * GG_MOMENTS;
+
+__device__ __forceinline__ int find_scale(const SplatArgs &a, int tile) {
+  int si = 0;
+#pragma unroll
+  for (int i = 1; i < GG_MAX_SCALES; ++i)
+    if (i < a.nscales && tile >= a.sc[i].tile_begin) si = i;
+  return si;
+}
+
+__device__ __forceinline__ void store8(float *p, int col0, int n, const float *v) {
+  if ((n & 3) == 0) {
+    if (col0 < n) st_f4(p, v[0], v[1], v[2], v[3]);
+    if (col0 + 4 < n) st_f4(p + 4, v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j)
+      if (col0 + j < n) p[j] = v[j];
+  }
+}
+
+__device__ __forceinline__ void load8(const float *p, int col0, int n, float *v) {
+  if ((n & 3) == 0) {
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    if (col0 < n) lo = __ldg(reinterpret_cast<const float4 *>(p));
+    if (col0 + 4 < n) hi = __ldg(reinterpret_cast<const float4 *>(p + 4));
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j) v[j] = (col0 + j < n) ? __ldg(p + j) : 0.f;
+  }
+}
+
+// thread -> strip geometry shared by the strip kernels
+struct StripPos {
+  int col0;       // first pixel column of the strip
+  int row0;       // row of pass r is row0 + r * rpp
+  bool valid;
+};
+
+__device__ __forceinline__ StripPos strip_pos(const ScaleDesc &s, int tile_local) {
+  StripPos p;
+  int rt = tile_local / s.chunks;
+  int ch = tile_local - rt * s.chunks;
+  int rp = threadIdx.x / s.sprc;
+  int sc = threadIdx.x - rp * s.sprc;
+  int strip = ch * kThreads + sc;
+  p.col0 = strip * kStrip;
+  p.row0 = rt * s.rows_per_tile + rp;
+  p.valid = (rp < s.rpp) && (strip < s.spr);
+  return p;
+}
+
+}  // namespace
+
+// =============================================================================== forward, strips
+// OUT: 0 = mask only, 1 = NCHW maps (+ mask when given), 2 = NHWC maps, scalar stores (+ mask)
+template <int RPT, int OUT>
+__global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_constant__ SplatArgs a) {
+  extern __shared__ float4 sp[];   // [K][2]
+  const int b = blockIdx.x / a.T;  // a.T = tiles per batch element in this launch
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+
+  const float4 *gp = reinterpret_cast<const float4 *>(a.params + (size_t)b * K * GG_PARAM_STRIDE);
+  for (int i = threadIdx.x; i < 2 * K; i += kThreads) sp[i] = __ldg(gp + i);
+  __syncthreads();
+
+  const StripPos pos = strip_pos(s, tile - s.tile_begin);
+  if (!pos.valid) return;
+
+  float x[kStrip];
+#pragma unroll
+  for (int j = 0; j < kStrip; ++j) x[j] = grid_coord(pos.col0 + j, s.step);
+  float y[RPT];
+  bool rv[RPT];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    int row = pos.row0 + r * s.rpp;
+    rv[r] = row < n;
+    y[r] = grid_coord(row, s.step);
+  }
+  float acc[RPT][kStrip];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j) acc[r][j] = 0.f;
+
+  for (int k = 0; k < K; ++k) {
+    const float4 p = sp[2 * k];          // mu_x, mu_y, nA, nr
+    const float nE = sp[2 * k + 1].x;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const float dy = y[r] - p.y;
+      const float sh = fmaf(p.w, dy, p.x);
+      const float e = (nE * dy) * dy;
+      float g[kStrip];
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j) {
+        const float t = x[j] - sh;
+        g[j] = ex2_approx(fmaf(p.z * t, t, e));
+        acc[r][j] += g[j];
+      }
+      if (OUT == 1) {
+        if (rv[r]) {
+          int row = pos.row0 + r * s.rpp;
+          store8(s.maps + (((size_t)b * K + k) * n + row) * n + pos.col0, pos.col0, n, g);
+        }
+      } else if (OUT == 2) {
+        if (rv[r]) {
+          int row = pos.row0 + r * s.rpp;
+          float *q = s.maps + (((size_t)b * n + row) * n + pos.col0) * K + k;
+#pragma unroll
+          for (int j = 0; j < kStrip; ++j)
+            if (pos.col0 + j < n) q[(size_t)j * K] = g[j];
+        }
+      }
+    }
+  }
+  if (s.mask) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      if (!rv[r]) continue;
+      int row = pos.row0 + r * s.rpp;
+      store8(s.mask + ((size_t)b * n + row) * n + pos.col0, pos.col0, n, acc[r]);
+    }
+  }
+}
+
+// ============================================================================== backward, strips
+// GIN: 0 = gradient w.r.t. mask only, 1 = NCHW gmaps (+ gmask), 2 = NHWC gmaps, scalar loads (+ gmask)
+template <int RPT, int GIN>
+__global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_constant__ SplatArgs a) {
+  __shared__ float4 sp[kKBlock * 2];
+  __shared__ float stage[kWarps][kStageCols][33];
+  __shared__ float warpsum[kWarps][kKBlock * GG_MOMENTS];
+
+  const int b = blockIdx.x / a.T;   // a.T here = tiles per batch element in THIS launch
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+  const int k0 = blockIdx.y * kKBlock;
+  const int kn = min(kKBlock, K - k0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const float4 *gp = reinterpret_cast<const float4 *>(a.params + ((size_t)b * K + k0) * GG_PARAM_STRIDE);
+  for (int i = threadIdx.x; i < 2 * kn; i += kThreads) sp[i] = __ldg(gp + i);
+  __syncthreads();
+
+  const StripPos pos = strip_pos(s, tile - s.tile_begin);
+  const float *gmask = s.mask;
+  const float *gmaps = s.maps;
+
+  float x[kStrip];
+#pragma unroll
+  for (int j = 0; j < kStrip; ++j) x[j] = grid_coord(pos.col0 + j, s.step);
+  float y[RPT];
+  bool rv[RPT];
+  float gm[RPT][kStrip];
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    int row = pos.row0 + r * s.rpp;
+    rv[r] = pos.valid && row < n;
+    y[r] = grid_coord(row, s.step);
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j) gm[r][j] = 0.f;
+    if (rv[r] && gmask) load8(gmask + ((size_t)b * n + row) * n + pos.col0, pos.col0, n, gm[r]);
+  }
+
+  for (int kk = 0; kk < kn; ++kk) {
+    const float4 p = sp[2 * kk];
+    const float nE = sp[2 * kk + 1].x;
+    float T20 = 0.f, T11 = 0.f, T02 = 0.f, T10 = 0.f, T01 = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      if (!rv[r]) continue;
+      float G[kStrip];
+      if (GIN == 0) {
+#pragma unroll
+        for (int j = 0; j < kStrip; ++j) G[j] = gm[r][j];
+      } else if (GIN == 1) {
+        int row = pos.row0 + r * s.rpp;
+        load8(gmaps + (((size_t)b * K + k0 + kk) * n + row) * n + pos.col0, pos.col0, n, G);
+#pragma unroll
+        for (int j = 0; j < kStrip; ++j) G[j] += gm[r][j];
+      } else {
+        int row = pos.row0 + r * s.rpp;
+        const float *q = gmaps + (((size_t)b * n + row) * n + pos.col0) * K + k0 + kk;
+#pragma unroll
+        for (int j = 0; j < kStrip; ++j)
+          G[j] = ((pos.col0 + j < n) ? __ldg(q + (size_t)j * K) : 0.f) + gm[r][j];
+      }
+      const float dy = y[r] - p.y;
+      const float sh = fmaf(p.w, dy, p.x);
+      const float e = (nE * dy) * dy;
+      float S0 = 0.f, S1 = 0.f, S2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j) {
+        const float t = x[j] - sh;
+        const float w = ex2_approx(fmaf(p.z * t, t, e)) * G[j];
+        const float wt = w * t;
+        S0 += w;
+        S1 += wt;
+        S2 = fmaf(wt, t, S2);
+      }
+      T20 += S2;
+      T10 += S1;
+      T11 = fmaf(dy, S1, T11);
+      const float d0 = dy * S0;
+      T01 += d0;
+      T02 = fmaf(dy, d0, T02);
+    }
+    const int c0 = (kk % kKC) * GG_MOMENTS;
+    stage[warp][c0 + 0][lane] = T20;
+    stage[warp][c0 + 1][lane] = T11;
+    stage[warp][c0 + 2][lane] = T02;
+    stage[warp][c0 + 3][lane] = T10;
+    stage[warp][c0 + 4][lane] = T01;
+    if ((kk % kKC) == kKC - 1 || kk == kn - 1) {
+      __syncwarp();
+      const int ncols = c0 + GG_MOMENTS;
+      const int cbase = (kk / kKC) * kStageCols;
+      if (lane < ncols) {
+        float acc = 0.f;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) acc += stage[warp][lane][l];
+        warpsum[warp][cbase + lane] = acc;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  float *out = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K + k0) * GG_MOMENTS;
+  for (int c = threadIdx.x; c < kn * GG_MOMENTS; c += kThreads) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) acc += warpsum[w][c];
+    out[c] = acc;
+  }
+}
+
+// ================================================================================ forward, quads
+// NHWC maps, K = 4 * KQ with KQ a power of two <= 32.  Thread = (pixel, 4 Gaussians).
+template <bool WITH_MASK>
+__global__ void __launch_bounds__(kThreads) splat_fwd_quad_kernel(const __grid_constant__ SplatArgs a,
+                                                                  int kq_shift) {
+  const int b = blockIdx.x / a.T;
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+  const int KQ = 1 << kq_shift;
+  const int kq = threadIdx.x & (KQ - 1);
+
+  float mux[4], muy[4], nA[4], nr[4], nE[4];
+  {
+    const float4 *gp = reinterpret_cast<const float4 *>(a.params + ((size_t)b * K + 4 * kq) * GG_PARAM_STRIDE);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 lo = __ldg(gp + 2 * i), hi = __ldg(gp + 2 * i + 1);
+      mux[i] = lo.x; muy[i] = lo.y; nA[i] = lo.z; nr[i] = lo.w; nE[i] = hi.x;
+    }
+  }
+  const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+  const int row_end = min(n, row_begin + s.rows_per_tile);
+  const int quads_per_row = n << kq_shift;
+
+  for (int row = row_begin; row < row_end; ++row) {
+    const float y = grid_coord(row, s.step);
+    float sh[4], e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float dy = y - muy[i];
+      sh[i] = fmaf(nr[i], dy, mux[i]);
+      e[i] = (nE[i] * dy) * dy;
+    }
+    float *mrow = s.maps + ((size_t)b * n + row) * n * K;
+    for (int q0 = 0; q0 < quads_per_row; q0 += kThreads) {
+      const int qq = q0 + threadIdx.x;
+      const bool active = qq < quads_per_row;
+      const int col = min(qq >> kq_shift, n - 1);
+      const float x = grid_coord(col, s.step);
+      float g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float t = x - sh[i];
+        g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+      }
+      if (active) st_f4(mrow + (size_t)qq * 4, g[0], g[1], g[2], g[3]);
+      if (WITH_MASK) {
+        float sum = (g[0] + g[1]) + (g[2] + g[3]);
+        for (int off = 1; off < KQ; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (active && kq == 0 && s.mask) s.mask[((size_t)b * n + row) * n + col] = sum;
+      }
+    }
+  }
+}
+
+// =============================================================================== backward, quads
+template <bool WITH_GMASK>
+__global__ void __launch_bounds__(kThreads) splat_bwd_quad_kernel(const __grid_constant__ SplatArgs a,
+                                                                  int kq_shift) {
+  __shared__ float wsum[kWarps][32 * 4 * GG_MOMENTS];   // [warp][kq][i][moment], K*5 <= 640 floats used
+
+  const int b = blockIdx.x / a.T;
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+  const int KQ = 1 << kq_shift;
+  const int kq = threadIdx.x & (KQ - 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  float mux[4], muy[4], nA[4], nr[4], nE[4];
+  {
+    const float4 *gp = reinterpret_cast<const float4 *>(a.params + ((size_t)b * K + 4 * kq) * GG_PARAM_STRIDE);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 lo = __ldg(gp + 2 * i), hi = __ldg(gp + 2 * i + 1);
+      mux[i] = lo.x; muy[i] = lo.y; nA[i] = lo.z; nr[i] = lo.w; nE[i] = hi.x;
+    }
+  }
+  const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+  const int row_end = min(n, row_begin + s.rows_per_tile);
+  const int quads_per_row = n << kq_shift;
+
+  float T[4][GG_MOMENTS];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < GG_MOMENTS; ++j) T[i][j] = 0.f;
+
+  for (int row = row_begin; row < row_end; ++row) {
+    const float y = grid_coord(row, s.step);
+    float dy[4], sh[4], e[4], S0[4], S1[4], S2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dy[i] = y - muy[i];
+      sh[i] = fmaf(nr[i], dy[i], mux[i]);
+      e[i] = (nE[i] * dy[i]) * dy[i];
+      S0[i] = S1[i] = S2[i] = 0.f;
+    }
+    const float *grow = s.maps + ((size_t)b * n + row) * n * K;
+    const bool use_gmask = WITH_GMASK && s.mask != nullptr;
+    const float *mrow = use_gmask ? s.mask + ((size_t)b * n + row) * n : nullptr;
+    for (int qq = threadIdx.x; qq < quads_per_row; qq += kThreads) {
+      const int col = qq >> kq_shift;
+      const float x = grid_coord(col, s.step);
+      float4 G = __ldg(reinterpret_cast<const float4 *>(grow + (size_t)qq * 4));
+      if (use_gmask) {
+        const float gmv = __ldg(mrow + col);
+        G.x += gmv; G.y += gmv; G.z += gmv; G.w += gmv;
+      }
+      const float Gv[4] = {G.x, G.y, G.z, G.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float t = x - sh[i];
+        const float w = ex2_approx(fmaf(nA[i] * t, t, e[i])) * Gv[i];
+        const float wt = w * t;
+        S0[i] += w;
+        S1[i] += wt;
+        S2[i] = fmaf(wt, t, S2[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      T[i][0] += S2[i];
+      T[i][3] += S1[i];
+      T[i][1] = fmaf(dy[i], S1[i], T[i][1]);
+      const float d0 = dy[i] * S0[i];
+      T[i][4] += d0;
+      T[i][2] = fmaf(dy[i], d0, T[i][2]);
+    }
+  }
+  // lanes that share kq (stride KQ) -> butterfly; then lanes 0..KQ-1 hold the warp totals
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < GG_MOMENTS; ++j) {
+      float v = T[i][j];
+      for (int off = KQ; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane < KQ) wsum[warp][(4 * kq + i) * GG_MOMENTS + j] = v;
+    }
+  __syncthreads();
+  float *out = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K) * GG_MOMENTS;
+  for (int c = threadIdx.x; c < K * GG_MOMENTS; c += kThreads) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) acc += wsum[w][c];
+    out[c] = acc;
+  }
+}
+
+// ====================================================================================== planning
+namespace {
+
+int env_int(const char *name, int dflt) {
+  const char *v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+void strip_geometry(ScaleDesc &d, int n, int rpt) {
+  d.n = n;
+  d.spr = (n + kStrip - 1) / kStrip;
+  d.sprc = d.spr < kThreads ? d.spr : kThreads;
+  d.rpp = d.spr <= kThreads ? kThreads / d.spr : 1;
+  d.chunks = (d.spr + kThreads - 1) / kThreads;
+  d.rows_per_tile = d.rpp * rpt;
+  d.tiles = ((n + d.rows_per_tile - 1) / d.rows_per_tile) * d.chunks;
+  d.step = n > 1 ? (1.0f - (-1.0f)) / (float)(n - 1) : 0.0f;
+}
+
+void quad_geometry(ScaleDesc &d, int n, int KQ, int passes) {
+  d.n = n;
+  d.spr = d.sprc = d.rpp = d.chunks = 0;
+  int per_row = (n * KQ + kThreads - 1) / kThreads;       // passes a CTA needs for one row
+  d.rows_per_tile = passes / per_row > 0 ? passes / per_row : 1;
+  if (d.rows_per_tile > n) d.rows_per_tile = n;
+  d.tiles = (n + d.rows_per_tile - 1) / d.rows_per_tile;
+  d.step = n > 1 ? (1.0f - (-1.0f)) / (float)(n - 1) : 0.0f;
+}
+
+bool quad_ok(int K, int *shift) {
+  if (K < 4 || (K & 3)) return false;
+  int KQ = K >> 2;
+  if (KQ & (KQ - 1)) return false;
+  if (KQ > 32) return false;
+  int sft = 0;
+  while ((1 << sft) < KQ) ++sft;
+  *shift = sft;
+  return true;
+}
+
+}  // namespace
+
+int fwd_rpt() { static int v = env_int("GG_RPT_FWD", 2); return v; }
+int bwd_rpt() { static int v = env_int("GG_RPT_BWD", 2); return v; }
+int quad_passes(bool backward) {
+  static int f = env_int("GG_QUAD_PASSES", 16), b = env_int("GG_QUAD_PASSES_BWD", 32);
+  return backward ? b : f;
+}
+
+// A launch plan: which scales go to which kernel family, with tile numbering.
+struct Plan {
+  SplatArgs strip_mask;    // scales with only a mask (or gmask)
+  SplatArgs maps;          // scales with maps (quad or strip kernel), mask fused
+  bool maps_quad;
+  int kq_shift;
+  bool maps_any_mask;
+  int tiles_mask, tiles_maps;
+};
+
+static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool *has_maps, const bool *has_mask,
+                      int layout, bool backward) {
+  pl = Plan();
+  pl.kq_shift = 0;
+  pl.maps_quad = (layout == GG_LAYOUT_NHWC) && quad_ok(K, &pl.kq_shift);
+  int rpt = backward ? bwd_rpt() : fwd_rpt();
+  int tb_mask = 0, tb_maps = 0;
+  for (int i = 0; i < nscales; ++i) {
+    if (has_maps[i]) {
+      ScaleDesc &d = pl.maps.sc[pl.maps.nscales++];
+      if (pl.maps_quad) quad_geometry(d, sizes[i], K >> 2, quad_passes(backward));
+      else strip_geometry(d, sizes[i], rpt);
+      d.tile_begin = tb_maps;
+      tb_maps += d.tiles;
+      if (has_mask[i]) pl.maps_any_mask = true;
+    } else if (has_mask[i]) {
+      ScaleDesc &d = pl.strip_mask.sc[pl.strip_mask.nscales++];
+      strip_geometry(d, sizes[i], rpt);
+      d.tile_begin = tb_mask;
+      tb_mask += d.tiles;
+    }
+  }
+  pl.tiles_mask = tb_mask;
+  pl.tiles_maps = tb_maps;
+  return true;
+}
+
+int plan_bwd_tiles(int K, int nscales, const int *sizes, const int *has_gmaps, const int *has_gmasks, int layout) {
+  Plan pl;
+  bool hm[GG_MAX_SCALES], hk[GG_MAX_SCALES];
+  for (int i = 0; i < nscales; ++i) { hm[i] = has_gmaps && has_gmaps[i]; hk[i] = has_gmasks && has_gmasks[i]; }
+  make_plan(pl, K, nscales, sizes, hm, hk, layout, true);
+  return pl.tiles_mask + pl.tiles_maps;
+}
+
+template <int RPT>
+static cudaError_t launch_fwd_strip(const SplatArgs &a, int out_mode, int B, cudaStream_t st) {
+  dim3 grid((unsigned)((size_t)B * a.T));
+  size_t smem = (size_t)a.K * GG_PARAM_STRIDE * sizeof(float);
+  switch (out_mode) {
+    case 0: splat_fwd_strip_kernel<RPT, 0><<<grid, kThreads, smem, st>>>(a); break;
+    case 1: splat_fwd_strip_kernel<RPT, 1><<<grid, kThreads, smem, st>>>(a); break;
+    default: splat_fwd_strip_kernel<RPT, 2><<<grid, kThreads, smem, st>>>(a); break;
+  }
+  return cudaGetLastError();
+}
+
+template <int RPT>
+static cudaError_t launch_bwd_strip(const SplatArgs &a, int gin_mode, int B, cudaStream_t st) {
+  dim3 grid((unsigned)((size_t)B * a.T), (unsigned)((a.K + kKBlock - 1) / kKBlock));
+  switch (gin_mode) {
+    case 0: splat_bwd_strip_kernel<RPT, 0><<<grid, kThreads, 0, st>>>(a); break;
+    case 1: splat_bwd_strip_kernel<RPT, 1><<<grid, kThreads, 0, st>>>(a); break;
+    default: splat_bwd_strip_kernel<RPT, 2><<<grid, kThreads, 0, st>>>(a); break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, const int *sizes, float *const *maps,
+                             float *const *masks, int layout, cudaStream_t st) {
+  bool hm[GG_MAX_SCALES], hk[GG_MAX_SCALES];
+  for (int i = 0; i < nscales; ++i) { hm[i] = maps && maps[i]; hk[i] = masks && masks[i]; }
+  Plan pl;
+  make_plan(pl, K, nscales, sizes, hm, hk, layout, false);
+  int im = 0, ik = 0;
+  for (int i = 0; i < nscales; ++i) {
+    if (hm[i]) { pl.maps.sc[im].maps = maps[i]; pl.maps.sc[im].mask = hk[i] ? masks[i] : nullptr; ++im; }
+    else if (hk[i]) { pl.strip_mask.sc[ik].maps = nullptr; pl.strip_mask.sc[ik].mask = masks[i]; ++ik; }
+  }
+  cudaError_t err = cudaSuccess;
+  const int rpt = fwd_rpt();
+  if (pl.strip_mask.nscales) {
+    SplatArgs &a = pl.strip_mask;
+    a.params = params; a.B = B; a.K = K; a.T = pl.tiles_mask; a.layout = layout;
+    err = rpt == 1 ? launch_fwd_strip<1>(a, 0, B, st) : rpt == 4 ? launch_fwd_strip<4>(a, 0, B, st)
+                                                                   : launch_fwd_strip<2>(a, 0, B, st);
+    if (err != cudaSuccess) return err;
+  }
+  if (pl.maps.nscales) {
+    SplatArgs &a = pl.maps;
+    a.params = params; a.B = B; a.K = K; a.T = pl.tiles_maps; a.layout = layout;
+    if (pl.maps_quad) {
+      dim3 grid((unsigned)((size_t)B * a.T));
+      if (pl.maps_any_mask) splat_fwd_quad_kernel<true><<<grid, kThreads, 0, st>>>(a, pl.kq_shift);
+      else splat_fwd_quad_kernel<false><<<grid, kThreads, 0, st>>>(a, pl.kq_shift);
+      err = cudaGetLastError();
+    } else {
+      int mode = layout == GG_LAYOUT_NCHW ? 1 : 2;
+      err = rpt == 1 ? launch_fwd_strip<1>(a, mode, B, st) : rpt == 4 ? launch_fwd_strip<4>(a, mode, B, st)
+                                                                       : launch_fwd_strip<2>(a, mode, B, st);
+    }
+  }
+  return err;
+}
+
+cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes,
+                             const float *const *gmaps, const float *const *gmasks, int layout, float *partials,
+                             int T, cudaStream_t st) {
+  bool hm[GG_MAX_SCALES], hk[GG_MAX_SCALES];
+  for (int i = 0; i < nscales; ++i) { hm[i] = gmaps && gmaps[i]; hk[i] = gmasks && gmasks[i]; }
+  Plan pl;
+  make_plan(pl, K, nscales, sizes, hm, hk, layout, true);
+  if (pl.tiles_mask + pl.tiles_maps != T) return cudaErrorInvalidValue;
+  int im = 0, ik = 0;
+  for (int i = 0; i < nscales; ++i) {
+    if (hm[i]) {
+      pl.maps.sc[im].maps = const_cast<float *>(gmaps[i]);
+      pl.maps.sc[im].mask = hk[i] ? const_cast<float *>(gmasks[i]) : nullptr;
+      ++im;
+    } else if (hk[i]) {
+      pl.strip_mask.sc[ik].maps = nullptr;
+      pl.strip_mask.sc[ik].mask = const_cast<float *>(gmasks[i]);
+      ++ik;
+    }
+  }
+  cudaError_t err = cudaSuccess;
+  const int rpt = bwd_rpt();
+  // SplatArgs.T is the tile count of THIS launch (splits blockIdx.x); SplatArgs.slots is the total
+  // number of partial slots per batch element (the partials stride).
+  if (pl.strip_mask.nscales) {
+    SplatArgs &a = pl.strip_mask;
+    a.params = params; a.partials = partials; a.B = B; a.K = K; a.T = pl.tiles_mask; a.slots = T; a.tile_offset = 0;
+    a.layout = layout;
+    err = rpt == 1 ? launch_bwd_strip<1>(a, 0, B, st) : rpt == 4 ? launch_bwd_strip<4>(a, 0, B, st)
+                                                                   : launch_bwd_strip<2>(a, 0, B, st);
+    if (err != cudaSuccess) return err;
+  }
+  if (pl.maps.nscales) {
+    SplatArgs &a = pl.maps;
+    a.params = params; a.partials = partials; a.B = B; a.K = K; a.T = pl.tiles_maps; a.slots = T;
+    a.tile_offset = pl.tiles_mask; a.layout = layout;
+    if (pl.maps_quad) {
+      dim3 grid((unsigned)((size_t)B * a.T));
+      // the quad kernel adds gmask to every channel only when a scale carries one; scales without a
+      // gmask are handled by giving the kernel a per-scale NULL check
+      if (pl.maps_any_mask) splat_bwd_quad_kernel<true><<<grid, kThreads, 0, st>>>(a, pl.kq_shift);
+      else splat_bwd_quad_kernel<false><<<grid, kThreads, 0, st>>>(a, pl.kq_shift);
+      err = cudaGetLastError();
+    } else {
+      int mode = layout == GG_LAYOUT_NCHW ? 1 : 2;
+      err = rpt == 1 ? launch_bwd_strip<1>(a, mode, B, st) : rpt == 4 ? launch_bwd_strip<4>(a, mode, B, st)
+                                                                       : launch_bwd_strip<2>(a, mode, B, st);
+    }
+  }
+  return err;
+}
+
+}  // namespace gg

@@ -1,0 +1,119 @@
+/*
+ * gaussigan.h -- C ABI of libgaussigan_sm100.so: the B200-native (sm_100a) drop-in for
+ * GaussiGAN's differentiable splat-to-silhouette renderer.
+ *
+ * The reference has no FFI: the path is two plain Python functions evaluated at TF
+ * graph-construction time.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference repository root):
+ *
+ *   get_landmarks(mus, sigma, rotx, roty, rotz, tx, ty, tz, focal)
+ *                                   mask/mask_gen_dynamic.py:233-323  (5 more copies)
+ *   get_gaussian_maps_2d(mu, sigma, shape_hw)
+ *                                   mask/mask_gen_dynamic.py:112-143, mask/infer_masks.py:345-373
+ *   sum composite / L1 consumers    mask/mask_gen_dynamic.py:785-791
+ *   their backward                  implicit tf.gradients, mask/GAN.py:113-119
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - the caller owns all memory; the library never allocates or frees device memory;
+ *   - every launch entry takes the CUDA device ordinal and a cudaStream_t (as void*); calls are
+ *     asynchronous on that stream, stateless and re-entrant; no implicit synchronisation;
+ *   - return value: 0 = ok, < 0 = error (GG_E_*); gg_last_error() gives a thread-local message;
+ *     nothing throws across the ABI;
+ *   - layouts: mus [B,K,3] f32; sigma [B,K,3,3] f32 or f64 (row-major); rot* [B] f32 DEGREES;
+ *     mu2d [B,K,2] (x = image column, y = row); sigma2d [B,K,2,2]; maps NHWC [B,n,n,K] or
+ *     NCHW [B,K,n,n] f32; mask [B,n,n] f32; pixel centres = float32 linspace(-1,1,n).
+ */
+#ifndef GAUSSIGAN_H_
+#define GAUSSIGAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GG_API __attribute__((visibility("default")))
+#else
+#define GG_API
+#endif
+
+#define GG_VERSION 100            /* 0.1.0 */
+#define GG_PARAM_STRIDE 8         /* floats per projected Gaussian in the staged `params` buffer */
+#define GG_MOMENTS 5              /* gradient accumulators per Gaussian */
+#define GG_MAX_SCALES 4           /* the reference's pyramid: 32, 64, 128, 256 (mask_gen_dynamic.py:315-316) */
+
+#define GG_LAYOUT_NHWC 0          /* the reference's layout, [B,n,n,K] (mask_gen_dynamic.py:141) */
+#define GG_LAYOUT_NCHW 1          /* [B,K,n,n], for PyTorch consumers */
+
+#define GG_OK 0
+#define GG_E_NULL -1              /* required pointer is NULL */
+#define GG_E_SHAPE -2             /* B/K/n out of range, bad scale count or layout */
+#define GG_E_ALIGN -3             /* pointer not aligned for vector access */
+#define GG_E_CUDA -4              /* CUDA runtime error (message in gg_last_error) */
+#define GG_E_WORKSPACE -5         /* partials buffer too small / inconsistent tile count */
+
+GG_API int gg_version(void);
+/* thread-local description of the last error returned on this thread ("" if none) */
+GG_API const char *gg_last_error(void);
+
+/* ---- projection: 3-D Gaussians + camera -> image ellipses -------------------------------------
+ * Replaces the body of get_landmarks up to the `mu2d` / `sigma2d` identities
+ * (mask/mask_gen_dynamic.py:240-314): float32 trig and R = RX RY RZ, then everything in float64.
+ * Outputs (each may be NULL except params): mu2d, sigma2d as float64 (the tensors the frozen decoder
+ * graph is fed, mask/infer_masks.py:394-395) and `params`, the float32 staging buffer
+ * [B,K,GG_PARAM_STRIDE] the splat kernels read. */
+GG_API int gg_project_fwd(const float *mus, const void *sigma, int sigma_is_f64,
+                   const float *rotx, const float *roty, const float *rotz,
+                   double tx, double ty, double tz, double focal, int B, int K,
+                   double *mu2d, double *sigma2d, float *params, int device, void *stream);
+
+/* Backward of gg_project_fwd.  `partials` [B,T,K,GG_MOMENTS] come from gg_splat_bwd (may be NULL
+ * when T == 0); gmu2d / gsigma2d (float64, may be NULL) are upstream gradients w.r.t. the mu2d /
+ * sigma2d outputs themselves.  Outputs: dmus [B,K,3] f32, dsigma [B,K,3,3] f64 (the raw, generally
+ * non-symmetric gradient the reference's autodiff yields), drot [B,3] f32 (d/d rotx,roty,rotz, per
+ * degree).  The forward is recomputed in registers; nothing is saved between passes. */
+GG_API int gg_project_bwd(const float *mus, const void *sigma, int sigma_is_f64,
+                   const float *rotx, const float *roty, const float *rotz,
+                   double tx, double ty, double tz, double focal, int B, int K,
+                   const float *partials, int T, const double *gmu2d, const double *gsigma2d,
+                   float *dmus, double *dsigma, float *drot, int device, void *stream);
+
+/* ---- conic staging for callers that already hold mu2d / sigma2d -------------------------------
+ * Replaces `invsigma = tf.linalg.inv(sigma)` of get_gaussian_maps_2d (mask/mask_gen_dynamic.py:131):
+ * mu2d [B,K,2], sigma2d [B,K,2,2] (both f32 or both f64) -> params. */
+GG_API int gg_conic_fwd(const void *mu2d, const void *sigma2d, int is_f64, int B, int K, float *params,
+                 int device, void *stream);
+/* partials -> dmu2d [B,K,2], dsigma2d [B,K,2,2] (float64). */
+GG_API int gg_conic_bwd(const void *mu2d, const void *sigma2d, int is_f64, int B, int K,
+                 const float *partials, int T, double *dmu2d, double *dsigma2d,
+                 int device, void *stream);
+
+/* ---- splat: evaluate every Gaussian at every pixel --------------------------------------------
+ * Replaces get_gaussian_maps_2d's raster (mask/mask_gen_dynamic.py:121-141), the float32 cast
+ * (:318), the 4-scale loop (:315-319) and, when `masks` is given, the unclamped sum over K
+ * (:785-786).  sizes_host[nscales] (host array, 1..GG_MAX_SCALES entries, H == W == n);
+ * maps_host[i] / masks_host[i] are host arrays of device pointers (entry or whole array may be
+ * NULL): maps [B,n,n,K] (NHWC) or [B,K,n,n] (NCHW) f32, mask [B,n,n] f32 = sum_k maps. */
+GG_API int gg_splat_fwd(const float *params, int B, int K, int nscales, const int *sizes_host,
+                 float *const *maps_host, float *const *masks_host, int layout,
+                 int device, void *stream);
+
+/* Number of [K,GG_MOMENTS] partial blocks per batch element that gg_splat_bwd writes for this
+ * configuration (T); < 0 on error.  has_gmaps_host / has_gmasks_host: per-scale 0/1 flags. */
+GG_API int gg_splat_bwd_tiles(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,
+                       const int *has_gmasks_host, int layout);
+
+/* Backward of the raster: upstream gradients w.r.t. maps and/or masks -> per-tile partial moments
+ * partials [B,T,K,GG_MOMENTS] (every slot is written; no zero-fill needed; deterministic -- no
+ * atomics).  T must equal gg_splat_bwd_tiles(...) for the same arguments. */
+GG_API int gg_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes_host,
+                 const float *const *gmaps_host, const float *const *gmasks_host, int layout,
+                 float *partials, int T, int device, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAUSSIGAN_H_ */

@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- silhouettes/sec, forward+backward, 256x256, K=16 (BASELINE.json metric; config[1]: batch 64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                        # the reference algorithm on host CPU cores
+    torchrun --nproc-per-node N bench.py --gpus N ...             # one rank per GPU, batch-sharded (weak scaling)
+
+One "step" = one pass of the hot path over one batch: projection -> splat (sum-composited silhouette,
+[B,256,256]) -> backward from an upstream gradient dL/dmask -> gradients into mus, Sigma and the camera
+angles (mask/mask_gen_dynamic.py:233-323, 785-786 and their tf.gradients).
+
+Numbers on the JSON line
+  value     whole-job silhouettes/s with inputs resident in HBM; each step is one CUDA-graph replay of the
+            4 kernels; R rotating buffer sets (> L2) so no step re-reads what the previous one left in L2.
+  e2e       same metric through the public host-buffer call (gaussigan_b200.host.HostSilhouetteStep):
+            pinned-host inputs copied H2D and loss+gradients copied D2H inside the timed region, every step.
+  roofline  dominant kernel (backward splat): algorithmic issue slots / measured duration vs the FP32 issue
+            peak; plus the HBM view of the same launch.  SURVEY.md 8d defines the algorithmic counts.
+  cpu_baseline  the oracle (float64 torch restatement of the reference) timed on this box's host cores on a
+            bounded sample.  A reported baseline only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "silhouettes/sec fwd+bwd at 256x256 K=16"
+UNIT = "silhouettes/s"
+B_PER_GPU, K_GAUSS, SIZE = 64, 16, 256
+# algorithmic work per (pixel, Gaussian) -- SURVEY.md 8d / BASELINE.md 3
+SLOTS_FWD, SLOTS_BWD = 9, 17
+SM_COUNT, FP32_LANES = 148, 128
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), sm_max_mhz=float(p.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return None
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if (t0 is None or t0 <= t <= t1)] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(self.NAMES, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_rate(budget_s: float, sample_B: int, min_iters: int = 2):
+    """fwd+bwd silhouettes/s of the oracle on ``sample_B`` batch elements of the C2 workload, all host threads."""
+    import torch
+    from oracle import reference_port as rp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = rp.synth_inputs(sample_B, K_GAUSS, seed=56)
+    tgt = rp.synth_target_masks(sample_B, SIZE)
+    rp.render_loss_and_grads(inp, tgt, SIZE)                       # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < min_iters or time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        rp.render_loss_and_grads(inp, tgt, SIZE)
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 50:
+            break
+    best = min(times)
+    return dict(value=sample_B / best, unit=UNIT, cores=cores, kind="port",
+                sample=f"{sample_B} of {B_PER_GPU} silhouettes of the C2 batch (K={K_GAUSS}, {SIZE}x{SIZE}, fwd+bwd, "
+                       f"float64 torch-CPU restatement of the reference), best of {len(times)} passes")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import reference_port as rp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_B = 16
+    inp = rp.synth_inputs(sample_B, K_GAUSS, seed=56)
+    tgt = rp.synth_target_masks(sample_B, SIZE)
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        rp.render_loss_and_grads(inp, tgt, SIZE)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rp.render_loss_and_grads(inp, tgt, SIZE)
+    dt = (time.perf_counter() - t0) / steps
+    val = sample_B / dt
+    sample = (f"each step = {sample_B} of {B_PER_GPU} silhouettes of the C2 batch, fwd+bwd, float64 torch-CPU "
+              f"restatement of mask/mask_gen_dynamic.py:112-143,233-323,785-787 (TensorFlow 1.12 is not installable)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"mask renderer fwd+bwd, batch {B_PER_GPU}, K={K_GAUSS}, {SIZE}x{SIZE} (BASELINE configs[1])",
+                   "sample_batch": sample_B},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from gaussigan_b200.plan import SilhouetteStep
+    from gaussigan_b200.host import HostSilhouetteStep
+    from oracle import reference_port as rp       # synthetic-input generator + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, n = B_PER_GPU, K_GAUSS, SIZE
+    peaks = _peaks()
+
+    # ---- synthetic inputs of the reference's activation ranges, R rotating sets (inputs > L2)
+    R = args.rotate
+    sets = []
+    for r in range(R):
+        inp = rp.synth_inputs(B, K, seed=56 + 1000 * rank + r)
+        tgt = rp.synth_target_masks(B, n, seed=57 + 1000 * rank + r)
+        step = SilhouetteStep(B, K, n, dev)
+        mus = inp["mus"].reshape(B, K, 3).contiguous().to(dev)
+        sig = inp["sigma"].contiguous().to(dev)
+        rx, ry, rz = (inp[k].reshape(B).contiguous().to(dev) for k in ("rotx", "roty", "rotz"))
+        step.bind(mus, sig, rx, ry, rz)
+        # upstream gradient of mean|0.5*(t+1) - m| w.r.t. m for a random-sign residual
+        gm = (-(torch.sign(torch.randn(B, n, n, device=dev))) / float(B * n * n)).contiguous()
+        step.capture(gm)
+        sets.append((step, gm, inp, tgt))
+    rot_bytes = R * 2 * B * n * n * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- timed region: W warm-up steps, then exactly K steps, device-timed, max over ranks
+    for i in range(max(3, args.warmup)):
+        sets[i % R][0].graph.replay()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        sets[i % R][0].graph.replay()
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel (backward splat) alone, same rotating buffers, CUDA events on the launch stream
+    from gaussigan_b200._lib import lib, check, ptr_array, LAYOUT_NHWC
+    st = torch.cuda.current_stream(dev).cuda_stream
+    gps = [ptr_array([s[1].data_ptr()]) for s in sets]
+
+    def bwd_only(i):
+        s = sets[i % R][0]
+        check(lib.gg_splat_bwd(s.params.data_ptr(), B, K, 1, s._sizes, s._null_ptrs, gps[i % R], LAYOUT_NHWC,
+                               s.partials.data_ptr(), s.T, dev.index, st), "gg_splat_bwd")
+
+    def fwd_only(i):
+        s = sets[i % R][0]
+        check(lib.gg_splat_fwd(s.params.data_ptr(), B, K, 1, s._sizes, s._null_ptrs, s._mask_ptrs, LAYOUT_NHWC,
+                               dev.index, st), "gg_splat_fwd")
+
+    def kernel_us(fn, reps):
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps * 1e3
+
+    reps = max(20, min(args.steps, 200))
+    us_bwd = kernel_us(bwd_only, reps)
+    us_fwd = kernel_us(fwd_only, reps)
+    pxk = B * n * n * K
+    issue_peak = SM_COUNT * FP32_LANES * peaks["sm_max_mhz"] * 1e6              # lane issue slots / s
+    ach = SLOTS_BWD * pxk / (us_bwd * 1e-6)
+    bytes_bwd = B * n * n * 4 + B * K * 32 + sets[0][0].partials.numel() * 4     # gmask in, params in, partials out
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("splat_bwd_mask_dram_bytes_per_launch")
+    roofline = {
+        "kernel": "gg::splat_bwd_strip_kernel (mask gradient -> per-Gaussian moments)", "bound": "fp32_issue",
+        "achieved": ach / 1e12, "peak": issue_peak / 1e12, "unit": "T lane-slots/s (17 algorithmic issue slots per pixel-Gaussian)",
+        "frac": ach / issue_peak, "traffic": traffic, "us_per_launch": us_bwd,
+        "peak_source": f"148 SMs x 128 FP32 lanes x sm_max_mhz ({peaks['source']} MEASURED_PEAKS.json); no tensor cores: not a contraction",
+        "hbm": {"achieved": bytes_bwd / (us_bwd * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": bytes_bwd / (us_bwd * 1e-6) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": bytes_bwd,
+                "peak_source": peaks["source"]},
+        "forward_kernel": {"us_per_launch": us_fwd, "frac": SLOTS_FWD * pxk / (us_fwd * 1e-6) / issue_peak},
+        "step": {"frac": (SLOTS_FWD + SLOTS_BWD) * pxk * (value / world / B) / issue_peak,
+                 "note": "whole fwd+bwd step (4 kernels) against the 26-slot algorithmic count"},
+    }
+
+    # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
+    e2e = None
+    try:
+        host = HostSilhouetteStep(B, K, n, dev, depth=2)
+        hsets = [host.make_host_inputs(s[2], s[3]) for s in sets[:min(R, 4)]]
+        for i in range(3):
+            host.submit(hsets[i % len(hsets)])
+        host.drain()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            host.submit(hsets[i % len(hsets)])
+        host.drain()
+        b.record()
+        barrier()
+        ems = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ems], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": world * B / (ems / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
+               "ms_per_step": ems / args.steps, "api": "gaussigan_b200.host.HostSilhouetteStep.submit (pinned host buffers)",
+               "launches_per_step": host.LAUNCHES_PER_STEP}
+    except Exception as exc:                      # pragma: no cover - reported, never hidden
+        e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
+
+    if rank == 0:
+        cpu = cpu_oracle_rate(args.cpu_budget, 16) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"mask renderer fwd+bwd, batch {B} per GPU, K={K}, {n}x{n} (BASELINE configs[1]); "
+                                   "projection in float64, splat in float32",
+                       "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2": f"{R} rotating input/output sets = {rot_bytes / 1e6:.0f} MB > 126 MB L2",
+                       "step": "one CUDA-graph replay: project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd"},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": args.steps * SilhouetteStep.LAUNCHES_PER_STEP,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="gaussigan_b200", choices=["gaussigan_b200", "reference"])
+    ap.add_argument("--rotate", type=int, default=8, help="rotating buffer sets (inputs larger than L2)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and args.impl != "reference":
+        if args.gpus > 1:
+            # convenience: re-launch under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -26,7 +26,7 @@ def _load() -> C.CDLL:
     path = Path(os.environ.get("GAUSSIGAN_LIB", _LIB_PATH))
     if not path.exists():
         raise ImportError(
-            f"{path} not found: build it with `python -m gaussigan_b200.build` "
+            f"{path} not found: build it with `python gaussigan_b200/build.py` "
             "(nvcc, sm_100a). gaussigan_b200 has no CPU or PyTorch fallback.")
     return C.CDLL(str(path))
 
@@ -48,6 +48,10 @@ SIGNATURES = {
     "gg_conic_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "gg_splat_fwd": (_i, [_vp, _i, _i, _i, _ip, _pp, _pp, _i, _i, _vp]),
     "gg_splat_bwd_tiles": (_i, [_i, _i, _ip, _ip, _ip, _i]),
+    "gg_mask_l1_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "gg_silhouette_step_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "gg_silhouette_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _i, _i, _i,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _vp]),
     "gg_splat_bwd": (_i, [_vp, _i, _i, _i, _ip, _pp, _pp, _i, _vp, _i, _i, _vp]),
 }
 

@@ -1,6 +1,7 @@
 """Build libgaussigan_sm100.so in-tree with nvcc for sm_100a (B200).
 
-``python -m gaussigan_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles without a
+``python gaussigan_b200/build.py [-v] [--force]`` or ``__graft_entry__.build()`` (run the file, not
+``-m``: importing the package loads the library it is about to build).  nvcc cross-compiles without a
 GPU.  The library lands in ``gaussigan_b200/lib/`` (git-ignored, shipped to the GPU box by gpurun).
 """
 from __future__ import annotations

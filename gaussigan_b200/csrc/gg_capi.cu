@@ -6,7 +6,8 @@
 #include "gg_common.cuh"
 #include "gg_launch.h"
 
-namespace {
+namespace gg {
+namespace api {
 
 thread_local char g_err[512] = "";
 
@@ -50,7 +51,10 @@ int check_scales(int K, int nscales, const int *sizes) {
   return GG_OK;
 }
 
-}  // namespace
+}  // namespace api
+}  // namespace gg
+
+using namespace gg::api;
 
 extern "C" {
 
@@ -130,6 +134,21 @@ int gg_splat_fwd(const float *params, int B, int K, int nscales, const int *size
   cudaError_t e = gg::launch_splat_fwd(params, B, K, nscales, sizes_host, maps_host, masks_host, layout,
                                        (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_splat_fwd");
+}
+
+int gg_mask_l1_loss_bwd(const float *mask, const void *target, int target_kind, int B, int n, float *gmask,
+                        float *loss_partials, int device, void *stream) {
+  if (B < 0 || n < 1) return fail(GG_E_SHAPE, "gg_mask_l1_loss_bwd: bad B=%d n=%d", B, n);
+  if (B == 0) return GG_OK;
+  if (((size_t)B * n * n) & 3) return fail(GG_E_SHAPE, "gg_mask_l1_loss_bwd: B*n*n must be a multiple of 4");
+  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32) return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
+  if (!mask || !target || !gmask || !loss_partials) return fail(GG_E_NULL, "gg_mask_l1_loss_bwd: NULL pointer");
+  if (!aligned16(mask) || !aligned16(gmask) || (reinterpret_cast<uintptr_t>(target) & 3))
+    return fail(GG_E_ALIGN, "gg_mask_l1_loss_bwd: mask/gmask need 16-byte, target 4-byte alignment");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_mask_l1_loss_bwd(mask, target, target_kind, B, n, gmask, loss_partials,
+                                              GG_LOSS_PARTIALS, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_mask_l1_loss_bwd");
 }
 
 int gg_splat_bwd_tiles(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,

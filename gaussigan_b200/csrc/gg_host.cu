@@ -1,0 +1,115 @@
+// gg_host.cu -- the host-buffer entry point: one call = H2D copies + the whole fwd/loss/bwd chain +
+// D2H copies, all asynchronous on the caller's stream.  This is the form a host-language binding of the
+// reference would use (the reference feeds numpy arrays through session.run, mask/infer_masks.py:435-456).
+#include <cstring>
+#include "gg_common.cuh"
+#include "gg_launch.h"
+
+namespace gg {
+
+struct StepLayout {
+  size_t mus, sigma, rot, target, params, mask, gmask, partials, loss, dmus, dsigma, drot, total;
+  int T;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+StepLayout step_layout(int B, int K, int n, int target_kind) {
+  StepLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  const int sizes[1] = {n}, zero[1] = {0}, one[1] = {1};
+  L.T = plan_bwd_tiles(K, 1, sizes, zero, one, GG_LAYOUT_NHWC);
+  L.mus = take((size_t)B * K * 3 * 4);
+  L.sigma = take((size_t)B * K * 9 * 8);
+  L.rot = take((size_t)B * 3 * 4);
+  L.target = take((size_t)B * n * n * (target_kind == 0 ? 1 : 4));
+  L.params = take((size_t)B * K * GG_PARAM_STRIDE * 4);
+  L.mask = take((size_t)B * n * n * 4);
+  L.gmask = take((size_t)B * n * n * 4);
+  L.partials = take((size_t)B * L.T * K * GG_MOMENTS * 4);
+  L.loss = take((size_t)GG_LOSS_PARTIALS * 4);
+  L.dmus = take((size_t)B * K * 3 * 4);
+  L.dsigma = take((size_t)B * K * 9 * 8);
+  L.drot = take((size_t)B * 3 * 4);
+  L.total = off;
+  return L;
+}
+
+}  // namespace gg
+
+using namespace gg::api;
+
+extern "C" {
+
+size_t gg_silhouette_step_workspace_bytes(int B, int K, int n, int target_kind) {
+  if (B <= 0 || K <= 0 || n < 1) return 0;
+  return gg::step_layout(B, K, n, target_kind).total;
+}
+
+int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, const float *rotx_host,
+                            const float *roty_host, const float *rotz_host, const void *target_host, int target_kind,
+                            double tx, double ty, double tz, double focal, int B, int K, int n,
+                            float *loss_partials_host, float *dmus_host, double *dsigma_host, float *drot_host,
+                            float *mask_host, void *workspace, size_t workspace_bytes, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  const int sizes[1] = {n};
+  if (int r = check_scales(K, 1, sizes)) return r;
+  if (B == 0) return GG_OK;
+  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32) return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
+  if (((size_t)B * n * n) & 3) return fail(GG_E_SHAPE, "gg_silhouette_step_host: B*n*n must be a multiple of 4");
+  if (!mus_host || !sigma_host || !rotx_host || !roty_host || !rotz_host || !target_host || !loss_partials_host ||
+      !dmus_host || !dsigma_host || !drot_host || !workspace)
+    return fail(GG_E_NULL, "gg_silhouette_step_host: NULL pointer");
+  const gg::StepLayout L = gg::step_layout(B, K, n, target_kind);
+  if (workspace_bytes < L.total)
+    return fail(GG_E_WORKSPACE, "gg_silhouette_step_host: workspace %zu < required %zu bytes", workspace_bytes, L.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(GG_E_ALIGN, "workspace must be 256-byte aligned");
+  if (int r = set_device(device)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  char *w = reinterpret_cast<char *>(workspace);
+  float *d_mus = reinterpret_cast<float *>(w + L.mus);
+  double *d_sigma = reinterpret_cast<double *>(w + L.sigma);
+  float *d_rot = reinterpret_cast<float *>(w + L.rot);
+  void *d_target = w + L.target;
+  float *d_params = reinterpret_cast<float *>(w + L.params);
+  float *d_mask = reinterpret_cast<float *>(w + L.mask);
+  float *d_gmask = reinterpret_cast<float *>(w + L.gmask);
+  float *d_part = reinterpret_cast<float *>(w + L.partials);
+  float *d_loss = reinterpret_cast<float *>(w + L.loss);
+  float *d_dmus = reinterpret_cast<float *>(w + L.dmus);
+  double *d_dsig = reinterpret_cast<double *>(w + L.dsigma);
+  float *d_drot = reinterpret_cast<float *>(w + L.drot);
+#define GG_TRY(call, what)                                  \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return cuda_fail(e__, what);    \
+  } while (0)
+  const size_t px = (size_t)B * n * n;
+  GG_TRY(cudaMemcpyAsync(d_mus, mus_host, (size_t)B * K * 3 * 4, cudaMemcpyHostToDevice, st), "H2D mus");
+  GG_TRY(cudaMemcpyAsync(d_sigma, sigma_host, (size_t)B * K * 9 * 8, cudaMemcpyHostToDevice, st), "H2D sigma");
+  GG_TRY(cudaMemcpyAsync(d_rot, rotx_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D rotx");
+  GG_TRY(cudaMemcpyAsync(d_rot + B, roty_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D roty");
+  GG_TRY(cudaMemcpyAsync(d_rot + 2 * (size_t)B, rotz_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D rotz");
+  GG_TRY(cudaMemcpyAsync(d_target, target_host, px * (target_kind == GG_TARGET_U8 ? 1 : 4), cudaMemcpyHostToDevice, st),
+         "H2D target");
+  GG_TRY(gg::launch_project_fwd(d_mus, d_sigma, 1, d_rot, d_rot + B, d_rot + 2 * (size_t)B, tx, ty, tz, focal, B, K,
+                                nullptr, nullptr, d_params, st), "project_fwd");
+  float *masks[1] = {d_mask};
+  GG_TRY(gg::launch_splat_fwd(d_params, B, K, 1, sizes, nullptr, masks, GG_LAYOUT_NHWC, st), "splat_fwd");
+  GG_TRY(gg::launch_mask_l1_loss_bwd(d_mask, d_target, target_kind, B, n, d_gmask, d_loss, GG_LOSS_PARTIALS, st),
+         "mask_l1_loss_bwd");
+  const float *gmasks[1] = {d_gmask};
+  GG_TRY(gg::launch_splat_bwd(d_params, B, K, 1, sizes, nullptr, gmasks, GG_LAYOUT_NHWC, d_part, L.T, st), "splat_bwd");
+  GG_TRY(gg::launch_project_bwd(d_mus, d_sigma, 1, d_rot, d_rot + B, d_rot + 2 * (size_t)B, tx, ty, tz, focal, B, K,
+                                d_part, L.T, nullptr, nullptr, d_dmus, d_dsig, d_drot, st), "project_bwd");
+  GG_TRY(cudaMemcpyAsync(loss_partials_host, d_loss, (size_t)GG_LOSS_PARTIALS * 4, cudaMemcpyDeviceToHost, st), "D2H loss");
+  GG_TRY(cudaMemcpyAsync(dmus_host, d_dmus, (size_t)B * K * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H dmus");
+  GG_TRY(cudaMemcpyAsync(dsigma_host, d_dsig, (size_t)B * K * 9 * 8, cudaMemcpyDeviceToHost, st), "D2H dsigma");
+  GG_TRY(cudaMemcpyAsync(drot_host, d_drot, (size_t)B * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H drot");
+  if (mask_host) GG_TRY(cudaMemcpyAsync(mask_host, d_mask, px * 4, cudaMemcpyDeviceToHost, st), "D2H mask");
+#undef GG_TRY
+  return GG_OK;
+}
+
+}  // extern "C"

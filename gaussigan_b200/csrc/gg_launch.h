@@ -22,4 +22,16 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
                              const float *const *gmaps, const float *const *gmasks, int layout, float *partials,
                              int T, cudaStream_t st);
 
+cudaError_t launch_mask_l1_loss_bwd(const float *mask, const void *target, int kind, int B, int n, float *gmask,
+                                    float *partials, int npartials, cudaStream_t st);
+
+namespace api {   // error/validation helpers shared by the extern "C" translation units (gg_capi.cu)
+int fail(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *where);
+bool aligned16(const void *p);
+int set_device(int device);
+int check_bk(int B, int K);
+int check_scales(int K, int nscales, const int *sizes);
+}  // namespace api
+
 }  // namespace gg

@@ -1,0 +1,133 @@
+"""Host-buffer front end: the training-style silhouette step for callers whose data lives in host memory.
+
+``HostSilhouetteStep.submit(inputs)`` is one ``gg_silhouette_step_host`` call (include/gaussigan.h): H2D of
+the Gaussians, camera and target mask, projection, splat, ``m_recon_loss_bis`` and its gradient
+(mask/mask_gen_dynamic.py:785-787), splat backward, projection backward, D2H of the loss partials and the
+gradients.  ``depth`` independent slots (device workspace + pinned result buffers + a CUDA stream each) are
+used round-robin, so the copies of step i+1 overlap the kernels of step i.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+
+GG_TARGET_U8, GG_TARGET_F32 = 0, 1
+GG_LOSS_PARTIALS = 296
+
+
+class HostInputs(NamedTuple):
+    """Pinned host tensors: mus [B,K,3] f32, sigma [B,K,3,3] f64, rot* [B] f32 (degrees), target [B,n,n] u8|f32."""
+    mus: torch.Tensor
+    sigma: torch.Tensor
+    rotx: torch.Tensor
+    roty: torch.Tensor
+    rotz: torch.Tensor
+    target: torch.Tensor
+
+
+class StepResult:
+    """Pinned host result buffers of one slot; valid after ``wait()``."""
+
+    def __init__(self, B, K, n, want_mask):
+        pin = dict(pin_memory=True)
+        self.loss_partials = torch.zeros(GG_LOSS_PARTIALS, dtype=torch.float32, **pin)
+        self.dmus = torch.zeros((B, K, 3), dtype=torch.float32, **pin)
+        self.dsigma = torch.zeros((B, K, 3, 3), dtype=torch.float64, **pin)
+        self.drot = torch.zeros((B, 3), dtype=torch.float32, **pin)
+        self.mask = torch.zeros((B, n, n), dtype=torch.float32, **pin) if want_mask else None
+        self.event: Optional[torch.cuda.Event] = None
+        self._npix = B * n * n
+
+    def wait(self) -> "StepResult":
+        if self.event is not None:
+            self.event.synchronize()
+        return self
+
+    @property
+    def loss(self) -> float:
+        """mean |0.5*(target+1) - mask| (float64 sum of the per-CTA partials)."""
+        self.wait()
+        return float(self.loss_partials.double().sum().item() / self._npix)
+
+
+class HostSilhouetteStep:
+    #: project_fwd, splat_fwd, mask_l1_loss_bwd, splat_bwd, project_bwd
+    LAUNCHES_PER_STEP = 5
+
+    def __init__(self, B: int, K: int, size: int = 256, device="cuda", depth: int = 2,
+                 tx: float = 0.0, ty: float = 0.0, tz: float = -2.0, focal: float = 1.0,
+                 target_dtype: torch.dtype = torch.uint8, want_mask: bool = False):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("gaussigan_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if target_dtype not in (torch.uint8, torch.float32):
+            raise ValueError("target_dtype must be uint8 (raw 0..255 mask) or float32 (mask in [-1,1])")
+        self.B, self.K, self.n, self.dev = int(B), int(K), int(size), dev
+        self.t = (float(tx), float(ty), float(tz))
+        self.focal = float(focal)
+        self.kind = GG_TARGET_U8 if target_dtype == torch.uint8 else GG_TARGET_F32
+        self.target_dtype = target_dtype
+        self.ws_bytes = int(lib.gg_silhouette_step_workspace_bytes(self.B, self.K, self.n, self.kind))
+        if self.ws_bytes <= 0:
+            raise ValueError("bad B/K/size")
+        self.depth = int(depth)
+        self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
+        self.streams = [torch.cuda.Stream(dev) for _ in range(self.depth)]
+        self.results = [StepResult(self.B, self.K, self.n, want_mask) for _ in range(self.depth)]
+        self._next = 0
+        tb = 1 if self.kind == GG_TARGET_U8 else 4
+        self.h2d_bytes = B * K * 3 * 4 + B * K * 9 * 8 + 3 * B * 4 + B * size * size * tb
+        self.d2h_bytes = (GG_LOSS_PARTIALS * 4 + B * K * 3 * 4 + B * K * 9 * 8 + B * 3 * 4
+                          + (B * size * size * 4 if want_mask else 0))
+
+    def make_host_inputs(self, inp: dict, target_pm1: torch.Tensor) -> HostInputs:
+        """Pack oracle-style inputs (mus [B,K,1,3], sigma, rot [B,1], target [B,n,n,1] in {-1,+1}) into pinned buffers."""
+        B, K, n = self.B, self.K, self.n
+        t = target_pm1.reshape(B, n, n)
+        if self.kind == GG_TARGET_U8:
+            t = ((t + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+        else:
+            t = t.float()
+        return HostInputs(inp["mus"].reshape(B, K, 3).float().contiguous().pin_memory(),
+                          inp["sigma"].double().contiguous().pin_memory(),
+                          inp["rotx"].reshape(B).float().contiguous().pin_memory(),
+                          inp["roty"].reshape(B).float().contiguous().pin_memory(),
+                          inp["rotz"].reshape(B).float().contiguous().pin_memory(),
+                          t.contiguous().pin_memory())
+
+    def submit(self, h: HostInputs) -> StepResult:
+        """Enqueue one whole step on the next slot; returns that slot's (asynchronously filled) result."""
+        B, K, n = self.B, self.K, self.n
+        assert h.mus.dtype == torch.float32 and h.mus.numel() == B * K * 3 and h.mus.is_contiguous()
+        assert h.sigma.dtype == torch.float64 and h.sigma.numel() == B * K * 9 and h.sigma.is_contiguous()
+        assert h.target.dtype == self.target_dtype and h.target.numel() == B * n * n and h.target.is_contiguous()
+        for r in (h.rotx, h.roty, h.rotz):
+            assert r.dtype == torch.float32 and r.numel() == B and r.is_contiguous()
+        assert not h.mus.is_cuda and not h.target.is_cuda, "HostSilhouetteStep takes HOST tensors"
+        i = self._next
+        self._next = (i + 1) % self.depth
+        res, st = self.results[i], self.streams[i]
+        res.wait()                                        # the slot's previous step must have drained
+        check(lib.gg_silhouette_step_host(
+            h.mus.data_ptr(), h.sigma.data_ptr(), h.rotx.data_ptr(), h.roty.data_ptr(), h.rotz.data_ptr(),
+            h.target.data_ptr(), self.kind, *self.t, self.focal, B, K, n,
+            res.loss_partials.data_ptr(), res.dmus.data_ptr(), res.dsigma.data_ptr(), res.drot.data_ptr(),
+            res.mask.data_ptr() if res.mask is not None else None,
+            self.ws[i].data_ptr(), self.ws_bytes, self.dev.index, st.cuda_stream), "gg_silhouette_step_host")
+        ev = torch.cuda.Event()
+        ev.record(st)
+        res.event = ev
+        return res
+
+    def drain(self):
+        """Make the current stream wait for every slot (so CUDA events recorded after it bracket the work)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            cur.wait_stream(st)

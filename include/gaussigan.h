@@ -48,6 +48,10 @@ extern "C" {
 #define GG_LAYOUT_NHWC 0          /* the reference's layout, [B,n,n,K] (mask_gen_dynamic.py:141) */
 #define GG_LAYOUT_NCHW 1          /* [B,K,n,n], for PyTorch consumers */
 
+#define GG_TARGET_U8 0            /* target mask as the raw 8-bit image; mask = raw/127.5 - 1 (mask_gen_dynamic.py:672) */
+#define GG_TARGET_F32 1           /* target mask already in [-1, 1], float32 */
+#define GG_LOSS_PARTIALS 296      /* per-CTA partial sums of |residual| written by gg_mask_l1_loss_bwd */
+
 #define GG_OK 0
 #define GG_E_NULL -1              /* required pointer is NULL */
 #define GG_E_SHAPE -2             /* B/K/n out of range, bad scale count or layout */
@@ -112,6 +116,30 @@ GG_API int gg_splat_bwd_tiles(int K, int nscales, const int *sizes_host, const i
 GG_API int gg_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes_host,
                  const float *const *gmaps_host, const float *const *gmasks_host, int layout,
                  float *partials, int T, int device, void *stream);
+
+/* ---- direct consumer: sum-composite L1 loss ------------------------------------------------------
+ * Replaces `m_recon_loss_bis` (mask/mask_gen_dynamic.py:785-787): loss = mean|0.5*(target+1) - mask| and its
+ * gradient w.r.t. mask.  target [B,n,n] is uint8 (GG_TARGET_U8, normalised as :672) or float32 in [-1,1].
+ * Writes gmask [B,n,n] = dloss/dmask and loss_partials[GG_LOSS_PARTIALS] (loss = sum(partials)/(B*n*n),
+ * summed by the caller: deterministic, no atomics). */
+GG_API int gg_mask_l1_loss_bwd(const float *mask, const void *target, int target_kind, int B, int n,
+                               float *gmask, float *loss_partials, int device, void *stream);
+
+/* ---- whole training-style step on HOST buffers ---------------------------------------------------
+ * What a host-language binding of the reference would call (the reference feeds numpy arrays through
+ * session.run, mask/infer_masks.py:435-456): H2D of the inputs, projection, splat (silhouette), L1 loss and its
+ * gradient, splat backward, projection backward, D2H of loss partials and gradients -- all enqueued on
+ * `stream`, no synchronisation.  *_host pointers are HOST memory (pinned for true asynchrony); `workspace` is
+ * DEVICE memory of at least gg_silhouette_step_workspace_bytes(...) bytes, 256-byte aligned, owned by the
+ * caller and private to this call until the stream has drained.  mask_host may be NULL (silhouette not
+ * copied back).  sigma_host is float64 [B,K,3,3]. */
+GG_API size_t gg_silhouette_step_workspace_bytes(int B, int K, int n, int target_kind);
+GG_API int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, const float *rotx_host,
+                                   const float *roty_host, const float *rotz_host, const void *target_host,
+                                   int target_kind, double tx, double ty, double tz, double focal,
+                                   int B, int K, int n, float *loss_partials_host, float *dmus_host,
+                                   double *dsigma_host, float *drot_host, float *mask_host,
+                                   void *workspace, size_t workspace_bytes, int device, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,107 @@
+"""The C-ABI shared library: loads, exports every symbol include/gaussigan.h declares, validates arguments.
+No compute calls here (no GPU needed): only host-side argument checks and the tile planner."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "gaussigan.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"GG_API\s+[\w\s\*]+?\b(gg_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gaussigan_b200 import _lib
+    names = _declared()
+    assert len(names) >= 9 and "gg_splat_fwd" in names and "gg_project_bwd" in names
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in gaussigan.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_constants():
+    from gaussigan_b200 import _lib
+    assert _lib.lib.gg_version() == 100
+    hdr = open(os.path.join(ROOT, "include", "gaussigan.h")).read()
+    assert int(re.search(r"#define GG_PARAM_STRIDE (\d+)", hdr).group(1)) == _lib.GG_PARAM_STRIDE
+    assert int(re.search(r"#define GG_MOMENTS (\d+)", hdr).group(1)) == _lib.GG_MOMENTS
+    assert int(re.search(r"#define GG_MAX_SCALES (\d+)", hdr).group(1)) == _lib.GG_MAX_SCALES
+
+
+def test_argument_validation_sets_last_error():
+    from gaussigan_b200 import _lib
+    lib, ia = _lib.lib, _lib.int_array
+    assert lib.gg_splat_bwd_tiles(0, 1, ia([256]), ia([0]), ia([1]), 0) == -2          # K <= 0
+    assert "K" in _lib.last_error()
+    assert lib.gg_splat_bwd_tiles(16, 0, ia([256]), ia([0]), ia([1]), 0) == -2         # no scales
+    assert lib.gg_splat_bwd_tiles(16, 5, ia([8] * 5), ia([0] * 5), ia([1] * 5), 0) == -2
+    assert lib.gg_splat_bwd_tiles(16, 1, ia([0]), ia([0]), ia([1]), 0) == -2           # n < 1
+    assert lib.gg_splat_bwd_tiles(16, 1, ia([256]), ia([0]), ia([1]), 7) == -2         # layout
+    # NULL / misaligned pointers are rejected before any launch (so this is safe without a GPU)
+    assert lib.gg_project_fwd(None, None, 1, None, None, None, 0., 0., -2., 1., 4, 8, None, None, None, 0, None) == -1
+    assert lib.gg_splat_fwd(None, 4, 8, 1, ia([32]), None, None, 0, 0, None) == -1
+    assert lib.gg_splat_fwd(C.c_void_p(4), 4, 8, 1, ia([32]), None, None, 0, 0, None) == -3
+    with pytest.raises(_lib.GaussiganError):
+        _lib.check(lib.gg_project_fwd(None, None, 1, None, None, None, 0., 0., -2., 1., 4, -1, None, None, None, 0, None), "x")
+    # B == 0 is a valid empty batch: no launch, status ok
+    assert lib.gg_project_fwd(None, None, 1, None, None, None, 0., 0., -2., 1., 0, 8, None, None, None, 0, None) == 0
+
+
+def test_tile_planner():
+    from gaussigan_b200 import _lib
+    lib, ia = _lib.lib, _lib.int_array
+    # mask-only gradient at 256: strips of 8 px, 8 rows per pass, GG_RPT_BWD (default 2) passes per tile
+    t256 = lib.gg_splat_bwd_tiles(16, 1, ia([256]), ia([0]), ia([1]), 0)
+    assert t256 > 0 and 256 % t256 == 0
+    # more scales -> more tiles; maps and mask-only scales are planned independently and add up
+    t4 = lib.gg_splat_bwd_tiles(16, 4, ia([32, 64, 128, 256]), ia([1, 1, 1, 1]), ia([0, 0, 0, 1]), 0)
+    t3 = lib.gg_splat_bwd_tiles(16, 3, ia([32, 64, 128]), ia([1, 1, 1]), ia([0, 0, 0]), 0)
+    t1 = lib.gg_splat_bwd_tiles(16, 1, ia([256]), ia([1]), ia([1]), 0)
+    assert t4 == t3 + t1
+    # K that is not 4*2^m falls back to the strip kernels but still plans
+    assert lib.gg_splat_bwd_tiles(6, 1, ia([100]), ia([1]), ia([0]), 0) > 0
+    assert lib.gg_splat_bwd_tiles(6, 1, ia([100]), ia([1]), ia([0]), 1) > 0
+    # nothing requested -> zero tiles
+    assert lib.gg_splat_bwd_tiles(6, 1, ia([100]), ia([0]), ia([0]), 0) == 0
+
+
+def test_public_api_rejects_cpu_tensors_and_bad_shapes():
+    import torch
+    import gaussigan_b200 as gg
+    z = torch.zeros(2, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gg.get_landmarks(torch.zeros(2, 4, 1, 3), torch.zeros(2, 4, 3, 3, dtype=torch.float64), z, z, z, 0, 0, -2.)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gg.get_gaussian_maps_2d(torch.zeros(2, 4, 2), torch.zeros(2, 4, 2, 2), [32, 32])
+    with pytest.raises(AssertionError):
+        gg.get_landmarks(None, torch.zeros(2, 4, 3, 3), z, z, z, 0, 0, -2.)          # reference: assert mus is not None
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        from gaussigan_b200.plan import SilhouetteStep
+        SilhouetteStep(2, 4, 32, "cpu")
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    import subprocess
+    import sys
+    env = dict(os.environ, GAUSSIGAN_LIB=str(tmp_path / "nope.so"), PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", "import gaussigan_b200"], env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU or PyTorch fallback" in r.stderr
+
+
+def test_product_does_not_import_the_oracle():
+    import subprocess
+    import sys
+    code = "import sys, gaussigan_b200, gaussigan_b200.plan, gaussigan_b200.dist; sys.exit(int(any(m.split('.')[0]=='oracle' for m in sys.modules)))"
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gaussigan_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

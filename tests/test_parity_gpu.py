@@ -1,0 +1,292 @@
+"""Parity of the CUDA path (through the public API and the C ABI) against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star; norm-relative):
+    forward  : max|out - ref| <= 1e-5 * max|ref|
+    gradients: max|g - ref|   <= 1e-4 * max|ref|
+Nothing here reads /root/reference (it does not exist on the GPU box).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as rp
+from util import FWD_RTOL, GRAD_RTOL, assert_close_norm, inputs_of, load, max_rel, sub, weights_like
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gg(cuda_device):
+    import gaussigan_b200
+    return gaussigan_b200
+
+
+def _dev(inp, dev):
+    return {k: v.to(dev) for k, v in inp.items()}
+
+
+def _leaves(inp, dev=None):
+    return {k: (v.to(dev) if dev is not None else v.clone()).requires_grad_(True) for k, v in inp.items()}
+
+
+# ------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", ["train_k6", "train_k12_general", "train_k16"])
+@pytest.mark.parametrize("layout", ["nhwc", "nchw"])
+def test_get_landmarks_vs_golden(gg, cuda_device, name, layout):
+    g = load(name)
+    lv = _leaves(inputs_of(g), cuda_device)
+    t = [float(v) for v in g["t"]]
+    maps = gg.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], *t, float(g["focal"]),
+                            layout=layout)
+    if layout == "nchw":
+        maps = [m.permute(0, 2, 3, 1) for m in maps]
+    assert [m.shape[1] for m in maps] == [32, 64, 128, 256] and all(m.dtype == torch.float32 for m in maps)
+    for m in maps:
+        n = m.shape[1]
+        assert_close_norm(sub(m), g[f"maps{n}"], FWD_RTOL, f"{name} maps{n}")
+        assert_close_norm(m.double().sum((1, 2)), g[f"maps{n}_sum"], FWD_RTOL, f"{name} sum{n}")
+    w = weights_like([m.shape for m in maps], g["wseed"])
+    sum((m * q.to(cuda_device)).sum() for m, q in zip(maps, w)).backward()
+    for k, v in lv.items():
+        assert v.grad.dtype == v.dtype and v.grad.shape == v.shape
+        assert_close_norm(v.grad, g[f"grad_{k}"], GRAD_RTOL, f"{name} grad_{k}")
+
+
+def test_infer_flavour_vs_golden(gg, cuda_device):
+    g = load("infer_k6")
+    d = _dev(inputs_of(g), cuda_device)
+    mu2d, s2d, maps = gg.get_landmarks_infer(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0., 0., -2.)
+    assert mu2d.dtype == s2d.dtype == maps.dtype == torch.float32 and tuple(maps.shape) == (2, 256, 256, 6)
+    np.testing.assert_array_equal(mu2d.cpu().numpy(), g["mu2d"])          # f64 projection -> same f32 rounding
+    np.testing.assert_array_equal(s2d.cpu().numpy(), g["sigma2d"])
+    assert_close_norm(sub(maps), g["maps256"], FWD_RTOL, "infer maps")
+
+
+def test_get_gaussian_maps_2d_vs_golden(gg, cuda_device):
+    g = load("raster_k8")
+    n = int(g["n"])
+    mu = torch.from_numpy(g["mu2d"]).to(cuda_device).requires_grad_(True)
+    sg = torch.from_numpy(g["sigma2d"]).to(cuda_device).requires_grad_(True)
+    m = gg.get_gaussian_maps_2d(mu, sg, [n, n])
+    assert_close_norm(m, g["maps"], FWD_RTOL, "raster maps")
+    w = weights_like([m.shape], g["wseed"])[0].to(cuda_device)
+    (m * w).sum().backward()
+    assert mu.grad.dtype == torch.float64
+    assert_close_norm(mu.grad, g["grad_mu2d"], GRAD_RTOL, "grad_mu2d")
+    assert_close_norm(sg.grad, g["grad_sigma2d"], GRAD_RTOL, "grad_sigma2d")
+    with pytest.raises(ValueError):
+        gg.get_gaussian_maps_2d(mu, sg, [32, 48])
+
+
+# ------------------------------------------------------------------- BASELINE.json configurations
+def test_config1_forward_b16_k8_128(gg, cuda_device):
+    inp = rp.synth_inputs(16, 8, seed=56)
+    d = _dev(inp, cuda_device)
+    ref = rp.get_landmarks(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0, 0, -2., sizes=(128,))[0]
+    out = gg.get_landmarks(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., sizes=(128,))[0]
+    assert_close_norm(out, ref, FWD_RTOL, "C1 maps")
+    mask = gg.render_silhouette(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., size=128)
+    assert_close_norm(mask, ref.sum(-1), FWD_RTOL, "C1 mask")
+
+
+def test_config2_forward_backward_b64_k16_256_full_size(gg, cuda_device):
+    """The headline configuration at full size: mask renderer fwd+bwd, gradient check vs the oracle."""
+    B, K, n = 64, 16, 256
+    inp = rp.synth_inputs(B, K, seed=56)
+    tgt = rp.synth_target_masks(B, n)
+    mask_ref, loss_ref, dmu_ref, dsig_ref, drot_ref = rp.render_loss_and_grads(inp, tgt, n)
+    d = _dev(inp, cuda_device)
+    mus, sig, roty = (d[k].clone().requires_grad_(True) for k in ("mus", "sigma", "roty"))
+    mask = gg.render_silhouette(mus, sig, d["rotx"], roty, d["rotz"], 0, 0, -2., size=n)
+    loss = ((tgt.to(cuda_device)[..., 0] + 1) * 0.5 - mask).abs().mean()
+    loss.backward()
+    assert_close_norm(mask, mask_ref, FWD_RTOL, "C2 mask")
+    assert abs(loss.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item())
+    assert_close_norm(mus.grad, dmu_ref, GRAD_RTOL, "C2 dmus")
+    assert_close_norm(sig.grad, dsig_ref, GRAD_RTOL, "C2 dsigma (raw, as the reference's autodiff)")
+    assert_close_norm(rp.sym(sig.grad), rp.sym(dsig_ref), GRAD_RTOL, "C2 sym(dsigma)")
+    assert_close_norm(roty.grad, drot_ref, GRAD_RTOL, "C2 droty")
+
+
+def test_config3_deformation_then_render(gg, cuda_device):
+    """Dynamic-object step: per-frame deformation (reference tail, here torch ops) feeding the renderer;
+    gradients flow back through the renderer into the canonical Gaussians and the deformation heads."""
+    B, K, n = 8, 16, 256
+    g = torch.Generator().manual_seed(56)
+    th = lambda *s: torch.tanh(torch.randn(*s, generator=g))
+    cann = rp.synth_inputs(1, K, seed=56)
+    heads = [th(B, K * 3), th(B, K * 3), th(B, K), th(B, K), th(B, K), th(B, 1)]
+    w = torch.randn(B, n, n, generator=g)
+
+    def run(dev, render):
+        cm = cann["mus"].to(dev).requires_grad_(True)
+        cs = cann["sigma"].to(dev).requires_grad_(True)
+        hs = [h.to(dev).requires_grad_(True) for h in heads]
+        mus, sig, theta = rp.deform(*hs, cm, cs)
+        m = render(mus, sig, torch.zeros_like(theta), theta, torch.zeros_like(theta))
+        (m * w.to(dev)).sum().backward()
+        return m.detach(), [cm.grad, cs.grad] + [h.grad for h in hs]
+
+    m_ref, g_ref = run(torch.device("cpu"),
+                       lambda mu, s, rx, ry, rz: rp.get_landmarks(mu, s, rx, ry, rz, 0, 0, -2., sizes=(n,))[0].sum(-1))
+    m_out, g_out = run(cuda_device, lambda mu, s, rx, ry, rz: gg.render_silhouette(mu, s, rx, ry, rz, 0, 0, -2., size=n))
+    # the deformation itself runs in torch on both sides (CPU vs GPU SVD/trig differ by ~1e-7), hence 5x slack
+    assert_close_norm(m_out, m_ref, 5 * FWD_RTOL, "C3 mask")
+    for a, b, nm in zip(g_out, g_ref, ["cannmu", "cannsigma", "mu_t", "scale", "rx", "ry", "rz", "theta"]):
+        assert_close_norm(a, b, 5 * GRAD_RTOL, "C3 grad " + nm)
+
+
+def test_config4_maps_pyramid_k16(gg, cuda_device):
+    """rgb path: K=16 per-Gaussian maps at the four scales (forward only in the reference, rgb_gen_dynamic.py:956)."""
+    B, K = 32, 16
+    inp = rp.synth_inputs(B, K, seed=4, angle=60.0)
+    d = _dev(inp, cuda_device)
+    ref = rp.get_landmarks(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0, 0, -2.)
+    out, mask = gg.get_landmarks_with_mask(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2.)
+    for o, r in zip(out, ref):
+        assert_close_norm(o, r, FWD_RTOL, f"C4 maps{r.shape[1]}")
+    assert tuple(mask.shape) == (B, 256, 256, 1)
+    assert_close_norm(mask, rp.sum_composite(ref[-1]), FWD_RTOL, "C4 fused sum composite")
+
+
+def test_config5_shape_k64_512_properties_and_oracle(gg, cuda_device):
+    """Throughput-sweep shape (K=64, 512x512) at a batch the oracle finishes in seconds, plus
+    size-independent properties."""
+    B, K, n = 2, 64, 512
+    inp = rp.synth_inputs(B, K, seed=5)
+    d = _dev(inp, cuda_device)
+    lv = _leaves(inp)
+    ref = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0, 0, -2., sizes=(n,))[0]
+    gen = torch.Generator().manual_seed(1)
+    gm = torch.randn(B, n, n, generator=gen)
+    (ref.sum(-1) * gm).sum().backward()
+    mus, sig, roty = (d[k].clone().requires_grad_(True) for k in ("mus", "sigma", "roty"))
+    mask = gg.render_silhouette(mus, sig, d["rotx"], roty, d["rotz"], 0, 0, -2., size=n)
+    mask.backward(gm.to(cuda_device))
+    assert_close_norm(mask, ref.sum(-1), FWD_RTOL, "C5 mask")
+    assert_close_norm(mus.grad, lv["mus"].grad, GRAD_RTOL, "C5 dmus")
+    assert_close_norm(sig.grad, lv["sigma"].grad, GRAD_RTOL, "C5 dsigma")
+    assert_close_norm(roty.grad, lv["roty"].grad, GRAD_RTOL, "C5 droty")
+    # property: K-channel maps (quad kernel, K=64 -> 16 lanes per pixel) sum to the mask-mode kernel's output
+    maps = gg.get_landmarks(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., sizes=(n,))[0]
+    assert_close_norm(maps.sum(-1), mask, 2e-6, "maps.sum == mask")
+    assert float(maps.max()) <= 1.0 + 1e-6 and float(maps.min()) >= 0.0
+
+
+def test_backward_is_linear_and_deterministic(gg, cuda_device):
+    B, K, n = 16, 16, 256
+    d = _dev(rp.synth_inputs(B, K, seed=8), cuda_device)
+    gen = torch.Generator().manual_seed(2)
+    g1 = torch.randn(B, n, n, generator=gen).to(cuda_device)
+    g2 = torch.randn(B, n, n, generator=gen).to(cuda_device)
+
+    def grads(gm):
+        mus, sig, roty = (d[k].clone().requires_grad_(True) for k in ("mus", "sigma", "roty"))
+        gg.render_silhouette(mus, sig, d["rotx"], roty, d["rotz"], 0, 0, -2., size=n).backward(gm)
+        return mus.grad, sig.grad, roty.grad
+
+    a, b, c, a2 = grads(g1), grads(g2), grads(2.0 * g1 - 3.0 * g2), grads(g1)
+    for x, y, z, x2 in zip(a, b, c, a2):
+        assert torch.equal(x, x2)                                  # no atomics: bit-reproducible
+        assert_close_norm(z, 2.0 * x.double() - 3.0 * y.double(), 1e-5, "linearity of the adjoint")
+
+
+# ----------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("B,K,sizes", [
+    (1, 1, (1,)), (1, 1, (2,)), (2, 3, (7, 33)), (2, 5, (100,)), (1, 6, (12, 20, 36, 44)),
+    (2, 12, (64,)), (2, 80, (40,)), (1, 256, (24,)), (1, 2, (1000,)), (1, 2, (2100,)),
+])
+@pytest.mark.parametrize("layout", ["nhwc", "nchw"])
+def test_ragged_shapes_forward_backward(gg, cuda_device, B, K, sizes, layout):
+    inp = rp.synth_inputs(B, K, seed=B * 1000 + K, angle=30.0)
+    lv = _leaves(inp)
+    ref = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0, 0, -2., sizes=sizes)
+    w = weights_like([r.shape for r in ref], 9)
+    sum((r * q).sum() for r, q in zip(ref, w)).backward()
+    dv = _leaves(inp, cuda_device)
+    out = gg.get_landmarks(dv["mus"], dv["sigma"], dv["rotx"], dv["roty"], dv["rotz"], 0, 0, -2., sizes=sizes, layout=layout)
+    if layout == "nchw":
+        out = [o.permute(0, 2, 3, 1) for o in out]
+    for o, r in zip(out, ref):
+        assert o.shape == r.shape
+        assert_close_norm(o, r, FWD_RTOL, f"maps n={r.shape[1]}")
+    sum((o * q.to(cuda_device)).sum() for o, q in zip(out, w)).backward()
+    for k in ("mus", "sigma", "rotx", "roty", "rotz"):
+        assert_close_norm(dv[k].grad, lv[k].grad, GRAD_RTOL, f"grad {k}")
+    # mask-only path on the last scale
+    m = gg.render_silhouette(dv["mus"].detach(), dv["sigma"].detach(), dv["rotx"].detach(), dv["roty"].detach(),
+                             dv["rotz"].detach(), 0, 0, -2., size=sizes[-1])
+    assert_close_norm(m, ref[-1].detach().sum(-1), FWD_RTOL, "mask")
+
+
+def test_empty_batch(gg, cuda_device):
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=cuda_device)
+    maps = gg.get_landmarks(z(0, 4, 1, 3), z(0, 4, 3, 3, dt=torch.float64), z(0, 1), z(0, 1), z(0, 1), 0, 0, -2.)
+    assert [tuple(m.shape) for m in maps] == [(0, 32, 32, 4), (0, 64, 64, 4), (0, 128, 128, 4), (0, 256, 256, 4)]
+    assert tuple(gg.render_silhouette(z(0, 4, 1, 3), z(0, 4, 3, 3), z(0, 1), z(0, 1), z(0, 1), 0, 0, -2.).shape) == (0, 256, 256)
+
+
+def test_float32_sigma_and_flat_shapes(gg, cuda_device):
+    inp = rp.synth_inputs(3, 8, seed=2)
+    s32 = inp["sigma"].float()
+    ref = rp.get_landmarks(inp["mus"], s32.double(), inp["rotx"], inp["roty"], inp["rotz"], 0, 0, -2., sizes=(64,))[0]
+    d = _dev(inp, cuda_device)
+    sig = s32.to(cuda_device).requires_grad_(True)
+    out = gg.get_landmarks(d["mus"].reshape(3, 8, 3), sig, d["rotx"].reshape(3), d["roty"].reshape(3),
+                           d["rotz"].reshape(3), 0, 0, -2., sizes=(64,), K=8)[0]
+    assert_close_norm(out, ref, FWD_RTOL, "f32 sigma")
+    out.sum().backward()
+    assert sig.grad.dtype == torch.float32 and sig.grad.shape == sig.shape
+    with pytest.raises(ValueError):
+        gg.get_landmarks(d["mus"], sig, d["rotx"], d["roty"], d["rotz"], 0, 0, -2., K=7)
+
+
+def test_offscreen_and_tiny_gaussians_stay_finite(gg, cuda_device):
+    """Gaussians far outside the frame or much smaller than a pixel: zeros / tiny values, never NaN."""
+    B, K, n = 2, 4, 64
+    mus = torch.tensor([[[3.0, 0, 0], [0, -3.0, 0], [0.0, 0, 0], [0.3, 0.3, 0]]] * B).view(B, K, 1, 3)
+    sig = torch.eye(3, dtype=torch.float64).view(1, 1, 3, 3).repeat(B, K, 1, 1) * 0.01
+    sig[:, 2] *= 1e-4
+    z = torch.zeros(B, 1)
+    ref = rp.get_landmarks(mus, sig, z, z, z, 0, 0, -2., sizes=(n,))[0]
+    dv = [t.to(cuda_device).requires_grad_(True) for t in (mus, sig)]
+    zz = z.to(cuda_device)
+    out = gg.get_landmarks(dv[0], dv[1], zz, zz, zz, 0, 0, -2., sizes=(n,))[0]
+    assert torch.isfinite(out).all()
+    assert_close_norm(out, ref, FWD_RTOL, "offscreen/tiny")
+    out.sum().backward()
+    assert torch.isfinite(dv[0].grad).all() and torch.isfinite(dv[1].grad).all()
+
+
+# --------------------------------------------------------------------- planned step / C ABI direct
+def test_planned_step_equals_autograd_and_graph_replay(gg, cuda_device):
+    from gaussigan_b200.plan import SilhouetteStep
+    B, K, n = 8, 16, 128
+    d = _dev(rp.synth_inputs(B, K, seed=12), cuda_device)
+    gm = torch.randn(B, n, n, device=cuda_device)
+    mus = d["mus"].reshape(B, K, 3).contiguous()
+    rx, ry, rz = (d[k].reshape(B).contiguous() for k in ("rotx", "roty", "rotz"))
+    step = SilhouetteStep(B, K, n, cuda_device)
+    mask = step.forward(mus, d["sigma"], rx, ry, rz).clone()
+    dmus, dsig, drot = (t.clone() for t in step.backward(gm))
+    lm, ls, lr = (t.clone().requires_grad_(True) for t in (d["mus"], d["sigma"], d["roty"]))
+    m2 = gg.render_silhouette(lm, ls, d["rotx"], lr, d["rotz"], 0, 0, -2., size=n)
+    m2.backward(gm)
+    assert torch.equal(mask, m2) and torch.equal(dmus.view_as(lm.grad), lm.grad)
+    assert torch.equal(dsig, ls.grad) and torch.equal(drot[:, 1], lr.grad.view(-1))
+    step.capture(gm)
+    step.mask.zero_(); step.dmus.zero_(); step.dsigma.zero_()
+    step.graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(step.mask, mask) and torch.equal(step.dmus, dmus) and torch.equal(step.dsigma, dsig)
+
+
+def test_projection_outputs_match_oracle_to_float64_roundoff(gg, cuda_device):
+    inp = rp.synth_inputs(16, 16, seed=77, angle=90.0)
+    inp["rotx"] = torch.randn(16, 1) * 20
+    inp["rotz"] = torch.randn(16, 1) * 20
+    d = _dev(inp, cuda_device)
+    mu2d, s2d = gg.project(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0.3, -0.1, -2.4, 1.7)
+    rmu, rs = rp.project(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0.3, -0.1, -2.4, 1.7)
+    assert mu2d.dtype == torch.float64
+    assert (mu2d.cpu() - rmu).abs().max() < 1e-12 and max_rel(s2d, rs) < 1e-12

@@ -119,9 +119,9 @@ def test_config3_deformation_then_render(gg, cuda_device):
     w = torch.randn(B, n, n, generator=g)
 
     def run(dev, render):
-        cm = cann["mus"].to(dev).requires_grad_(True)
-        cs = cann["sigma"].to(dev).requires_grad_(True)
-        hs = [h.to(dev).requires_grad_(True) for h in heads]
+        cm = cann["mus"].detach().clone().to(dev).requires_grad_(True)
+        cs = cann["sigma"].detach().clone().to(dev).requires_grad_(True)
+        hs = [h.detach().clone().to(dev).requires_grad_(True) for h in heads]
         mus, sig, theta = rp.deform(*hs, cm, cs)
         m = render(mus, sig, torch.zeros_like(theta), theta, torch.zeros_like(theta))
         (m * w.to(dev)).sum().backward()

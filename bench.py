@@ -273,7 +273,7 @@ def run_gpu(args):
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
     e2e = None
     try:
-        host = HostSilhouetteStep(B, K, n, dev, depth=2)
+        host = HostSilhouetteStep(B, K, n, dev, depth=3)
         hsets = [host.make_host_inputs(s[2], s[3]) for s in sets[:min(R, 4)]]
         for i in range(3):
             host.submit(hsets[i % len(hsets)])

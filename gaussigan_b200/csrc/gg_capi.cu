@@ -151,6 +151,25 @@ int gg_mask_l1_loss_bwd(const float *mask, const void *target, int target_kind, 
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_mask_l1_loss_bwd");
 }
 
+int gg_silhouette_loss_fused(const float *params, const void *target, int target_kind, int B, int K, int n,
+                             float *mask_out, float *partials, int T, float *loss_partials, int device,
+                             void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  const int sizes[1] = {n};
+  if (int r = check_scales(K, 1, sizes)) return r;
+  if (K > 64) return fail(GG_E_SHAPE, "gg_silhouette_loss_fused: K=%d > 64 (use the unfused entry points)", K);
+  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32) return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
+  if (B == 0) return GG_OK;
+  if (!params || !target || !partials || !loss_partials) return fail(GG_E_NULL, "gg_silhouette_loss_fused: NULL pointer");
+  if (!aligned16(params) || (mask_out && !aligned16(mask_out)) || !aligned16(target))
+    return fail(GG_E_ALIGN, "gg_silhouette_loss_fused: params/target/mask_out must be 16-byte aligned");
+  if (T != gg::fused_loss_tiles(K, n)) return fail(GG_E_WORKSPACE, "gg_silhouette_loss_fused: T=%d, expected %d", T, gg::fused_loss_tiles(K, n));
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_silhouette_loss_fused(params, target, target_kind, B, K, n, mask_out, partials,
+                                                   loss_partials, T, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_silhouette_loss_fused");
+}
+
 int gg_splat_bwd_tiles(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,
                        const int *has_gmasks_host, int layout) {
   if (K <= 0) return fail(GG_E_SHAPE, "K must be > 0");

@@ -43,6 +43,11 @@ struct SplatArgs {
   int nscales;
   int layout;
   int tile_offset;       // backward: first partial slot written by this launch
+  // fused silhouette-loss kernel only (gg_silhouette_loss_fused):
+  const void *target;    // [B,n,n] uint8 (raw) or float32 ([-1,1])
+  int target_kind;
+  float inv_n;           // 1 / (B*n*n)
+  float *loss_partials;  // [B*T] per-CTA sums of |residual|
   ScaleDesc sc[GG_MAX_SCALES];
 };
 
@@ -56,6 +61,42 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // out[j] = start + step * j, product and sum each rounded (no FMA contraction).
 __device__ __forceinline__ float grid_coord(int j, float step) {
   return __fadd_rn(-1.0f, __fmul_rn(step, (float)j));
+}
+
+// ---- packed FP32x2 arithmetic (sm_100a: FFMA2 / FADD2 / FMUL2).  One instruction = two IEEE-rn float32
+// operations on a 64-bit register pair: same lane throughput as the scalar forms (measured,
+// tools/microbench/issue_peaks.cu) at half the issue slots -- which is what an issue-bound loop needs.
+#ifndef GG_USE_F32X2
+#define GG_USE_F32X2 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
 __device__ __forceinline__ void st_f4(float *p, float a, float b, float c, float d) {

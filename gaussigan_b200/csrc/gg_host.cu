@@ -10,6 +10,7 @@ namespace gg {
 struct StepLayout {
   size_t mus, sigma, rot, target, params, mask, gmask, partials, loss, dmus, dsigma, drot, total;
   int T;
+  int nloss;   // loss partials written by the step (fused path: one per CTA; unfused: GG_LOSS_PARTIALS)
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
@@ -28,7 +29,8 @@ StepLayout step_layout(int B, int K, int n, int target_kind) {
   L.mask = take((size_t)B * n * n * 4);
   L.gmask = take((size_t)B * n * n * 4);
   L.partials = take((size_t)B * L.T * K * GG_MOMENTS * 4);
-  L.loss = take((size_t)GG_LOSS_PARTIALS * 4);
+  L.nloss = K <= 64 ? B * L.T : GG_LOSS_PARTIALS;
+  L.loss = take((size_t)L.nloss * 4);
   L.dmus = take((size_t)B * K * 3 * 4);
   L.dsigma = take((size_t)B * K * 9 * 8);
   L.drot = take((size_t)B * 3 * 4);
@@ -45,6 +47,11 @@ extern "C" {
 size_t gg_silhouette_step_workspace_bytes(int B, int K, int n, int target_kind) {
   if (B <= 0 || K <= 0 || n < 1) return 0;
   return gg::step_layout(B, K, n, target_kind).total;
+}
+
+int gg_silhouette_step_loss_count(int B, int K, int n) {
+  if (B <= 0 || K <= 0 || n < 1) return fail(GG_E_SHAPE, "bad B/K/n");
+  return gg::step_layout(B, K, n, GG_TARGET_U8).nloss;
 }
 
 int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, const float *rotx_host,
@@ -95,15 +102,20 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
          "H2D target");
   GG_TRY(gg::launch_project_fwd(d_mus, d_sigma, 1, d_rot, d_rot + B, d_rot + 2 * (size_t)B, tx, ty, tz, focal, B, K,
                                 nullptr, nullptr, d_params, st), "project_fwd");
-  float *masks[1] = {d_mask};
-  GG_TRY(gg::launch_splat_fwd(d_params, B, K, 1, sizes, nullptr, masks, GG_LAYOUT_NHWC, st), "splat_fwd");
-  GG_TRY(gg::launch_mask_l1_loss_bwd(d_mask, d_target, target_kind, B, n, d_gmask, d_loss, GG_LOSS_PARTIALS, st),
-         "mask_l1_loss_bwd");
-  const float *gmasks[1] = {d_gmask};
-  GG_TRY(gg::launch_splat_bwd(d_params, B, K, 1, sizes, nullptr, gmasks, GG_LAYOUT_NHWC, d_part, L.T, st), "splat_bwd");
+  if (K <= 64) {
+    GG_TRY(gg::launch_silhouette_loss_fused(d_params, d_target, target_kind, B, K, n, mask_host ? d_mask : nullptr,
+                                            d_part, d_loss, L.T, st), "silhouette_loss_fused");
+  } else {
+    float *masks[1] = {d_mask};
+    GG_TRY(gg::launch_splat_fwd(d_params, B, K, 1, sizes, nullptr, masks, GG_LAYOUT_NHWC, st), "splat_fwd");
+    GG_TRY(gg::launch_mask_l1_loss_bwd(d_mask, d_target, target_kind, B, n, d_gmask, d_loss, GG_LOSS_PARTIALS, st),
+           "mask_l1_loss_bwd");
+    const float *gmasks[1] = {d_gmask};
+    GG_TRY(gg::launch_splat_bwd(d_params, B, K, 1, sizes, nullptr, gmasks, GG_LAYOUT_NHWC, d_part, L.T, st), "splat_bwd");
+  }
   GG_TRY(gg::launch_project_bwd(d_mus, d_sigma, 1, d_rot, d_rot + B, d_rot + 2 * (size_t)B, tx, ty, tz, focal, B, K,
                                 d_part, L.T, nullptr, nullptr, d_dmus, d_dsig, d_drot, st), "project_bwd");
-  GG_TRY(cudaMemcpyAsync(loss_partials_host, d_loss, (size_t)GG_LOSS_PARTIALS * 4, cudaMemcpyDeviceToHost, st), "D2H loss");
+  GG_TRY(cudaMemcpyAsync(loss_partials_host, d_loss, (size_t)L.nloss * 4, cudaMemcpyDeviceToHost, st), "D2H loss");
   GG_TRY(cudaMemcpyAsync(dmus_host, d_dmus, (size_t)B * K * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H dmus");
   GG_TRY(cudaMemcpyAsync(dsigma_host, d_dsig, (size_t)B * K * 9 * 8, cudaMemcpyDeviceToHost, st), "D2H dsigma");
   GG_TRY(cudaMemcpyAsync(drot_host, d_drot, (size_t)B * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H drot");

@@ -25,6 +25,11 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
 cudaError_t launch_mask_l1_loss_bwd(const float *mask, const void *target, int kind, int B, int n, float *gmask,
                                     float *partials, int npartials, cudaStream_t st);
 
+int fused_loss_tiles(int K, int n);
+cudaError_t launch_silhouette_loss_fused(const float *params, const void *target, int target_kind, int B, int K, int n,
+                                         float *mask_out, float *partials, float *loss_partials, int T,
+                                         cudaStream_t st);
+
 namespace api {   // error/validation helpers shared by the extern "C" translation units (gg_capi.cu)
 int fail(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *where);

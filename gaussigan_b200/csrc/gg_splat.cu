@@ -131,12 +131,27 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_
       const float sh = fmaf(p.w, dy, p.x);
       const float e = (nE * dy) * dy;
       float g[kStrip];
+#if GG_USE_F32X2
+      {
+        const f32x2 sh2 = pack2(sh, sh), nA2 = pack2(p.z, p.z), e2 = pack2(e, e);
+#pragma unroll
+        for (int j = 0; j < kStrip; j += 2) {
+          const f32x2 t2 = sub2(pack2(x[j], x[j + 1]), sh2);
+          float a0, a1;
+          unpack2(fma2(nA2, mul2(t2, t2), e2), a0, a1);
+          g[j] = ex2_approx(a0);
+          g[j + 1] = ex2_approx(a1);
+          unpack2(add2(pack2(acc[r][j], acc[r][j + 1]), pack2(g[j], g[j + 1])), acc[r][j], acc[r][j + 1]);
+        }
+      }
+#else
 #pragma unroll
       for (int j = 0; j < kStrip; ++j) {
         const float t = x[j] - sh;
-        g[j] = ex2_approx(fmaf(p.z * t, t, e));
+        g[j] = ex2_approx(fmaf(p.z, t * t, e));
         acc[r][j] += g[j];
       }
+#endif
       if (OUT == 1) {
         if (rv[r]) {
           int row = pos.row0 + r * s.rpp;
@@ -164,7 +179,11 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_
 }
 
 // ============================================================================== backward, strips
-// GIN: 0 = gradient w.r.t. mask only, 1 = NCHW gmaps (+ gmask), 2 = NHWC gmaps, scalar loads (+ gmask)
+// GIN: 0 = gradient w.r.t. mask only, 1 = NCHW gmaps (+ gmask), 2 = NHWC gmaps, scalar loads (+ gmask),
+//      3 = FUSED silhouette loss: a forward pass over the K Gaussians builds the silhouette in registers,
+//          the residual against the target gives dL/dmask = -sign(0.5*(t+1) - m)/N on the spot
+//          (mask/mask_gen_dynamic.py:785-787), and the same CTA runs the backward -- the mask and its gradient
+//          never touch HBM (optionally the mask is written out through s.mask).  Requires K <= kKBlock.
 template <int RPT, int GIN>
 __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_constant__ SplatArgs a) {
   __shared__ float4 sp[kKBlock * 2];
@@ -200,7 +219,79 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
     y[r] = grid_coord(row, s.step);
 #pragma unroll
     for (int j = 0; j < kStrip; ++j) gm[r][j] = 0.f;
-    if (rv[r] && gmask) load8(gmask + ((size_t)b * n + row) * n + pos.col0, pos.col0, n, gm[r]);
+    if (GIN != 3 && rv[r] && gmask) load8(gmask + ((size_t)b * n + row) * n + pos.col0, pos.col0, n, gm[r]);
+  }
+
+  if (GIN == 3) {
+    // ---- forward pass: gm <- silhouette
+    for (int kk = 0; kk < kn; ++kk) {
+      const float4 p = sp[2 * kk];
+      const float nE = sp[2 * kk + 1].x;
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const float dy = y[r] - p.y;
+        const float sh = fmaf(p.w, dy, p.x);
+        const float e = (nE * dy) * dy;
+        const f32x2 sh2 = pack2(sh, sh), nA2 = pack2(p.z, p.z), e2 = pack2(e, e);
+#pragma unroll
+        for (int j = 0; j < kStrip; j += 2) {
+          const f32x2 t2 = sub2(pack2(x[j], x[j + 1]), sh2);
+          float a0, a1;
+          unpack2(fma2(nA2, mul2(t2, t2), e2), a0, a1);
+          unpack2(add2(pack2(gm[r][j], gm[r][j + 1]), pack2(ex2_approx(a0), ex2_approx(a1))), gm[r][j], gm[r][j + 1]);
+        }
+      }
+    }
+    // ---- residual -> loss partial and dL/dmask, in place
+    float lsum = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      if (!rv[r]) continue;
+      const int row = pos.row0 + r * s.rpp;
+      const size_t off = ((size_t)b * n + row) * n + pos.col0;
+      if (gmask) store8(s.mask + off, pos.col0, n, gm[r]);         // optional silhouette output
+      float tg[kStrip];
+      if (a.target_kind == GG_TARGET_U8) {
+        const unsigned char *tp = reinterpret_cast<const unsigned char *>(a.target) + off;
+        if ((n & 7) == 0) {
+          const uint2 u = __ldg(reinterpret_cast<const uint2 *>(tp));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            tg[j] = (float)((u.x >> (8 * j)) & 0xffu);
+            tg[j + 4] = (float)((u.y >> (8 * j)) & 0xffu);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kStrip; ++j) tg[j] = (pos.col0 + j < n) ? (float)__ldg(tp + j) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kStrip; ++j)   // (raw/127.5 - 1 + 1) * 0.5, op by op as the reference (:672, :787)
+          tg[j] = __fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(tg[j], 127.5f), 1.0f), 1.0f), 0.5f);
+      } else {
+        load8(reinterpret_cast<const float *>(a.target) + off, pos.col0, n, tg);
+#pragma unroll
+        for (int j = 0; j < kStrip; ++j) tg[j] = __fmul_rn(__fadd_rn(tg[j], 1.0f), 0.5f);
+      }
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j) {
+        const float res = tg[j] - gm[r][j];
+        const bool in = pos.col0 + j < n;
+        lsum += in ? fabsf(res) : 0.f;
+        gm[r][j] = !in ? 0.f : (res > 0.f ? -a.inv_n : (res < 0.f ? a.inv_n : 0.f));
+      }
+    }
+    // per-CTA loss partial (fixed order: lanes by butterfly, warps serially)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if (lane == 0) warpsum[warp][0] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += warpsum[w][0];
+      a.loss_partials[(size_t)b * a.T + tile] = tot;
+    }
+    __syncthreads();
   }
 
   for (int kk = 0; kk < kn; ++kk) {
@@ -211,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
     for (int r = 0; r < RPT; ++r) {
       if (!rv[r]) continue;
       float G[kStrip];
-      if (GIN == 0) {
+      if (GIN == 0 || GIN == 3) {
 #pragma unroll
         for (int j = 0; j < kStrip; ++j) G[j] = gm[r][j];
       } else if (GIN == 1) {
@@ -229,16 +320,39 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
       const float dy = y[r] - p.y;
       const float sh = fmaf(p.w, dy, p.x);
       const float e = (nE * dy) * dy;
-      float S0 = 0.f, S1 = 0.f, S2 = 0.f;
+      float S0, S1, S2;
+#if GG_USE_F32X2
+      {
+        const f32x2 sh2 = pack2(sh, sh), nA2 = pack2(p.z, p.z), e2 = pack2(e, e);
+        f32x2 s0 = pack2(0.f, 0.f), s1 = s0, s2 = s0;
+#pragma unroll
+        for (int j = 0; j < kStrip; j += 2) {
+          const f32x2 t2 = sub2(pack2(x[j], x[j + 1]), sh2);
+          const f32x2 u2 = mul2(t2, t2);
+          float a0, a1;
+          unpack2(fma2(nA2, u2, e2), a0, a1);
+          const f32x2 w2 = mul2(pack2(ex2_approx(a0), ex2_approx(a1)), pack2(G[j], G[j + 1]));
+          s0 = add2(s0, w2);
+          s1 = fma2(w2, t2, s1);
+          s2 = fma2(w2, u2, s2);
+        }
+        float lo, hi;
+        unpack2(s0, lo, hi); S0 = lo + hi;
+        unpack2(s1, lo, hi); S1 = lo + hi;
+        unpack2(s2, lo, hi); S2 = lo + hi;
+      }
+#else
+      S0 = S1 = S2 = 0.f;
 #pragma unroll
       for (int j = 0; j < kStrip; ++j) {
         const float t = x[j] - sh;
-        const float w = ex2_approx(fmaf(p.z * t, t, e)) * G[j];
-        const float wt = w * t;
+        const float u = t * t;
+        const float w = ex2_approx(fmaf(p.z, u, e)) * G[j];
         S0 += w;
-        S1 += wt;
-        S2 = fmaf(wt, t, S2);
+        S1 = fmaf(w, t, S1);
+        S2 = fmaf(w, u, S2);
       }
+#endif
       T20 += S2;
       T10 += S1;
       T11 = fmaf(dy, S1, T11);
@@ -537,6 +651,7 @@ static cudaError_t launch_bwd_strip(const SplatArgs &a, int gin_mode, int B, cud
   switch (gin_mode) {
     case 0: splat_bwd_strip_kernel<RPT, 0><<<grid, kThreads, 0, st>>>(a); break;
     case 1: splat_bwd_strip_kernel<RPT, 1><<<grid, kThreads, 0, st>>>(a); break;
+    case 3: splat_bwd_strip_kernel<RPT, 3><<<grid, kThreads, 0, st>>>(a); break;
     default: splat_bwd_strip_kernel<RPT, 2><<<grid, kThreads, 0, st>>>(a); break;
   }
   return cudaGetLastError();
@@ -629,6 +744,33 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
     }
   }
   return err;
+}
+
+// fused silhouette + L1 loss + backward, one launch (K <= kKBlock)
+int fused_loss_tiles(int K, int n) {
+  const int sizes[1] = {n}, zero[1] = {0}, one[1] = {1};
+  return plan_bwd_tiles(K, 1, sizes, zero, one, GG_LAYOUT_NHWC);
+}
+
+cudaError_t launch_silhouette_loss_fused(const float *params, const void *target, int target_kind, int B, int K, int n,
+                                         float *mask_out, float *partials, float *loss_partials, int T,
+                                         cudaStream_t st) {
+  if (K > kKBlock) return cudaErrorInvalidValue;
+  bool hm[1] = {false}, hk[1] = {true};
+  const int sizes[1] = {n};
+  Plan pl;
+  make_plan(pl, K, 1, sizes, hm, hk, GG_LAYOUT_NHWC, true);
+  if (pl.tiles_mask != T) return cudaErrorInvalidValue;
+  SplatArgs &a = pl.strip_mask;
+  a.params = params; a.partials = partials; a.B = B; a.K = K; a.T = T; a.slots = T; a.tile_offset = 0;
+  a.layout = GG_LAYOUT_NHWC;
+  a.sc[0].maps = nullptr;
+  a.sc[0].mask = mask_out;
+  a.target = target; a.target_kind = target_kind; a.inv_n = 1.0f / (float)((size_t)B * n * n);
+  a.loss_partials = loss_partials;
+  const int rpt = bwd_rpt();
+  return rpt == 1 ? launch_bwd_strip<1>(a, 3, B, st) : rpt == 4 ? launch_bwd_strip<4>(a, 3, B, st)
+                                                                : launch_bwd_strip<2>(a, 3, B, st);
 }
 
 }  // namespace gg

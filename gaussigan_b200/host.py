@@ -33,9 +33,9 @@ class HostInputs(NamedTuple):
 class StepResult:
     """Pinned host result buffers of one slot; valid after ``wait()``."""
 
-    def __init__(self, B, K, n, want_mask):
+    def __init__(self, B, K, n, want_mask, nloss):
         pin = dict(pin_memory=True)
-        self.loss_partials = torch.zeros(GG_LOSS_PARTIALS, dtype=torch.float32, **pin)
+        self.loss_partials = torch.zeros(nloss, dtype=torch.float32, **pin)
         self.dmus = torch.zeros((B, K, 3), dtype=torch.float32, **pin)
         self.dsigma = torch.zeros((B, K, 3, 3), dtype=torch.float64, **pin)
         self.drot = torch.zeros((B, 3), dtype=torch.float32, **pin)
@@ -56,8 +56,9 @@ class StepResult:
 
 
 class HostSilhouetteStep:
-    #: project_fwd, splat_fwd, mask_l1_loss_bwd, splat_bwd, project_bwd
-    LAUNCHES_PER_STEP = 5
+    #: K <= 64: project_fwd, silhouette_loss_fused, project_bwd; else project_fwd, splat_fwd, mask_l1_loss_bwd,
+    #: splat_bwd, project_bwd
+    LAUNCHES_PER_STEP = 3
 
     def __init__(self, B: int, K: int, size: int = 256, device="cuda", depth: int = 2,
                  tx: float = 0.0, ty: float = 0.0, tz: float = -2.0, focal: float = 1.0,
@@ -80,11 +81,13 @@ class HostSilhouetteStep:
         self.depth = int(depth)
         self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
         self.streams = [torch.cuda.Stream(dev) for _ in range(self.depth)]
-        self.results = [StepResult(self.B, self.K, self.n, want_mask) for _ in range(self.depth)]
+        self.nloss = check(lib.gg_silhouette_step_loss_count(self.B, self.K, self.n), "gg_silhouette_step_loss_count")
+        self.LAUNCHES_PER_STEP = 3 if self.K <= 64 else 5
+        self.results = [StepResult(self.B, self.K, self.n, want_mask, self.nloss) for _ in range(self.depth)]
         self._next = 0
         tb = 1 if self.kind == GG_TARGET_U8 else 4
         self.h2d_bytes = B * K * 3 * 4 + B * K * 9 * 8 + 3 * B * 4 + B * size * size * tb
-        self.d2h_bytes = (GG_LOSS_PARTIALS * 4 + B * K * 3 * 4 + B * K * 9 * 8 + B * 3 * 4
+        self.d2h_bytes = (self.nloss * 4 + B * K * 3 * 4 + B * K * 9 * 8 + B * 3 * 4
                           + (B * size * size * 4 if want_mask else 0))
 
     def make_host_inputs(self, inp: dict, target_pm1: torch.Tensor) -> HostInputs:

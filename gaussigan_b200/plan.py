@@ -114,3 +114,60 @@ class SilhouetteStep:
             self.backward(gmask)
         self.graph = g
         return g
+
+
+class SilhouetteLossStep(SilhouetteStep):
+    """``SilhouetteStep`` with the consumer fused in: projection -> ONE kernel that renders the silhouette,
+    evaluates ``mean|0.5*(target+1) - silhouette|`` (mask/mask_gen_dynamic.py:785-787), forms its gradient and
+    runs the splat backward -> projection adjoint.  The silhouette and dL/dmask never reach HBM.  K <= 64.
+
+        step = SilhouetteLossStep(B, K, size, device)
+        step.bind(mus, sigma, rotx, roty, rotz)
+        dmus, dsigma, drot = step.loss_backward(target)     # target [B,n,n] uint8 (raw 0..255) or f32 in [-1,1]
+        step.loss()                                          # float (synchronises)
+    """
+
+    LAUNCHES_PER_STEP = 3
+
+    def __init__(self, *a, want_mask: bool = False, **kw):
+        super().__init__(*a, **kw)
+        if self.K > 64:
+            raise ValueError("the fused loss kernel handles K <= 64")
+        self.loss_partials = torch.empty(self.B * self.T, dtype=torch.float32, device=self.dev)
+        self.want_mask = want_mask
+
+    def loss_backward(self, target: torch.Tensor):
+        assert target.is_cuda and target.is_contiguous() and target.numel() == self.B * self.n * self.n
+        assert target.dtype in (torch.uint8, torch.float32)
+        kind = 0 if target.dtype == torch.uint8 else 1
+        mus, sigma, rotx, roty, rotz = self._inputs
+        st = self._stream()
+        check(lib.gg_project_fwd(mus.data_ptr(), sigma.data_ptr(), self.sigma_f64, rotx.data_ptr(),
+                                 roty.data_ptr(), rotz.data_ptr(), *self.t, self.focal, self.B, self.K,
+                                 None, None, self.params.data_ptr(), self.dev.index, st), "gg_project_fwd")
+        check(lib.gg_silhouette_loss_fused(self.params.data_ptr(), target.data_ptr(), kind, self.B, self.K, self.n,
+                                           self.mask.data_ptr() if self.want_mask else None,
+                                           self.partials.data_ptr(), self.T, self.loss_partials.data_ptr(),
+                                           self.dev.index, st), "gg_silhouette_loss_fused")
+        check(lib.gg_project_bwd(mus.data_ptr(), sigma.data_ptr(), self.sigma_f64, rotx.data_ptr(),
+                                 roty.data_ptr(), rotz.data_ptr(), *self.t, self.focal, self.B, self.K,
+                                 self.partials.data_ptr(), self.T, None, None, self.dmus.data_ptr(),
+                                 self.dsigma.data_ptr(), self.drot.data_ptr(), self.dev.index, st),
+              "gg_project_bwd")
+        return self.dmus, self.dsigma, self.drot
+
+    def loss(self) -> float:
+        return float(self.loss_partials.double().sum().item() / (self.B * self.n * self.n))
+
+    def capture_loss(self, target: torch.Tensor) -> torch.cuda.CUDAGraph:
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self.loss_backward(target)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.loss_backward(target)
+        self.graph = g
+        return g

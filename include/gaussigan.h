@@ -125,6 +125,14 @@ GG_API int gg_splat_bwd(const float *params, int B, int K, int nscales, const in
 GG_API int gg_mask_l1_loss_bwd(const float *mask, const void *target, int target_kind, int B, int n,
                                float *gmask, float *loss_partials, int device, void *stream);
 
+/* Fused form of gg_splat_fwd(mask) + gg_mask_l1_loss_bwd + gg_splat_bwd(gmask) for one scale: the silhouette and
+ * its gradient stay in registers (mask/mask_gen_dynamic.py:785-787 and their gradients in ONE launch).  Requires
+ * K <= 64.  T = gg_splat_bwd_tiles(K, 1, {n}, {0}, {1}, NHWC).  Outputs: partials [B,T,K,GG_MOMENTS] (feed
+ * gg_project_bwd), loss_partials [B*T] (loss = sum / (B*n*n)), and, if mask_out != NULL, the silhouette [B,n,n]. */
+GG_API int gg_silhouette_loss_fused(const float *params, const void *target, int target_kind, int B, int K, int n,
+                                    float *mask_out, float *partials, int T, float *loss_partials,
+                                    int device, void *stream);
+
 /* ---- whole training-style step on HOST buffers ---------------------------------------------------
  * What a host-language binding of the reference would call (the reference feeds numpy arrays through
  * session.run, mask/infer_masks.py:435-456): H2D of the inputs, projection, splat (silhouette), L1 loss and its
@@ -132,8 +140,11 @@ GG_API int gg_mask_l1_loss_bwd(const float *mask, const void *target, int target
  * `stream`, no synchronisation.  *_host pointers are HOST memory (pinned for true asynchrony); `workspace` is
  * DEVICE memory of at least gg_silhouette_step_workspace_bytes(...) bytes, 256-byte aligned, owned by the
  * caller and private to this call until the stream has drained.  mask_host may be NULL (silhouette not
- * copied back).  sigma_host is float64 [B,K,3,3]. */
+ * copied back).  sigma_host is float64 [B,K,3,3].  loss_partials_host receives
+ * gg_silhouette_step_loss_count(B, K, n) floats; loss = sum(partials) / (B*n*n).  For K <= 64 the step is three
+ * launches (projection, fused splat+loss+backward, projection adjoint), otherwise five. */
 GG_API size_t gg_silhouette_step_workspace_bytes(int B, int K, int n, int target_kind);
+GG_API int gg_silhouette_step_loss_count(int B, int K, int n);
 GG_API int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, const float *rotx_host,
                                    const float *roty_host, const float *rotz_host, const void *target_host,
                                    int target_kind, double tx, double ty, double tz, double focal,

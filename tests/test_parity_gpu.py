@@ -290,3 +290,69 @@ def test_projection_outputs_match_oracle_to_float64_roundoff(gg, cuda_device):
     rmu, rs = rp.project(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0.3, -0.1, -2.4, 1.7)
     assert mu2d.dtype == torch.float64
     assert (mu2d.cpu() - rmu).abs().max() < 1e-12 and max_rel(s2d, rs) < 1e-12
+
+
+# ------------------------------------------------------------------ fused consumers / host-buffer step
+@pytest.mark.parametrize("B,K,n,dtype", [(6, 16, 256, torch.uint8), (3, 6, 64, torch.float32), (2, 5, 100, torch.uint8),
+                                         (2, 64, 40, torch.float32)])
+def test_fused_silhouette_loss_step_vs_oracle(gg, cuda_device, B, K, n, dtype):
+    from gaussigan_b200.plan import SilhouetteLossStep
+    inp = rp.synth_inputs(B, K, seed=31 + K)
+    tgt = rp.synth_target_masks(B, n, seed=5)                  # {-1,+1}
+    if dtype == torch.uint8:
+        raw = ((tgt + 1.0) * 127.5).round().clamp(0, 255)
+        raw[:, ::7, ::5] = 93.0                                 # grey levels too, like a resized mask
+        tgt = raw / 127.5 - 1.0                                 # what the reference sees (:672)
+        dev_t = raw.reshape(B, n, n).to(torch.uint8).to(cuda_device)
+    else:
+        tgt = tgt * 0.8 + 0.1 * torch.randn(tgt.shape, generator=torch.Generator().manual_seed(1))
+        dev_t = tgt.reshape(B, n, n).float().contiguous().to(cuda_device)
+    mask_ref, loss_ref, dmu_ref, dsig_ref, drot_ref = rp.render_loss_and_grads(inp, tgt, n)
+    d = _dev(inp, cuda_device)
+    step = SilhouetteLossStep(B, K, n, cuda_device, want_mask=True)
+    step.bind(d["mus"].reshape(B, K, 3).contiguous(), d["sigma"], *(d[k].reshape(B).contiguous() for k in ("rotx", "roty", "rotz")))
+    dmus, dsig, drot = step.loss_backward(dev_t)
+    assert abs(step.loss() - float(loss_ref)) <= 2e-6 * abs(float(loss_ref))
+    assert_close_norm(step.mask, mask_ref, FWD_RTOL, "fused mask")
+    assert_close_norm(dmus, dmu_ref.reshape(B, K, 3), GRAD_RTOL, "fused dmus")
+    assert_close_norm(dsig, dsig_ref, GRAD_RTOL, "fused dsigma")
+    assert_close_norm(drot[:, 1], drot_ref.reshape(B), GRAD_RTOL, "fused droty")
+    # same numbers as the three-kernel path (splat fwd -> loss kernel -> splat bwd), bit for bit
+    plain = gg.render_silhouette(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., size=n)
+    assert torch.equal(plain, step.mask)
+
+
+def test_host_buffer_step_matches_oracle(gg, cuda_device):
+    from gaussigan_b200.host import HostSilhouetteStep
+    B, K, n = 8, 16, 128
+    inp = rp.synth_inputs(B, K, seed=77)
+    tgt = rp.synth_target_masks(B, n, seed=3)
+    mask_ref, loss_ref, dmu_ref, dsig_ref, drot_ref = rp.render_loss_and_grads(inp, tgt, n)
+    host = HostSilhouetteStep(B, K, n, cuda_device, depth=2, want_mask=True)
+    h = host.make_host_inputs(inp, tgt)
+    results = [host.submit(h) for _ in range(3)]               # reuses slots: exercises the back-pressure path
+    res = results[-1].wait()
+    assert abs(res.loss - float(loss_ref)) <= 2e-6 * abs(float(loss_ref))
+    assert_close_norm(res.mask, mask_ref, FWD_RTOL, "host mask")
+    assert_close_norm(res.dmus, dmu_ref.reshape(B, K, 3), GRAD_RTOL, "host dmus")
+    assert_close_norm(res.dsigma, dsig_ref, GRAD_RTOL, "host dsigma")
+    assert_close_norm(res.drot[:, 1], drot_ref.reshape(B), GRAD_RTOL, "host droty")
+    assert host.h2d_bytes == B * K * 3 * 4 + B * K * 9 * 8 + 3 * B * 4 + B * n * n and host.LAUNCHES_PER_STEP == 3
+
+
+def test_unfused_loss_kernel_matches_fused(gg, cuda_device):
+    """gg_mask_l1_loss_bwd (used when K > 64) against the oracle's loss and Abs gradient."""
+    from gaussigan_b200._lib import lib, check
+    B, n = 4, 64
+    g = torch.Generator().manual_seed(0)
+    mask = (torch.rand(B, n, n, generator=g) * 2).to(cuda_device)
+    raw = torch.randint(0, 256, (B, n, n), generator=g, dtype=torch.uint8)
+    gm = torch.empty_like(mask)
+    lp = torch.empty(296, device=cuda_device)
+    check(lib.gg_mask_l1_loss_bwd(mask.data_ptr(), raw.to(cuda_device).data_ptr(), 0, B, n, gm.data_ptr(), lp.data_ptr(),
+                                  0, torch.cuda.current_stream().cuda_stream), "loss")
+    m = mask.cpu().clone().requires_grad_(True)
+    loss = rp.mask_recon_loss_bis((raw.float() / 127.5 - 1.0).unsqueeze(-1), m.unsqueeze(-1).expand(B, n, n, 1))
+    loss.backward()
+    assert abs(float(lp.double().sum()) / (B * n * n) - float(loss)) < 1e-6
+    assert torch.equal(gm.cpu(), m.grad)

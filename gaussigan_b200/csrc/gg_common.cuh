@@ -22,7 +22,7 @@ constexpr int kKBlock = 64;            // Gaussians handled per CTA along grid.z
 // which is exp(-(a dx^2 + 2 b dx dy + c dy^2)) after completing the square along x.
 struct ScaleDesc {
   int n;           // image side
-  int spr;         // strips per row            = ceil(n / kStrip)
+  int spr;         // strips (threads) per row  = ceil(ceil(n/4) / 2); a strip = quads s and s + spr
   int sprc;        // strips per row per chunk  = min(spr, kThreads)
   int rpp;         // rows per pass of one CTA  = max(1, kThreads / spr)
   int chunks;      // column chunks             = ceil(spr / kThreads)

@@ -44,8 +44,15 @@ __device__ void make_cam(float rx_deg, float ry_deg, float rz_deg, Cam &cam) {
   float a[3] = {deg2rad_f32(rx_deg), deg2rad_f32(ry_deg), deg2rad_f32(rz_deg)};
 #pragma unroll
   for (int i = 0; i < 3; ++i) {   // correctly rounded float32 trig (oracle: cos_f32 / sin_f32)
-    cam.c[i] = (float)cos((double)a[i]);
-    cam.s[i] = (float)sin((double)a[i]);
+    if (a[i] == 0.0f) {           // every reference call site passes rotx = rotz = 0 (:706-709): exact, no trig
+      cam.c[i] = 1.0f;
+      cam.s[i] = 0.0f;
+    } else {
+      double sd, cd;
+      sincos((double)a[i], &sd, &cd);   // ~200 cycles each (tools/microbench/latency.cu)
+      cam.c[i] = (float)cd;
+      cam.s[i] = (float)sd;
+    }
   }
   const float cx = cam.c[0], sx = cam.s[0], cy = cam.c[1], sy = cam.s[1], cz = cam.c[2], sz = cam.s[2];
   // inner tf.stack lists are matrix COLUMNS (:246-252)
@@ -166,9 +173,19 @@ __device__ void stage_params(const double mu[2], const double sg[4], float *out)
 __device__ void conic_adjoint(const double mu[2], const double sg[4], const float *partials, int T,
                               size_t tile_stride, double gmu[2], double gsg[4]) {
   double Tm[GG_MOMENTS] = {0, 0, 0, 0, 0};
-  for (int t = 0; t < T; ++t) {                     // fixed order: deterministic
+  // fixed summation order (deterministic); loads are issued 8 tiles at a time so the T round trips to L2
+  // overlap instead of serialising (measured: 3200 -> ~900 cycles at T = 16)
+  for (int t0 = 0; t0 < T; t0 += 8) {
+    float v[8][GG_MOMENTS];
 #pragma unroll
-    for (int j = 0; j < GG_MOMENTS; ++j) Tm[j] += (double)partials[(size_t)t * tile_stride + j];
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int j = 0; j < GG_MOMENTS; ++j)
+        v[u][j] = (t0 + u < T) ? __ldg(partials + (size_t)(t0 + u) * tile_stride + j) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int j = 0; j < GG_MOMENTS; ++j) Tm[j] += (double)v[u][j];
   }
   double det2 = sg[0] * sg[3] - sg[1] * sg[2];
   double idet = 1.0 / det2;
@@ -215,12 +232,14 @@ __global__ void __launch_bounds__(128) project_fwd_kernel(
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * K) return;
   int b = idx / K;
-  Cam cam;
-  make_cam(rotx[b], roty[b], rotz[b], cam);
+  // issue every global load before the first use (one round trip instead of two)
+  const float rxd = __ldg(rotx + b), ryd = __ldg(roty + b), rzd = __ldg(rotz + b);
   Proj p;
   load_sigma(sigma, sigma_is_f64, idx, p.S);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) p.mu[i] = (double)mus[(size_t)idx * 3 + i];
+  for (int i = 0; i < 3; ++i) p.mu[i] = (double)__ldg(mus + (size_t)idx * 3 + i);
+  Cam cam;
+  make_cam(rxd, ryd, rzd, cam);
   const double t[3] = {tx, ty, tz};
   project_one(cam, t, (double)(float)focal, p);   // focal passes through float32 (:266, :271)
   if (mu2d) { mu2d[(size_t)idx * 2] = p.mu2d[0]; mu2d[(size_t)idx * 2 + 1] = p.mu2d[1]; }

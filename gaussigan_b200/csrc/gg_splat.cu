@@ -42,35 +42,14 @@ __device__ __forceinline__ int find_scale(const SplatArgs &a, int tile) {
   return si;
 }
 
-__device__ __forceinline__ void store8(float *p, int col0, int n, const float *v) {
-  if ((n & 3) == 0) {
-    if (col0 < n) st_f4(p, v[0], v[1], v[2], v[3]);
-    if (col0 + 4 < n) st_f4(p + 4, v[4], v[5], v[6], v[7]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < kStrip; ++j)
-      if (col0 + j < n) p[j] = v[j];
-  }
-}
-
-__device__ __forceinline__ void load8(const float *p, int col0, int n, float *v) {
-  if ((n & 3) == 0) {
-    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-    if (col0 < n) lo = __ldg(reinterpret_cast<const float4 *>(p));
-    if (col0 + 4 < n) hi = __ldg(reinterpret_cast<const float4 *>(p + 4));
-    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < kStrip; ++j) v[j] = (col0 + j < n) ? __ldg(p + j) : 0.f;
-  }
-}
-
-// thread -> strip geometry shared by the strip kernels
+// thread -> strip geometry shared by the strip kernels.  A strip is TWO quads of one row: pixels
+// [colA, colA+4) and [colB, colB+4) with colB = colA + 4*ceil(Q/2), Q = quads per row -- so that the 32
+// lanes of a warp-level 128-bit access touch one contiguous 512-byte run instead of every other 16 bytes.
 struct StripPos {
-  int col0;       // first pixel column of the strip
+  int colA, colB;
   int row0;       // row of pass r is row0 + r * rpp
   bool valid;
+  __device__ __forceinline__ int col(int j) const { return j < 4 ? colA + j : colB + (j - 4); }
 };
 
 __device__ __forceinline__ StripPos strip_pos(const ScaleDesc &s, int tile_local) {
@@ -80,10 +59,36 @@ __device__ __forceinline__ StripPos strip_pos(const ScaleDesc &s, int tile_local
   int rp = threadIdx.x / s.sprc;
   int sc = threadIdx.x - rp * s.sprc;
   int strip = ch * kThreads + sc;
-  p.col0 = strip * kStrip;
+  p.colA = strip * 4;
+  p.colB = (strip + s.spr) * 4;
   p.row0 = rt * s.rows_per_tile + rp;
   p.valid = (rp < s.rpp) && (strip < s.spr);
   return p;
+}
+
+// rowp = address of column 0 of the row
+__device__ __forceinline__ void store8(float *rowp, const StripPos &pos, int n, const float *v) {
+  if ((n & 3) == 0) {
+    if (pos.colA < n) st_f4(rowp + pos.colA, v[0], v[1], v[2], v[3]);
+    if (pos.colB < n) st_f4(rowp + pos.colB, v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j)
+      if (pos.col(j) < n) rowp[pos.col(j)] = v[j];
+  }
+}
+
+__device__ __forceinline__ void load8(const float *rowp, const StripPos &pos, int n, float *v) {
+  if ((n & 3) == 0) {
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    if (pos.colA < n) lo = __ldg(reinterpret_cast<const float4 *>(rowp + pos.colA));
+    if (pos.colB < n) hi = __ldg(reinterpret_cast<const float4 *>(rowp + pos.colB));
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j) v[j] = (pos.col(j) < n) ? __ldg(rowp + pos.col(j)) : 0.f;
+  }
 }
 
 }  // namespace
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_
 
   float x[kStrip];
 #pragma unroll
-  for (int j = 0; j < kStrip; ++j) x[j] = grid_coord(pos.col0 + j, s.step);
+  for (int j = 0; j < kStrip; ++j) x[j] = grid_coord(pos.col(j), s.step);
   float y[RPT];
   bool rv[RPT];
 #pragma unroll
@@ -155,15 +160,15 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_
       if (OUT == 1) {
         if (rv[r]) {
           int row = pos.row0 + r * s.rpp;
-          store8(s.maps + (((size_t)b * K + k) * n + row) * n + pos.col0, pos.col0, n, g);
+          store8(s.maps + (((size_t)b * K + k) * n + row) * n, pos, n, g);
         }
       } else if (OUT == 2) {
         if (rv[r]) {
           int row = pos.row0 + r * s.rpp;
-          float *q = s.maps + (((size_t)b * n + row) * n + pos.col0) * K + k;
+          float *q = s.maps + ((size_t)b * n + row) * n * K + k;
 #pragma unroll
           for (int j = 0; j < kStrip; ++j)
-            if (pos.col0 + j < n) q[(size_t)j * K] = g[j];
+            if (pos.col(j) < n) q[(size_t)pos.col(j) * K] = g[j];
         }
       }
     }
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_
     for (int r = 0; r < RPT; ++r) {
       if (!rv[r]) continue;
       int row = pos.row0 + r * s.rpp;
-      store8(s.mask + ((size_t)b * n + row) * n + pos.col0, pos.col0, n, acc[r]);
+      store8(s.mask + ((size_t)b * n + row) * n, pos, n, acc[r]);
     }
   }
 }
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
 
   float x[kStrip];
 #pragma unroll
-  for (int j = 0; j < kStrip; ++j) x[j] = grid_coord(pos.col0 + j, s.step);
+  for (int j = 0; j < kStrip; ++j) x[j] = grid_coord(pos.col(j), s.step);
   float y[RPT];
   bool rv[RPT];
   float gm[RPT][kStrip];
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
     y[r] = grid_coord(row, s.step);
 #pragma unroll
     for (int j = 0; j < kStrip; ++j) gm[r][j] = 0.f;
-    if (GIN != 3 && rv[r] && gmask) load8(gmask + ((size_t)b * n + row) * n + pos.col0, pos.col0, n, gm[r]);
+    if (GIN != 3 && rv[r] && gmask) load8(gmask + ((size_t)b * n + row) * n, pos, n, gm[r]);
   }
 
   if (GIN == 3) {
@@ -248,34 +253,35 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
     for (int r = 0; r < RPT; ++r) {
       if (!rv[r]) continue;
       const int row = pos.row0 + r * s.rpp;
-      const size_t off = ((size_t)b * n + row) * n + pos.col0;
-      if (gmask) store8(s.mask + off, pos.col0, n, gm[r]);         // optional silhouette output
+      const size_t off = ((size_t)b * n + row) * n;
+      if (gmask) store8(s.mask + off, pos, n, gm[r]);              // optional silhouette output
       float tg[kStrip];
       if (a.target_kind == GG_TARGET_U8) {
         const unsigned char *tp = reinterpret_cast<const unsigned char *>(a.target) + off;
-        if ((n & 7) == 0) {
-          const uint2 u = __ldg(reinterpret_cast<const uint2 *>(tp));
+        if ((n & 3) == 0) {
+          const unsigned ua = pos.colA < n ? __ldg(reinterpret_cast<const unsigned *>(tp + pos.colA)) : 0u;
+          const unsigned ub = pos.colB < n ? __ldg(reinterpret_cast<const unsigned *>(tp + pos.colB)) : 0u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            tg[j] = (float)((u.x >> (8 * j)) & 0xffu);
-            tg[j + 4] = (float)((u.y >> (8 * j)) & 0xffu);
+            tg[j] = (float)((ua >> (8 * j)) & 0xffu);
+            tg[j + 4] = (float)((ub >> (8 * j)) & 0xffu);
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < kStrip; ++j) tg[j] = (pos.col0 + j < n) ? (float)__ldg(tp + j) : 0.f;
+          for (int j = 0; j < kStrip; ++j) tg[j] = (pos.col(j) < n) ? (float)__ldg(tp + pos.col(j)) : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < kStrip; ++j)   // (raw/127.5 - 1 + 1) * 0.5, op by op as the reference (:672, :787)
           tg[j] = __fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(tg[j], 127.5f), 1.0f), 1.0f), 0.5f);
       } else {
-        load8(reinterpret_cast<const float *>(a.target) + off, pos.col0, n, tg);
+        load8(reinterpret_cast<const float *>(a.target) + off, pos, n, tg);
 #pragma unroll
         for (int j = 0; j < kStrip; ++j) tg[j] = __fmul_rn(__fadd_rn(tg[j], 1.0f), 0.5f);
       }
 #pragma unroll
       for (int j = 0; j < kStrip; ++j) {
         const float res = tg[j] - gm[r][j];
-        const bool in = pos.col0 + j < n;
+        const bool in = pos.col(j) < n;
         lsum += in ? fabsf(res) : 0.f;
         gm[r][j] = !in ? 0.f : (res > 0.f ? -a.inv_n : (res < 0.f ? a.inv_n : 0.f));
       }
@@ -294,10 +300,32 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
     __syncthreads();
   }
 
+  // NCHW upstream gradients are software-pipelined one Gaussian ahead: the 128-bit loads of k+1 are in
+  // flight while k is being evaluated (the loop is otherwise a load -> use chain per Gaussian).
+  float Gn[GIN == 1 ? RPT : 1][kStrip];
+  if (GIN == 1) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j) Gn[r][j] = 0.f;
+      if (rv[r]) load8(gmaps + (((size_t)b * K + k0) * n + pos.row0 + r * s.rpp) * n, pos, n, Gn[r]);
+    }
+  }
+
   for (int kk = 0; kk < kn; ++kk) {
     const float4 p = sp[2 * kk];
     const float nE = sp[2 * kk + 1].x;
     float T20 = 0.f, T11 = 0.f, T02 = 0.f, T10 = 0.f, T01 = 0.f;
+    float Gc[GIN == 1 ? RPT : 1][kStrip];
+    if (GIN == 1) {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+#pragma unroll
+        for (int j = 0; j < kStrip; ++j) Gc[r][j] = Gn[r][j] + gm[r][j];
+        if (rv[r] && kk + 1 < kn)
+          load8(gmaps + (((size_t)b * K + k0 + kk + 1) * n + pos.row0 + r * s.rpp) * n, pos, n, Gn[r]);
+      }
+    }
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       if (!rv[r]) continue;
@@ -306,16 +334,14 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < kStrip; ++j) G[j] = gm[r][j];
       } else if (GIN == 1) {
-        int row = pos.row0 + r * s.rpp;
-        load8(gmaps + (((size_t)b * K + k0 + kk) * n + row) * n + pos.col0, pos.col0, n, G);
 #pragma unroll
-        for (int j = 0; j < kStrip; ++j) G[j] += gm[r][j];
+        for (int j = 0; j < kStrip; ++j) G[j] = Gc[r][j];
       } else {
         int row = pos.row0 + r * s.rpp;
-        const float *q = gmaps + (((size_t)b * n + row) * n + pos.col0) * K + k0 + kk;
+        const float *q = gmaps + ((size_t)b * n + row) * n * K + k0 + kk;
 #pragma unroll
         for (int j = 0; j < kStrip; ++j)
-          G[j] = ((pos.col0 + j < n) ? __ldg(q + (size_t)j * K) : 0.f) + gm[r][j];
+          G[j] = ((pos.col(j) < n) ? __ldg(q + (size_t)pos.col(j) * K) : 0.f) + gm[r][j];
       }
       const float dy = y[r] - p.y;
       const float sh = fmaf(p.w, dy, p.x);
@@ -447,7 +473,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quad_kernel(const __grid_c
 
 // =============================================================================== backward, quads
 template <bool WITH_GMASK>
-__global__ void __launch_bounds__(kThreads) splat_bwd_quad_kernel(const __grid_constant__ SplatArgs a,
+__global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_kernel(const __grid_constant__ SplatArgs a,
                                                                   int kq_shift) {
   __shared__ float wsum[kWarps][32 * 4 * GG_MOMENTS];   // [warp][kq][i][moment], K*5 <= 640 floats used
 
@@ -491,23 +517,45 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_quad_kernel(const __grid_c
     const float *grow = s.maps + ((size_t)b * n + row) * n * K;
     const bool use_gmask = WITH_GMASK && s.mask != nullptr;
     const float *mrow = use_gmask ? s.mask + ((size_t)b * n + row) * n : nullptr;
-    for (int qq = threadIdx.x; qq < quads_per_row; qq += kThreads) {
-      const int col = qq >> kq_shift;
-      const float x = grid_coord(col, s.step);
-      float4 G = __ldg(reinterpret_cast<const float4 *>(grow + (size_t)qq * 4));
-      if (use_gmask) {
-        const float gmv = __ldg(mrow + col);
-        G.x += gmv; G.y += gmv; G.z += gmv; G.w += gmv;
-      }
-      const float Gv[4] = {G.x, G.y, G.z, G.w};
+    // batches of kUQ quads per thread: all 128-bit loads of a batch are issued before any use (MLP)
+    constexpr int kUQ = 4;
+    for (int q0 = threadIdx.x; q0 < quads_per_row; q0 += kUQ * kThreads) {
+      float4 G[kUQ];
+      float gmv[kUQ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float t = x - sh[i];
-        const float w = ex2_approx(fmaf(nA[i] * t, t, e[i])) * Gv[i];
-        const float wt = w * t;
-        S0[i] += w;
-        S1[i] += wt;
-        S2[i] = fmaf(wt, t, S2[i]);
+      for (int u = 0; u < kUQ; ++u) {
+        const int qq = q0 + u * kThreads;
+        G[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gmv[u] = 0.f;
+        if (qq < quads_per_row) {
+          G[u] = __ldg(reinterpret_cast<const float4 *>(grow + (size_t)qq * 4));
+          if (use_gmask) gmv[u] = __ldg(mrow + (qq >> kq_shift));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUQ; ++u) {
+        const int qq = q0 + u * kThreads;
+        const float x = grid_coord(qq >> kq_shift, s.step);
+        const f32x2 x2 = pack2(x, x);
+        const f32x2 gm2 = pack2(gmv[u], gmv[u]);
+        const f32x2 Ga = add2(pack2(G[u].x, G[u].y), gm2), Gb = add2(pack2(G[u].z, G[u].w), gm2);
+        // Gaussians (0,1) and (2,3) as packed pairs
+        const f32x2 ta = sub2(x2, pack2(sh[0], sh[1])), tb = sub2(x2, pack2(sh[2], sh[3]));
+        const f32x2 ua = mul2(ta, ta), ub = mul2(tb, tb);
+        float a0, a1, a2, a3;
+        unpack2(fma2(pack2(nA[0], nA[1]), ua, pack2(e[0], e[1])), a0, a1);
+        unpack2(fma2(pack2(nA[2], nA[3]), ub, pack2(e[2], e[3])), a2, a3);
+        const f32x2 wa = mul2(pack2(ex2_approx(a0), ex2_approx(a1)), Ga);
+        const f32x2 wb = mul2(pack2(ex2_approx(a2), ex2_approx(a3)), Gb);
+        f32x2 s0a = pack2(S0[0], S0[1]), s0b = pack2(S0[2], S0[3]);
+        f32x2 s1a = pack2(S1[0], S1[1]), s1b = pack2(S1[2], S1[3]);
+        f32x2 s2a = pack2(S2[0], S2[1]), s2b = pack2(S2[2], S2[3]);
+        s0a = add2(s0a, wa); s0b = add2(s0b, wb);
+        s1a = fma2(wa, ta, s1a); s1b = fma2(wb, tb, s1b);
+        s2a = fma2(wa, ua, s2a); s2b = fma2(wb, ub, s2b);
+        unpack2(s0a, S0[0], S0[1]); unpack2(s0b, S0[2], S0[3]);
+        unpack2(s1a, S1[0], S1[1]); unpack2(s1b, S1[2], S1[3]);
+        unpack2(s2a, S2[0], S2[1]); unpack2(s2b, S2[2], S2[3]);
       }
     }
 #pragma unroll
@@ -549,7 +597,7 @@ int env_int(const char *name, int dflt) {
 
 void strip_geometry(ScaleDesc &d, int n, int rpt) {
   d.n = n;
-  d.spr = (n + kStrip - 1) / kStrip;
+  d.spr = ((n + 3) / 4 + 1) / 2;     // threads per row: half the quads, each thread takes quad s and s + spr
   d.sprc = d.spr < kThreads ? d.spr : kThreads;
   d.rpp = d.spr <= kThreads ? kThreads / d.spr : 1;
   d.chunks = (d.spr + kThreads - 1) / kThreads;

@@ -9,6 +9,12 @@ from ._lib import GaussiganError, lib as _capi  # noqa: F401  (import = load the
 from .renderer import (REFERENCE_SIZES, get_gaussian_maps_2d, get_landmarks, get_landmarks_infer,
                        get_landmarks_with_mask, project, render_silhouette)
 
-__all__ = ["REFERENCE_SIZES", "GaussiganError", "get_gaussian_maps_2d", "get_landmarks", "get_landmarks_infer",
+from .consumers import (colorize_gaussians, colorize_landmark_maps, gm_cycle_loss, mask_recon_loss_bis,  # noqa: E402
+                        turntable)
+from .interchange import decoder_feed, load_reference_gaussians, save_reference_gaussians  # noqa: E402
+
+__all__ = ["colorize_gaussians", "colorize_landmark_maps", "gm_cycle_loss", "mask_recon_loss_bis", "turntable",
+           "decoder_feed", "load_reference_gaussians", "save_reference_gaussians",
+           "REFERENCE_SIZES", "GaussiganError", "get_gaussian_maps_2d", "get_landmarks", "get_landmarks_infer",
            "get_landmarks_with_mask", "project", "render_silhouette"]
 __version__ = "0.1.0"

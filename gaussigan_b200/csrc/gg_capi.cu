@@ -170,6 +170,48 @@ int gg_silhouette_loss_fused(const float *params, const void *target, int target
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_silhouette_loss_fused");
 }
 
+int gg_cycle_tiles(int n) {
+  if (n < 1 || n > 16384) return fail(GG_E_SHAPE, "n=%d out of range", n);
+  return gg::cycle_tiles(n);
+}
+
+int gg_cycle_loss_count(int B, int K, int n) {
+  if (B < 0 || K <= 0 || n < 1 || n > 16384) return fail(GG_E_SHAPE, "bad B/K/n");
+  return B * gg::cycle_tiles(n) * ((K + 31) / 32);
+}
+
+int gg_cycle_l1_fused(const float *params_a, const float *params_b, int B, int K, int n, float *partials_a,
+                      float *partials_b, int T, float *loss_partials, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  const int sizes[1] = {n};
+  if (int r = check_scales(K, 1, sizes)) return r;
+  if (B == 0) return GG_OK;
+  if (!params_a || !params_b || !partials_a || !partials_b || !loss_partials)
+    return fail(GG_E_NULL, "gg_cycle_l1_fused: NULL pointer");
+  if (!aligned16(params_a) || !aligned16(params_b)) return fail(GG_E_ALIGN, "gg_cycle_l1_fused: params must be 16-byte aligned");
+  if (T != gg::cycle_tiles(n)) return fail(GG_E_WORKSPACE, "gg_cycle_l1_fused: T=%d, expected %d", T, gg::cycle_tiles(n));
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_cycle_l1_fused(params_a, params_b, B, K, n, partials_a, partials_b, loss_partials, T,
+                                            (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_cycle_l1_fused");
+}
+
+int gg_colorize(const float *params, const float *maps, const float *colors, int B, int K, int n, void *out,
+                int out_mode, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (n < 1 || n > 16384) return fail(GG_E_SHAPE, "n=%d out of range", n);
+  if (out_mode < 0 || out_mode > 2) return fail(GG_E_SHAPE, "unknown out_mode %d", out_mode);
+  if (B == 0) return GG_OK;
+  if ((params == nullptr) == (maps == nullptr)) return fail(GG_E_NULL, "gg_colorize: exactly one of params / maps");
+  if (!colors || !out) return fail(GG_E_NULL, "gg_colorize: NULL pointer");
+  if (params && (!aligned16(params) || K > 1024)) return fail(GG_E_ALIGN, "gg_colorize: params alignment / K <= 1024");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = params ? gg::launch_colorize_params(params, colors, B, K, n, out, out_mode, (cudaStream_t)stream)
+                         : gg::launch_colorize_maps(maps, colors, (size_t)B * n * n, K, out, out_mode,
+                                                    (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_colorize");
+}
+
 int gg_splat_bwd_tiles(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,
                        const int *has_gmasks_host, int layout) {
   if (K <= 0) return fail(GG_E_SHAPE, "K must be > 0");

@@ -30,6 +30,20 @@ cudaError_t launch_silhouette_loss_fused(const float *params, const void *target
                                          float *mask_out, float *partials, float *loss_partials, int T,
                                          cudaStream_t st);
 
+struct ScaleDesc;
+void make_strip_desc(ScaleDesc &d, int n, int rpt);
+int bwd_rpt();
+int fwd_rpt();
+
+// fused cycle L1 between two renders (mask/mask_gen_dynamic.py:791) and the viz composite (:221-231)
+int cycle_tiles(int n);
+cudaError_t launch_cycle_l1_fused(const float *params_a, const float *params_b, int B, int K, int n, float *partials_a,
+                                  float *partials_b, float *loss_partials, int T, cudaStream_t st);
+cudaError_t launch_colorize_params(const float *params, const float *colors, int B, int K, int n, void *out,
+                                   int out_u8, cudaStream_t st);
+cudaError_t launch_colorize_maps(const float *maps, const float *colors, size_t npix, int K, void *out, int out_u8,
+                                 cudaStream_t st);
+
 namespace api {   // error/validation helpers shared by the extern "C" translation units (gg_capi.cu)
 int fail(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *where);

@@ -133,6 +133,29 @@ GG_API int gg_silhouette_loss_fused(const float *params, const void *target, int
                                     float *mask_out, float *partials, int T, float *loss_partials,
                                     int device, void *stream);
 
+/* ---- direct consumer: cycle L1 between two renders ----------------------------------------------------
+ * Replaces `gm_cycle_loss = reduce_mean(|pose_embeddings[-1] - pose_embeddings_cyc[-1]|)`
+ * (mask/mask_gen_dynamic.py:791) AND its gradient into both renders, without materialising either
+ * [B,n,n,K] tensor.  params_a / params_b: two staged projections of the same B, K.  T = gg_cycle_tiles(n).
+ * Outputs: partials_a, partials_b [B,T,K,GG_MOMENTS] (moments of d loss / d maps, feed gg_project_bwd of each
+ * side) and loss_partials [gg_cycle_loss_count(B,K,n)] with loss = sum(partials) / (B*n*n*K). */
+GG_API int gg_cycle_tiles(int n);
+GG_API int gg_cycle_loss_count(int B, int K, int n);
+GG_API int gg_cycle_l1_fused(const float *params_a, const float *params_b, int B, int K, int n,
+                             float *partials_a, float *partials_b, int T, float *loss_partials,
+                             int device, void *stream);
+
+/* ---- viz composite -----------------------------------------------------------------------------------
+ * Replaces colorize_landmark_maps (mask/mask_gen_dynamic.py:221-231, mask/infer_masks.py:174-184):
+ * rgb = max_k maps[...,k] * colors[k].  Exactly one of `params` ([B,K,GG_PARAM_STRIDE], maps never written) and
+ * `maps` (NHWC [B,n,n,K]) is non-NULL.  colors [K,3] f32 (device).  out [B,n,n,3]: GG_RGB_F32, GG_RGB_U8
+ * (uint8(rgb*255), numpy truncation) or GG_RGB_U8_INV (255 - that: the frames of infer_masks.py:463). */
+#define GG_RGB_F32 0
+#define GG_RGB_U8 1
+#define GG_RGB_U8_INV 2
+GG_API int gg_colorize(const float *params, const float *maps, const float *colors, int B, int K, int n,
+                       void *out, int out_mode, int device, void *stream);
+
 /* ---- whole training-style step on HOST buffers ---------------------------------------------------
  * What a host-language binding of the reference would call (the reference feeds numpy arrays through
  * session.run, mask/infer_masks.py:435-456): H2D of the inputs, projection, splat (silhouette), L1 loss and its

@@ -356,3 +356,95 @@ def test_unfused_loss_kernel_matches_fused(gg, cuda_device):
     loss.backward()
     assert abs(float(lp.double().sum()) / (B * n * n) - float(loss)) < 1e-6
     assert torch.equal(gm.cpu(), m.grad)
+
+
+# ---------------------------------------------------------------- consumers
+def test_mask_recon_loss_bis_autograd(gg, cuda_device):
+    B, K, n = 5, 12, 128
+    inp = rp.synth_inputs(B, K, seed=19, angle=20.0)
+    tgt = rp.synth_target_masks(B, n, seed=8)
+    lv = _leaves(inp)
+    maps = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0, 0, -2., sizes=(n,))[0]
+    (3.0 * rp.mask_recon_loss_bis(tgt, maps)).backward()
+    dv = _leaves(inp, cuda_device)
+    loss = gg.mask_recon_loss_bis(tgt.to(cuda_device), dv["mus"], dv["sigma"], dv["rotx"], dv["roty"], dv["rotz"],
+                                  0, 0, -2., size=n)
+    (3.0 * loss).backward()
+    assert abs(loss.item() - rp.mask_recon_loss_bis(tgt, maps).item()) < 2e-6 * abs(loss.item())
+    for k in ("mus", "sigma", "roty"):
+        assert_close_norm(dv[k].grad, lv[k].grad, GRAD_RTOL, "loss_bis grad " + k)
+
+
+@pytest.mark.parametrize("B,K,n", [(4, 16, 256), (2, 6, 64), (2, 40, 48), (1, 3, 100)])
+def test_gm_cycle_loss_vs_oracle(gg, cuda_device, B, K, n):
+    ia = rp.synth_inputs(B, K, seed=40 + K, angle=10.0)
+    ib = {k: v.clone() for k, v in ia.items()}
+    g = torch.Generator().manual_seed(2)
+    ib["mus"] = ib["mus"] + 0.05 * torch.randn(ib["mus"].shape, generator=g)       # the cycle render is a perturbation
+    ib["roty"] = ib["roty"] + 5.0 * torch.randn(ib["roty"].shape, generator=g)
+    ib["sigma"] = ib["sigma"] * (1.0 + 0.1 * torch.rand(B, K, 1, 1, generator=g, dtype=torch.float64))
+    la, lb = _leaves(ia), _leaves(ib)
+    ma = rp.get_landmarks(la["mus"], la["sigma"], la["rotx"], la["roty"], la["rotz"], 0, 0, -2., sizes=(n,))[0]
+    mb = rp.get_landmarks(lb["mus"], lb["sigma"], lb["rotx"], lb["roty"], lb["rotz"], 0, 0, -2., sizes=(n,))[0]
+    ref = rp.gm_cycle_loss(ma, mb)
+    ref.backward()
+    da, db = _leaves(ia, cuda_device), _leaves(ib, cuda_device)
+    order = ("mus", "sigma", "rotx", "roty", "rotz")
+    loss = gg.gm_cycle_loss([da[k] for k in order], [db[k] for k in order], 0, 0, -2., size=n)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 3e-6 * abs(ref.item())
+    for k in ("mus", "sigma", "roty"):
+        assert_close_norm(da[k].grad, la[k].grad, GRAD_RTOL, "cycle grad a." + k)
+        assert_close_norm(db[k].grad, lb[k].grad, GRAD_RTOL, "cycle grad b." + k)
+
+
+def test_colorize_both_sources(gg, cuda_device):
+    B, K, n = 3, 6, 64
+    inp = rp.synth_inputs(B, K, seed=3)
+    colors = torch.rand(K, 3, generator=torch.Generator().manual_seed(0))
+    maps = rp.get_landmarks(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0, 0, -2., sizes=(n,))[0]
+    ref = rp.colorize_landmark_maps(maps, colors)
+    d = _dev(inp, cuda_device)
+    a = gg.colorize_landmark_maps(maps.to(cuda_device), colors.to(cuda_device))
+    assert torch.equal(a.cpu(), ref)                                   # same float32 products and max
+    b = gg.colorize_gaussians(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., colors.to(cuda_device), size=n)
+    assert_close_norm(b, ref, FWD_RTOL, "colorize from Gaussians")
+    u = gg.colorize_landmark_maps(maps.to(cuda_device), colors.to(cuda_device), out="u8_inv")
+    expect = 255 - (ref.numpy() * 255).astype(np.uint8)               # mask/infer_masks.py:463
+    assert u.dtype == torch.uint8 and np.array_equal(u.cpu().numpy(), expect)
+
+
+def test_turntable_matches_per_angle_reference_loop(gg, cuda_device):
+    K, n = 6, 256
+    g = rp.synth_inputs(1, K, seed=56)
+    colors = torch.rand(K, 3, generator=torch.Generator().manual_seed(1))
+    angles = np.linspace(0.0, 120.0, 7)                                # the reference uses 60 (infer_masks.py:426-428)
+    theta0 = torch.tensor([[17.5]])
+    out = gg.turntable(g["mus"].to(cuda_device), g["sigma"].to(cuda_device), theta0, angles, colors.to(cuda_device),
+                       want_maps=True)
+    assert tuple(out["frames"].shape) == (7, n, n, 3) and out["frames"].dtype == torch.uint8
+    for f, x in enumerate(angles):                                      # the reference's loop body, one angle at a time
+        xr = torch.tensor([[x]], dtype=torch.float32)
+        z = torch.zeros_like(xr)
+        mu2d, s2d, gm = rp.get_landmarks_infer(g["mus"], g["sigma"], z, theta0[0, 0] + xr * 1., z, 0., 0., -2.)
+        np.testing.assert_array_equal(out["mu2d"][f:f + 1].cpu().numpy(), mu2d.numpy())
+        np.testing.assert_array_equal(out["sigma2d"][f:f + 1].cpu().numpy(), s2d.numpy())
+        assert_close_norm(out["maps"][f:f + 1], gm, FWD_RTOL, "turntable maps")
+        frame = 255 - (rp.colorize_landmark_maps(gm, colors).numpy() * 255).astype(np.uint8)
+        diff = np.abs(out["frames"][f:f + 1].cpu().numpy().astype(int) - frame.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3            # uint8 truncation of values 1e-7 apart
+
+
+def test_interchange_roundtrip(gg, cuda_device, tmp_path):
+    K = 12
+    g = rp.synth_inputs(1, K, seed=9)
+    m_path, s_path = gg.save_reference_gaussians(g["mus"], g["sigma"], str(tmp_path), 3)
+    assert m_path.endswith("m_3.npy") and s_path.endswith("sig3d_3.npy")
+    assert np.load(m_path).shape == (1, K, 1, 3) and np.load(m_path).dtype == np.float32      # infer_masks.py:447
+    assert np.load(s_path).shape == (1, K, 3, 3) and np.load(s_path).dtype == np.float64      # infer_masks.py:448
+    mu, sig = gg.load_reference_gaussians(m_path, s_path, cuda_device)
+    assert torch.equal(mu.cpu(), g["mus"]) and torch.equal(sig.cpu(), g["sigma"])
+    z = torch.zeros(1, 1, device=cuda_device)
+    mu2d, s2d, _ = gg.get_landmarks_infer(mu, sig, z, z + 30., z, 0., 0., -2.)
+    feed = gg.decoder_feed(mu2d, s2d)
+    assert feed["gen/genlandmarks/mu2d:0"].shape == (1, K, 2) and feed["gen/genlandmarks/sigma2d:0"].dtype == np.float32

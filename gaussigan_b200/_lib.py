@@ -50,6 +50,10 @@ SIGNATURES = {
     "gg_splat_bwd_tiles": (_i, [_i, _i, _ip, _ip, _ip, _i]),
     "gg_mask_l1_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "gg_silhouette_loss_fused": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "gg_sigma_from_frame_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "gg_sigma_from_frame_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "gg_deform_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "gg_deform_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "gg_cycle_tiles": (_i, [_i]),
     "gg_cycle_loss_count": (_i, [_i, _i, _i]),
     "gg_cycle_l1_fused": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),

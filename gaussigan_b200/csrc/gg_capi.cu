@@ -212,6 +212,52 @@ int gg_colorize(const float *params, const float *maps, const float *colors, int
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_colorize");
 }
 
+int gg_sigma_from_frame_fwd(const float *v0, const float *v1, const float *u, int N, double *sigma, int device,
+                            void *stream) {
+  if (N < 0) return fail(GG_E_SHAPE, "N < 0");
+  if (N == 0) return GG_OK;
+  if (!v0 || !v1 || !u || !sigma) return fail(GG_E_NULL, "gg_sigma_from_frame_fwd: NULL pointer");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_sigma_from_frame_fwd(v0, v1, u, N, sigma, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_sigma_from_frame_fwd");
+}
+
+int gg_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, const double *gsigma, int N, float *dv0,
+                            float *dv1, float *du, int device, void *stream) {
+  if (N < 0) return fail(GG_E_SHAPE, "N < 0");
+  if (N == 0) return GG_OK;
+  if (!v0 || !v1 || !u || !gsigma || !dv0 || !dv1 || !du) return fail(GG_E_NULL, "gg_sigma_from_frame_bwd: NULL pointer");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_sigma_from_frame_bwd(v0, v1, u, gsigma, N, dv0, dv1, du, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_sigma_from_frame_bwd");
+}
+
+int gg_deform_fwd(const float *mu_t, const float *scale, const float *ang, const float *cmu, const double *U,
+                  const double *S, const float *theta_raw, int B, int K, float *mus, double *sigmas, float *theta,
+                  int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (B == 0) return GG_OK;
+  if (!mu_t || !scale || !ang || !cmu || !U || !S || !mus || !sigmas) return fail(GG_E_NULL, "gg_deform_fwd: NULL pointer");
+  if ((theta == nullptr) != (theta_raw == nullptr)) return fail(GG_E_NULL, "gg_deform_fwd: theta and theta_raw go together");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_deform_fwd(mu_t, scale, ang, cmu, U, S, theta_raw, B, K, mus, sigmas, theta,
+                                        (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_deform_fwd");
+}
+
+int gg_deform_bwd(const float *scale, const float *ang, const double *U, const double *S, const float *gmus,
+                  const double *gsig, const float *gtheta, int B, int K, float *dtheta_raw, float *dmu_t,
+                  float *dscale, float *dang, float *dcmu, double *dU, double *dS, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (B == 0) return GG_OK;
+  if (!scale || !ang || !U || !S || !dmu_t || !dscale || !dang || !dcmu || !dU || !dS)
+    return fail(GG_E_NULL, "gg_deform_bwd: NULL pointer");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_deform_bwd(scale, ang, U, S, gmus, gsig, gtheta, B, K, dtheta_raw, dmu_t, dscale, dang,
+                                        dcmu, dU, dS, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_deform_bwd");
+}
+
 int gg_splat_bwd_tiles(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,
                        const int *has_gmasks_host, int layout) {
   if (K <= 0) return fail(GG_E_SHAPE, "K must be > 0");

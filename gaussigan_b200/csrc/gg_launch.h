@@ -44,6 +44,17 @@ cudaError_t launch_colorize_params(const float *params, const float *colors, int
 cudaError_t launch_colorize_maps(const float *maps, const float *colors, size_t npix, int K, void *out, int out_u8,
                                  cudaStream_t st);
 
+cudaError_t launch_sigma_from_frame_fwd(const float *v0, const float *v1, const float *u, int N, double *sigma,
+                                        cudaStream_t st);
+cudaError_t launch_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, const double *gsigma, int N,
+                                        float *dv0, float *dv1, float *du, cudaStream_t st);
+cudaError_t launch_deform_fwd(const float *mu_t, const float *sc, const float *ang, const float *cmu, const double *U,
+                              const double *S, const float *theta_raw, int B, int K, float *mus, double *sigmas,
+                              float *theta, cudaStream_t st);
+cudaError_t launch_deform_bwd(const float *sc, const float *ang, const double *U, const double *S, const float *gmus,
+                              const double *gsig, const float *gtheta, int B, int K, float *dtheta_raw, float *dmu_t,
+                              float *dsc, float *dang, float *dcmu, double *dU, double *dS, cudaStream_t st);
+
 namespace api {   // error/validation helpers shared by the extern "C" translation units (gg_capi.cu)
 int fail(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *where);

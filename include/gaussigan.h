@@ -156,6 +156,27 @@ GG_API int gg_cycle_l1_fused(const float *params_a, const float *params_b, int B
 GG_API int gg_colorize(const float *params, const float *maps, const float *colors, int B, int K, int n,
                        void *out, int out_mode, int device, void *stream);
 
+/* ---- Gaussian construction and per-frame deformation ---------------------------------------------------
+ * gg_sigma_from_frame_*: tail of get_musigma (mask/mask_gen_dynamic.py:383-401).  v0, v1 [N,3] f32 (tanh outputs),
+ * u [N,3] f32 (pre-sigmoid) -> sigma [N,3,3] f64 = V diag(0.5*sigmoid(u)+0.01) V^T built in float32.
+ * Backward: gsigma [N,3,3] f64 -> dv0, dv1, du [N,3] f32. */
+GG_API int gg_sigma_from_frame_fwd(const float *v0, const float *v1, const float *u, int N, double *sigma,
+                                   int device, void *stream);
+GG_API int gg_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, const double *gsigma, int N,
+                                   float *dv0, float *dv1, float *du, int device, void *stream);
+/* gg_deform_*: tail of transform_mu_sigma (mask/mask_gen_dynamic.py:426-458).  Head outputs AFTER tanh, f32:
+ * mu_t [B,K,3], scale [B,K,3], ang [B,K,3] (x,y,z), theta_raw [B]; canonical cmu [K,3] f32 and the SVD factors
+ * U [K,3,3], S [K,3] (float64) of the canonical covariances (the SVD itself, :430, stays with the caller).
+ * -> mus [B,K,3] f32, sigmas [B,K,3,3] f64, theta [B] f32 (degrees).
+ * Backward returns PER-SAMPLE gradients for the broadcast canonical parameters (dcmu [B,K,3] f32, dU [B,K,3,3],
+ * dS [B,K,3] f64): the caller sums them over the batch.  gmus / gsig / gtheta may be NULL (treated as zero). */
+GG_API int gg_deform_fwd(const float *mu_t, const float *scale, const float *ang, const float *cmu, const double *U,
+                         const double *S, const float *theta_raw, int B, int K, float *mus, double *sigmas,
+                         float *theta, int device, void *stream);
+GG_API int gg_deform_bwd(const float *scale, const float *ang, const double *U, const double *S, const float *gmus,
+                         const double *gsig, const float *gtheta, int B, int K, float *dtheta_raw, float *dmu_t,
+                         float *dscale, float *dang, float *dcmu, double *dU, double *dS, int device, void *stream);
+
 /* ---- whole training-style step on HOST buffers ---------------------------------------------------
  * What a host-language binding of the reference would call (the reference feeds numpy arrays through
  * session.run, mask/infer_masks.py:435-456): H2D of the inputs, projection, splat (silhouette), L1 loss and its

@@ -448,3 +448,79 @@ def test_interchange_roundtrip(gg, cuda_device, tmp_path):
     mu2d, s2d, _ = gg.get_landmarks_infer(mu, sig, z, z + 30., z, 0., 0., -2.)
     feed = gg.decoder_feed(mu2d, s2d)
     assert feed["gen/genlandmarks/mu2d:0"].shape == (1, K, 2) and feed["gen/genlandmarks/sigma2d:0"].dtype == np.float32
+
+
+# --------------------------------------------------- Gaussian construction / deformation
+def test_sigma_from_frame_vs_oracle(gg, cuda_device):
+    g = torch.Generator().manual_seed(11)
+    N, K = 3, 16
+    raw = [torch.tanh(torch.randn(N, K, 3, generator=g)), torch.tanh(torch.randn(N, K, 3, generator=g)),
+           torch.randn(N, K, 3, generator=g)]
+    ref_in = [t.clone().requires_grad_(True) for t in raw]
+    ref = rp.sigma_from_frame(*ref_in)
+    w = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * w).sum().backward()
+    dev_in = [t.to(cuda_device).requires_grad_(True) for t in raw]
+    out = gg.sigma_from_frame(*dev_in)
+    assert out.dtype == torch.float64 and out.shape == ref.shape
+    assert_close_norm(out, ref, 1e-6, "sigma_from_frame (float32 arithmetic, 1-2 ulp of sigmoid/rsqrt)")
+    (out * w.to(cuda_device)).sum().backward()
+    for a, b, nm in zip(dev_in, ref_in, ("v0", "v1", "u")):
+        assert_close_norm(a.grad, b.grad, GRAD_RTOL, "sigma_from_frame grad " + nm)
+
+
+def test_deform_vs_oracle(gg, cuda_device):
+    B, K = 5, 12
+    g = torch.Generator().manual_seed(21)
+    th = lambda *s: torch.tanh(torch.randn(*s, generator=g))
+    cann = rp.synth_inputs(1, K, seed=56)
+    heads = [th(B, K * 3), th(B, K * 3), th(B, K), th(B, K), th(B, K), th(B, 1)]
+    wm, ws, wt = torch.randn(B, K, 1, 3, generator=g), torch.randn(B, K, 3, 3, generator=g, dtype=torch.float64), torch.randn(B, 1, generator=g)
+
+    def run(fn, dev):
+        cm = cann["mus"].detach().clone().to(dev).requires_grad_(True)
+        cs = cann["sigma"].detach().clone().to(dev).requires_grad_(True)
+        hs = [h.detach().clone().to(dev).requires_grad_(True) for h in heads]
+        mus, sig, theta = fn(*hs, cm, cs)
+        ((mus * wm.to(dev)).sum() + (sig * ws.to(dev)).sum() + (theta * wt.to(dev)).sum()).backward()
+        return (mus, sig, theta), [cm.grad, cs.grad] + [h.grad for h in hs]
+
+    (rm, rs, rt), gref = run(rp.deform, torch.device("cpu"))
+    (om, os_, ot), gout = run(gg.deform, cuda_device)
+    assert om.shape == rm.shape and om.dtype == torch.float32 and os_.dtype == torch.float64 and ot.shape == rt.shape
+    assert torch.equal(om.cpu(), rm.detach()) and torch.equal(ot.cpu(), rt.detach())
+    assert_close_norm(os_, rs, 1e-9, "deform sigmas")       # float64 chain; CPU vs GPU SVD differ at round-off
+    for a, b, nm in zip(gout, gref, ["cannmu", "cannsigma", "mu_t", "scale", "rx", "ry", "rz", "theta"]):
+        assert_close_norm(a, b, GRAD_RTOL, "deform grad " + nm)
+
+
+def test_config3_full_cuda_pipeline(gg, cuda_device):
+    """Config 3 end to end on the CUDA path: frame -> Sigma_c, deformation, render, fused loss; gradients reach the
+    canonical frame parameters and the deformation heads.  Checked against the oracle's same chain."""
+    B, K, n = 6, 16, 128
+    g = torch.Generator().manual_seed(33)
+    th = lambda *s: torch.tanh(torch.randn(*s, generator=g))
+    frame = [th(1, K, 3), th(1, K, 3), torch.randn(1, K, 3, generator=g)]
+    cmu = th(1, K, 1, 3)
+    heads = [th(B, K * 3), th(B, K * 3), th(B, K), th(B, K), th(B, K), th(B, 1)]
+    tgt = rp.synth_target_masks(B, n, seed=4)
+
+    def run(mod, dev, loss_fn):
+        fr = [t.detach().clone().to(dev).requires_grad_(True) for t in frame]
+        cm = cmu.detach().clone().to(dev).requires_grad_(True)
+        hs = [h.detach().clone().to(dev).requires_grad_(True) for h in heads]
+        csig = mod.sigma_from_frame(*fr)
+        mus, sig, theta = mod.deform(*hs, cm, csig)
+        loss = loss_fn(mus, sig, torch.zeros_like(theta), theta, torch.zeros_like(theta), dev)
+        loss.backward()
+        return loss.detach(), [t.grad for t in fr] + [cm.grad] + [h.grad for h in hs]
+
+    ref_loss = lambda mus, sig, rx, ry, rz, dev: rp.mask_recon_loss_bis(
+        tgt, rp.get_landmarks(mus, sig, rx, ry, rz, 0, 0, -2., sizes=(n,))[0])
+    out_loss = lambda mus, sig, rx, ry, rz, dev: gg.mask_recon_loss_bis(tgt.to(dev), mus, sig, rx, ry, rz, 0, 0, -2., size=n)
+    lr, gr = run(rp, torch.device("cpu"), ref_loss)
+    lo, go = run(gg, cuda_device, out_loss)
+    assert abs(lo.item() - lr.item()) <= 1e-5 * abs(lr.item())
+    names = ["v0", "v1", "u", "cannmu", "mu_t", "scale", "rx", "ry", "rz", "theta"]
+    for a, b, nm in zip(go, gr, names):
+        assert_close_norm(a, b, 5 * GRAD_RTOL, "C3 pipeline grad " + nm)

@@ -270,6 +270,64 @@ def run_gpu(args):
                  "note": "whole fwd+bwd step (4 kernels) against the 26-slot algorithmic count"},
     }
 
+    # ---- the same step with the consumer fused in (3 launches: projection, splat+loss+backward, adjoint)
+    fused = None
+    try:
+        from gaussigan_b200.plan import SilhouetteLossStep
+        fsets = []
+        for r in range(R):
+            st_, _, inp, tgt = sets[r]
+            fs = SilhouetteLossStep(B, K, n, dev)
+            fs.bind(*st_._inputs)
+            raw = ((tgt.reshape(B, n, n) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).to(dev)
+            fs.capture_loss(raw)
+            fsets.append((fs, raw))
+        for i in range(5):
+            fsets[i % R][0].graph.replay()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            fsets[i % R][0].graph.replay()
+        b.record()
+        barrier()
+        fms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([fms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fms = float(t.item())
+        fused = {"value": world * B / (fms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": fms / args.steps,
+                 "launches_per_step": SilhouetteLossStep.LAUNCHES_PER_STEP,
+                 "note": "mask_recon_loss_bis fused into the splat kernel: the silhouette and dL/dmask never reach HBM"}
+        del fsets
+    except Exception as exc:                      # pragma: no cover
+        fused = {"value": None, "error": repr(exc)}
+
+    # ---- training-time exchange: all-reduce of the shared (canonical-Gaussian) gradients after every step
+    allreduce = None
+    if world > 1:
+        from gaussigan_b200.dist import reduce_shared_grads
+        for i in range(3):
+            s0 = sets[i % R][0]
+            s0.graph.replay()
+            reduce_shared_grads([s0.dmus, s0.dsigma])
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            s0 = sets[i % R][0]
+            s0.graph.replay()
+            reduce_shared_grads([s0.dmus, s0.dsigma])
+        b.record()
+        barrier()
+        ams = a.elapsed_time(b)
+        t = torch.tensor([ams], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ams = float(t.item())
+        allreduce = {"value": world * B / (ams / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ams / args.steps,
+                     "payload_bytes": K * 3 * 8 + K * 9 * 8,
+                     "note": "value with one NCCL all_reduce(SUM) of the batch-summed canonical-Gaussian gradients per step"}
+
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
     e2e = None
     try:
@@ -309,7 +367,8 @@ def run_gpu(args):
                        "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": f"{R} rotating input/output sets = {rot_bytes / 1e6:.0f} MB > 126 MB L2",
                        "step": "one CUDA-graph replay: project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd"},
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "fused_loss": fused,
+            "allreduce": allreduce,
             "gpu_launches": args.steps * SilhouetteStep.LAUNCHES_PER_STEP,
         }
         print(json.dumps(line))

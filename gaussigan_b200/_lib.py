@@ -41,6 +41,7 @@ _pp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "gg_version": (_i, []),
     "gg_last_error": (C.c_char_p, []),
+    "gg_set_fast_mask": (_i, [_i]),
     "gg_project_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "gg_project_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _vp, _i, _vp, _vp,
                             _vp, _vp, _vp, _i, _vp]),

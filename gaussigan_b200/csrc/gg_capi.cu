@@ -62,6 +62,8 @@ int gg_version(void) { return GG_VERSION; }
 
 const char *gg_last_error(void) { return g_err; }
 
+int gg_set_fast_mask(int enable) { return gg::set_fast_mask(enable); }
+
 int gg_project_fwd(const float *mus, const void *sigma, int sigma_is_f64, const float *rotx, const float *roty,
                    const float *rotz, double tx, double ty, double tz, double focal, int B, int K, double *mu2d,
                    double *sigma2d, float *params, int device, void *stream) {

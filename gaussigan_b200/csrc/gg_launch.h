@@ -34,6 +34,8 @@ struct ScaleDesc;
 void make_strip_desc(ScaleDesc &d, int n, int rpt);
 int bwd_rpt();
 int fwd_rpt();
+bool fast_mask();
+int set_fast_mask(int enable);
 
 // fused cycle L1 between two renders (mask/mask_gen_dynamic.py:791) and the viz composite (:221-231)
 int cycle_tiles(int n);

@@ -533,8 +533,9 @@ int env_int(const char *name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-void strip_geometry(ScaleDesc &d, int n, int rpt) {
+void strip_geometry(ScaleDesc &d, int n, int rpt, bool contig = false) {
   d.n = n;
+  d.contig = contig ? 1 : 0;
   d.spr = ((n + 3) / 4 + 1) / 2;     // threads per row: half the quads, each thread takes quad s and s + spr
   d.sprc = d.spr < kThreads ? d.spr : kThreads;
   d.rpp = d.spr <= kThreads ? kThreads / d.spr : 1;
@@ -546,6 +547,7 @@ void strip_geometry(ScaleDesc &d, int n, int rpt) {
 
 void quad_geometry(ScaleDesc &d, int n, int KQ, int passes) {
   d.n = n;
+  d.contig = 0;
   d.spr = d.sprc = d.rpp = d.chunks = 0;
   int per_row = (n * KQ + kThreads - 1) / kThreads;       // passes a CTA needs for one row
   d.rows_per_tile = passes / per_row > 0 ? passes / per_row : 1;
@@ -569,6 +571,22 @@ bool quad_ok(int K, int *shift) {
 
 // exported for gg_fused.cu
 void make_strip_desc(ScaleDesc &d, int n, int rpt) { strip_geometry(d, n, rpt); }
+
+cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st);
+cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st);
+
+// Mask-only launches use the forward-differenced kernels of gg_splat_fast.cu unless GG_PRECISE_MASK=1 (or
+// gg_set_fast_mask(0)) asks for the direct one-exponential-per-pixel form.
+static int g_fast_mask = -1;
+bool fast_mask() {
+  if (g_fast_mask < 0) g_fast_mask = env_int("GG_PRECISE_MASK", 0) ? 0 : 1;
+  return g_fast_mask != 0;
+}
+int set_fast_mask(int enable) {
+  const int prev = fast_mask() ? 1 : 0;
+  g_fast_mask = enable ? 1 : 0;
+  return prev;
+}
 
 int fwd_rpt() { static int v = env_int("GG_RPT_FWD", 2); return v; }
 int bwd_rpt() { static int v = env_int("GG_RPT_BWD", 2); return v; }
@@ -604,7 +622,8 @@ static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool
       if (has_mask[i]) pl.maps_any_mask = true;
     } else if (has_mask[i]) {
       ScaleDesc &d = pl.strip_mask.sc[pl.strip_mask.nscales++];
-      strip_geometry(d, sizes[i], rpt);
+      if (fast_mask()) strip_geometry(d, sizes[i], rpt >= 4 ? 4 : 2, true);   // fast kernels work on row pairs
+      else strip_geometry(d, sizes[i], rpt);
       d.tile_begin = tb_mask;
       tb_mask += d.tiles;
     }
@@ -662,8 +681,9 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
   if (pl.strip_mask.nscales) {
     SplatArgs &a = pl.strip_mask;
     a.params = params; a.B = B; a.K = K; a.T = pl.tiles_mask; a.layout = layout;
-    err = rpt == 1 ? launch_fwd_strip<1>(a, 0, B, st) : rpt == 4 ? launch_fwd_strip<4>(a, 0, B, st)
-                                                                   : launch_fwd_strip<2>(a, 0, B, st);
+    if (fast_mask()) err = launch_fwd_mask_fast(a, B, rpt, st);
+    else err = rpt == 1 ? launch_fwd_strip<1>(a, 0, B, st) : rpt == 4 ? launch_fwd_strip<4>(a, 0, B, st)
+                                                                        : launch_fwd_strip<2>(a, 0, B, st);
     if (err != cudaSuccess) return err;
   }
   if (pl.maps.nscales) {
@@ -711,8 +731,9 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
     SplatArgs &a = pl.strip_mask;
     a.params = params; a.partials = partials; a.B = B; a.K = K; a.T = pl.tiles_mask; a.slots = T; a.tile_offset = 0;
     a.layout = layout;
-    err = rpt == 1 ? launch_bwd_strip<1>(a, 0, B, st) : rpt == 4 ? launch_bwd_strip<4>(a, 0, B, st)
-                                                                   : launch_bwd_strip<2>(a, 0, B, st);
+    if (fast_mask()) err = launch_bwd_mask_fast(a, false, B, rpt, st);
+    else err = rpt == 1 ? launch_bwd_strip<1>(a, 0, B, st) : rpt == 4 ? launch_bwd_strip<4>(a, 0, B, st)
+                                                                        : launch_bwd_strip<2>(a, 0, B, st);
     if (err != cudaSuccess) return err;
   }
   if (pl.maps.nscales) {
@@ -758,6 +779,7 @@ cudaError_t launch_silhouette_loss_fused(const float *params, const void *target
   a.target = target; a.target_kind = target_kind; a.inv_n = 1.0f / (float)((size_t)B * n * n);
   a.loss_partials = loss_partials;
   const int rpt = bwd_rpt();
+  if (fast_mask()) return launch_bwd_mask_fast(a, true, B, rpt, st);
   return rpt == 1 ? launch_bwd_strip<1>(a, 3, B, st) : rpt == 4 ? launch_bwd_strip<4>(a, 3, B, st)
                                                                 : launch_bwd_strip<2>(a, 3, B, st);
 }

@@ -1,0 +1,416 @@
+// gg_splat_fast.cu -- mask-only splat kernels with the Gaussians FORWARD-DIFFERENCED along each pixel strip.
+//
+// Same contract as the strip kernels of gg_splat.cu in their mask-only modes (sum composite
+// mask/mask_gen_dynamic.py:785-786, its gradient, and the fused m_recon_loss_bis :785-787), different
+// arithmetic.  The direct form pays one MUFU.EX2 per (pixel, Gaussian) and the MUFU pipe (16 lanes/clk/SM)
+// is what bounds it.  Along a row the pixel centres are equally spaced (step h), so with
+//     a_j = nA t_j^2 + e,   t_j = t_0 + j h          (log2 of the Gaussian at pixel j of the strip)
+//     g_{j+1} = g_j r_j,    r_j = exp2(nA h (2 t_j + h)),    r_{j+1} = r_j c,    c = exp2(2 nA h^2)
+// a strip of 8 pixels needs TWO exponentials (g_0, r_0) instead of eight; c is computed once per
+// (CTA, Gaussian) in float64.  MUFU work drops 4x and the kernels become FP32-pipe bound.
+//
+// Lanes.  A thread owns one 8-pixel strip of TWO rows (row, row + rpp).  Every FP32x2 register holds the
+// same quantity for the two rows, so the whole per-(Gaussian,row) set-up (dy, t0, the two exponents), the
+// recurrence and the moment folding run as packed FFMA2/FMUL2/FADD2: half the issue slots of the scalar form.
+//
+// Accuracy (tools/study/recurrence_accuracy.py, float32 emulation against the float64 oracle, reference
+// activation ranges): silhouette max|err|/max = 8e-7 (direct form: 1e-7; tolerance 1e-5).
+//
+// Guard.  The recurrence is only used where the per-pixel change of the exponent is small,
+// |nA h (2 t + h)| <= 13 over the whole tile: then nothing can overflow and a strip whose first pixel
+// underflows (g_0 < 2^-126) stays below 2^-35 everywhere.  The test is made once per (CTA, Gaussian) from the
+// tile's corners (t is linear in the pixel position); Gaussians that fail it (sub-pixel-thin or very distant)
+// are evaluated directly, one exponential per pixel, by the whole CTA.
+//
+// Backward.  The upstream gradient of a pixel is shared by all K Gaussians, so each thread forms
+// (Gbar, Gbar xi, Gbar xi^2) once per pixel (xi = j h, strip-local) and the per-(pixel, Gaussian) work is three
+// packed FMAs; the strip sums are re-centred to the sheared coordinate t per row.
+#include "gg_common.cuh"
+#include "gg_strip.cuh"
+#include "gg_launch.h"
+
+namespace gg {
+
+namespace {
+
+constexpr float kMaxSlope = 13.0f;     // largest |d(exponent)/d(pixel)| the recurrence is trusted with
+
+// Per-Gaussian constants of one CTA (its scale fixes h): 3 x float4 in shared memory
+//   c0 = mu_x, mu_y, nA, -nr      c1 = nE, 2 nA h, nA h^2, c      c2 = steep flag (0/1), 0, 0, 0
+// `steep` is decided per (CTA, Gaussian) from the tile's corners: t = dx + r dy is linear in the pixel position,
+// so max |t| over the tile is attained at a corner.
+__device__ __forceinline__ void stage_fast_consts(const float *__restrict__ gparams, int kn, float h, float x_lo,
+                                                  float x_hi, float y_lo, float y_hi, float4 *sc) {
+  const float4 *gp = reinterpret_cast<const float4 *>(gparams);
+  for (int k = threadIdx.x; k < kn; k += kThreads) {
+    const float4 lo = __ldg(gp + 2 * k);
+    const float nE = __ldg(reinterpret_cast<const float *>(gp + 2 * k + 1));
+    const float nAh = __fmul_rn(lo.z, h);
+    const float nAhh = __fmul_rn(nAh, h);
+    const double c = exp2(2.0 * (double)lo.z * (double)h * (double)h);
+    float tmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float xx = (i & 1) ? x_hi : x_lo, yy = (i & 2) ? y_hi : y_lo;
+      tmax = fmaxf(tmax, fabsf((xx - lo.x) - lo.w * (yy - lo.y)));
+    }
+    // exponent slope over a strip: |b_j| <= |2 nA h| (|t| + 8 h)
+    const float slope = fabsf(2.0f * nAh) * (tmax + 8.0f * h);
+    const bool steep = !(slope <= kMaxSlope);          // NaN -> steep
+    sc[3 * k + 0] = make_float4(lo.x, lo.y, lo.z, -lo.w);
+    sc[3 * k + 1] = make_float4(nE, 2.0f * nAh, nAhh, (float)c);
+    sc[3 * k + 2] = make_float4(steep ? 1.f : 0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ f32x2 bc(float v) { return pack2(v, v); }
+__device__ __forceinline__ f32x2 ex2_2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return pack2(ex2_approx(lo), ex2_approx(hi));
+}
+
+// One Gaussian on one strip of a ROW PAIR: lanes of every f32x2 are the two rows, G[j] is pixel j of the strip.
+//   dy = y - mu_y;  t0 = (x_0 - mu_x) - nr dy;  e = nE dy^2   (per lane)
+__device__ __forceinline__ void eval_strip(const float4 &c0, const float4 &c1, bool steep, f32x2 t0, f32x2 e, float h,
+                                           f32x2 (&G)[8]) {
+  const f32x2 nA = bc(c0.z);
+  if (steep) {
+    // sub-pixel-thin or very distant Gaussian: one exponential per pixel, as gg_splat.cu does
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const f32x2 t = add2(t0, bc((float)j * h));
+      G[j] = ex2_2(fma2(mul2(nA, t), t, e));
+    }
+    return;
+  }
+  f32x2 g = ex2_2(fma2(mul2(nA, t0), t0, e));
+  f32x2 r = ex2_2(fma2(bc(c1.y), t0, bc(c1.z)));
+  const f32x2 c = bc(c1.w);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    G[j] = g;
+    if (j < 7) g = mul2(g, r);
+    if (j < 6) r = mul2(r, c);
+  }
+}
+
+__device__ __forceinline__ void store8c(float *rowp, int col0, int n, const float *f) {
+  if ((n & 3) == 0) {
+    if (col0 < n) st_f4(rowp + col0, f[0], f[1], f[2], f[3]);
+    if (col0 + 4 < n) st_f4(rowp + col0 + 4, f[4], f[5], f[6], f[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (col0 + j < n) rowp[col0 + j] = f[j];
+  }
+}
+
+__device__ __forceinline__ void load8c(const float *rowp, int col0, int n, float *v) {
+  if ((n & 3) == 0) {
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    if (col0 < n) lo = __ldg(reinterpret_cast<const float4 *>(rowp + col0));
+    if (col0 + 4 < n) hi = __ldg(reinterpret_cast<const float4 *>(rowp + col0 + 4));
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (col0 + j < n) ? __ldg(rowp + col0 + j) : 0.f;
+  }
+}
+
+// tile extent in grid coordinates, for the steepness test
+__device__ __forceinline__ void tile_extent(const ScaleDesc &s, int tile_local, float &x_lo, float &x_hi, float &y_lo,
+                                            float &y_hi) {
+  const int rt = tile_local / s.chunks, ch = tile_local - rt * s.chunks;
+  const int c_lo = ch * kThreads * 8, c_hi = min(s.n, c_lo + kThreads * 8) - 1;
+  const int r_lo = rt * s.rows_per_tile, r_hi = min(s.n, r_lo + s.rows_per_tile) - 1;
+  x_lo = grid_coord(c_lo, s.step); x_hi = grid_coord(c_hi, s.step);
+  y_lo = grid_coord(r_lo, s.step); y_hi = grid_coord(r_hi, s.step);
+}
+
+}  // namespace
+
+// ================================================================================== forward (mask)
+// NP = row pairs per thread (rows per thread = 2 NP, spaced s.rpp apart)
+template <int NP>
+__global__ void __launch_bounds__(kThreads) splat_fwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
+  extern __shared__ float4 sc[];   // [K][3]
+  const int b = blockIdx.x / a.T;
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+  const float h = s.step;
+  {
+    float x_lo, x_hi, y_lo, y_hi;
+    tile_extent(s, tile - s.tile_begin, x_lo, x_hi, y_lo, y_hi);
+    stage_fast_consts(a.params + (size_t)b * K * GG_PARAM_STRIDE, K, h, x_lo, x_hi, y_lo, y_hi, sc);
+  }
+  __syncthreads();
+
+  const StripPos pos = strip_pos(s, tile - s.tile_begin);   // contiguous strips: colB = colA + 4
+  if (!pos.valid) return;
+  const float x0 = grid_coord(pos.colA, h);
+  f32x2 y[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+    y[p] = pack2(grid_coord(pos.row0 + (2 * p) * s.rpp, h), grid_coord(pos.row0 + (2 * p + 1) * s.rpp, h));
+
+  f32x2 acc[NP][8];
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = pack2(0.f, 0.f);
+
+  for (int k = 0; k < K; ++k) {
+    const float4 c0 = sc[3 * k], c1 = sc[3 * k + 1];
+    const bool steep = sc[3 * k + 2].x != 0.f;
+    const float xm = x0 - c0.x;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const f32x2 dy = sub2(y[p], bc(c0.y));
+      const f32x2 t0 = fma2(bc(c0.w), dy, bc(xm));
+      const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
+      f32x2 G[8];
+      eval_strip(c0, c1, steep, t0, e, h, G);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = add2(acc[p][j], G[j]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    float fa[8], fb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) unpack2(acc[p][j], fa[j], fb[j]);
+    const int rowA = pos.row0 + (2 * p) * s.rpp, rowB = rowA + s.rpp;
+    if (rowA < n) store8c(s.mask + ((size_t)b * n + rowA) * n, pos.colA, n, fa);
+    if (rowB < n) store8c(s.mask + ((size_t)b * n + rowB) * n, pos.colA, n, fb);
+  }
+}
+
+// ================================================================================= backward (mask)
+// FUSED = false: upstream gradient dL/dmask read from s.mask.
+// FUSED = true : m_recon_loss_bis in one launch -- a forward pass builds the silhouette in registers, the residual
+//                against the target gives dL/dmask = -sign(0.5 (t + 1) - m) / N (mask/mask_gen_dynamic.py:785-787)
+//                and the loss partial; then the same CTA runs the backward.  K <= kKBlock.
+template <int NP, bool FUSED>
+__global__ void __launch_bounds__(kThreads) splat_bwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
+  __shared__ float4 sc[kKBlock * 3];
+  __shared__ float stage[kWarps][kStageCols][33];
+  __shared__ float warpsum[kWarps][kKBlock * GG_MOMENTS];
+  __shared__ float lut[FUSED ? 256 : 1];
+
+  const int b = blockIdx.x / a.T;
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+  const float h = s.step;
+  const int k0 = blockIdx.y * kKBlock;
+  const int kn = min(kKBlock, K - k0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    float x_lo, x_hi, y_lo, y_hi;
+    tile_extent(s, tile - s.tile_begin, x_lo, x_hi, y_lo, y_hi);
+    stage_fast_consts(a.params + ((size_t)b * K + k0) * GG_PARAM_STRIDE, kn, h, x_lo, x_hi, y_lo, y_hi, sc);
+  }
+  if (FUSED && a.target_kind == GG_TARGET_U8) {
+    // 0.5 * ((raw / 127.5 - 1) + 1), op by op in float32 as the reference (:672, :787): one division per
+    // thread instead of one per pixel
+    const float v = (float)threadIdx.x;
+    lut[threadIdx.x] = __fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(v, 127.5f), 1.0f), 1.0f), 0.5f);
+  }
+  __syncthreads();
+
+  const StripPos pos = strip_pos(s, tile - s.tile_begin);
+  const float x0 = grid_coord(pos.colA, h);
+  f32x2 y[NP];
+  int row[2 * NP];
+  bool rv[2 * NP];
+#pragma unroll
+  for (int r = 0; r < 2 * NP; ++r) {
+    row[r] = pos.row0 + r * s.rpp;
+    rv[r] = pos.valid && row[r] < n;
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) y[p] = pack2(grid_coord(row[2 * p], h), grid_coord(row[2 * p + 1], h));
+
+  float gm[2 * NP][8];     // upstream gradient dL/dmask of this thread's pixels
+  float lsum = 0.f;
+  if (!FUSED) {
+#pragma unroll
+    for (int r = 0; r < 2 * NP; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gm[r][j] = 0.f;
+      if (rv[r]) load8c(s.mask + ((size_t)b * n + row[r]) * n, pos.colA, n, gm[r]);
+    }
+  } else {
+    // ---- forward pass: the silhouette of this thread's strips
+    f32x2 acc[NP][8];
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = pack2(0.f, 0.f);
+    for (int kk = 0; kk < kn; ++kk) {
+      const float4 c0 = sc[3 * kk], c1 = sc[3 * kk + 1];
+      const bool steep = sc[3 * kk + 2].x != 0.f;
+      const float xm = x0 - c0.x;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const f32x2 dy = sub2(y[p], bc(c0.y));
+        const f32x2 t0 = fma2(bc(c0.w), dy, bc(xm));
+        const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
+        f32x2 G[8];
+        eval_strip(c0, c1, steep, t0, e, h, G);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[p][j] = add2(acc[p][j], G[j]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) unpack2(acc[p][j], gm[2 * p][j], gm[2 * p + 1][j]);
+    // ---- residual -> loss partial and dL/dmask
+#pragma unroll
+    for (int r = 0; r < 2 * NP; ++r) {
+      if (!rv[r]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gm[r][j] = 0.f;
+        continue;
+      }
+      const size_t off = ((size_t)b * n + row[r]) * n;
+      if (s.mask) store8c(s.mask + off, pos.colA, n, gm[r]);        // optional silhouette output
+      float tg[8];
+      if (a.target_kind == GG_TARGET_U8) {
+        const unsigned char *tp = reinterpret_cast<const unsigned char *>(a.target) + off;
+        if ((n & 7) == 0) {
+          const uint2 u = pos.colA < n ? __ldg(reinterpret_cast<const uint2 *>(tp + pos.colA)) : make_uint2(0u, 0u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            tg[j] = lut[(u.x >> (8 * j)) & 0xffu];
+            tg[j + 4] = lut[(u.y >> (8 * j)) & 0xffu];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tg[j] = (pos.colA + j < n) ? lut[__ldg(tp + pos.colA + j)] : 0.f;
+        }
+      } else {
+        load8c(reinterpret_cast<const float *>(a.target) + off, pos.colA, n, tg);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tg[j] = __fmul_rn(__fadd_rn(tg[j], 1.0f), 0.5f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float res = tg[j] - gm[r][j];
+        const bool in = pos.colA + j < n;
+        lsum += in ? fabsf(res) : 0.f;
+        gm[r][j] = !in ? 0.f : (res > 0.f ? -a.inv_n : (res < 0.f ? a.inv_n : 0.f));
+      }
+    }
+    // per-CTA loss partial (fixed order: lanes by butterfly, warps serially)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if (lane == 0) warpsum[warp][0] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += warpsum[w][0];
+      a.loss_partials[(size_t)b * a.T + tile] = tot;
+    }
+    __syncthreads();
+  }
+  // the upstream gradient of a pixel is shared by all Gaussians: Gbar, Gbar xi, Gbar xi^2 once (xi = j h)
+  f32x2 W0[NP][8], W1[NP][8], W2[NP][8];
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xi = (float)j * h;
+      const float ga = gm[2 * p][j], gb = gm[2 * p + 1][j];
+      W0[p][j] = pack2(ga, gb);
+      W1[p][j] = pack2(ga * xi, gb * xi);
+      W2[p][j] = pack2((ga * xi) * xi, (gb * xi) * xi);
+    }
+
+  for (int kk = 0; kk < kn; ++kk) {
+    const float4 c0 = sc[3 * kk], c1 = sc[3 * kk + 1];
+    const bool steep = sc[3 * kk + 2].x != 0.f;
+    const float xm = x0 - c0.x;
+    f32x2 P20 = pack2(0.f, 0.f), P11 = P20, P02 = P20, P10 = P20, P01 = P20;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const f32x2 dy = sub2(y[p], bc(c0.y));
+      const f32x2 t0 = fma2(bc(c0.w), dy, bc(xm));
+      const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
+      f32x2 G[8];
+      eval_strip(c0, c1, steep, t0, e, h, G);
+      f32x2 S0 = mul2(G[0], W0[p][0]), S1 = mul2(G[0], W1[p][0]), S2 = mul2(G[0], W2[p][0]);
+#pragma unroll
+      for (int j = 1; j < 8; ++j) {
+        S0 = fma2(G[j], W0[p][j], S0);
+        S1 = fma2(G[j], W1[p][j], S1);
+        S2 = fma2(G[j], W2[p][j], S2);
+      }
+      // strip-local moments (about x_0) -> moments of t = t0 + xi, then the row weights
+      const f32x2 m1 = fma2(t0, S0, S1);
+      const f32x2 m2 = fma2(t0, add2(S1, m1), S2);
+      const f32x2 d0 = mul2(dy, S0);
+      if (p == 0) {
+        P20 = m2; P10 = m1; P11 = mul2(dy, m1); P01 = d0; P02 = mul2(dy, d0);
+      } else {
+        P20 = add2(P20, m2); P10 = add2(P10, m1); P11 = fma2(dy, m1, P11); P01 = add2(P01, d0); P02 = fma2(dy, d0, P02);
+      }
+    }
+    float lo, hi;
+    const int cc = (kk % kKC) * GG_MOMENTS;
+    unpack2(P20, lo, hi); stage[warp][cc + 0][lane] = lo + hi;
+    unpack2(P11, lo, hi); stage[warp][cc + 1][lane] = lo + hi;
+    unpack2(P02, lo, hi); stage[warp][cc + 2][lane] = lo + hi;
+    unpack2(P10, lo, hi); stage[warp][cc + 3][lane] = lo + hi;
+    unpack2(P01, lo, hi); stage[warp][cc + 4][lane] = lo + hi;
+    if ((kk % kKC) == kKC - 1 || kk == kn - 1) {
+      __syncwarp();
+      const int ncols = cc + GG_MOMENTS;
+      const int cbase = (kk / kKC) * kStageCols;
+      if (lane < ncols) {
+        float acc = 0.f;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) acc += stage[warp][lane][l];
+        warpsum[warp][cbase + lane] = acc;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  float *out = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K + k0) * GG_MOMENTS;
+  for (int c = threadIdx.x; c < kn * GG_MOMENTS; c += kThreads) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) acc += warpsum[w][c];
+    out[c] = acc;
+  }
+}
+
+// ====================================================================================== launchers
+// rpt = rows per thread of the plan (2 or 4; fast_rpt() in gg_splat.cu clamps)
+cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st) {
+  dim3 grid((unsigned)((size_t)B * a.T));
+  size_t smem = (size_t)a.K * 3 * sizeof(float4);
+  if (rpt == 4) splat_fwd_mask_fast_kernel<2><<<grid, kThreads, smem, st>>>(a);
+  else splat_fwd_mask_fast_kernel<1><<<grid, kThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st) {
+  dim3 grid((unsigned)((size_t)B * a.T), (unsigned)((a.K + kKBlock - 1) / kKBlock));
+  if (fused) {
+    if (rpt == 4) splat_bwd_mask_fast_kernel<2, true><<<grid, kThreads, 0, st>>>(a);
+    else splat_bwd_mask_fast_kernel<1, true><<<grid, kThreads, 0, st>>>(a);
+  } else {
+    if (rpt == 4) splat_bwd_mask_fast_kernel<2, false><<<grid, kThreads, 0, st>>>(a);
+    else splat_bwd_mask_fast_kernel<1, false><<<grid, kThreads, 0, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace gg

@@ -34,8 +34,8 @@ __device__ __forceinline__ StripPos strip_pos(const ScaleDesc &s, int tile_local
   int rp = threadIdx.x / s.sprc;
   int sc = threadIdx.x - rp * s.sprc;
   int strip = ch * kThreads + sc;
-  p.colA = strip * 4;
-  p.colB = (strip + s.spr) * 4;
+  p.colA = s.contig ? strip * 8 : strip * 4;
+  p.colB = s.contig ? strip * 8 + 4 : (strip + s.spr) * 4;
   p.row0 = rt * s.rows_per_tile + rp;
   p.valid = (rp < s.rpp) && (strip < s.spr);
   return p;

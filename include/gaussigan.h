@@ -117,6 +117,13 @@ GG_API int gg_splat_bwd(const float *params, int B, int K, int nscales, const in
                  const float *const *gmaps_host, const float *const *gmasks_host, int layout,
                  float *partials, int T, int device, void *stream);
 
+/* Arithmetic of the MASK-ONLY launches (gg_splat_fwd / gg_splat_bwd on scales that carry only a mask, and
+ * gg_silhouette_loss_fused).  1 (default): Gaussians forward-differenced along each 8-pixel strip -- two
+ * exponentials per strip instead of eight, FP32-pipe bound, silhouette error ~6e-7 of its maximum.  0: one
+ * exponential per (pixel, Gaussian), ~1e-7.  Maps outputs always use the direct form.  Process-wide; returns the
+ * previous setting.  Environment GG_PRECISE_MASK=1 selects 0 at load time. */
+GG_API int gg_set_fast_mask(int enable);
+
 /* ---- direct consumer: sum-composite L1 loss ------------------------------------------------------
  * Replaces `m_recon_loss_bis` (mask/mask_gen_dynamic.py:785-787): loss = mean|0.5*(target+1) - mask| and its
  * gradient w.r.t. mask.  target [B,n,n] is uint8 (GG_TARGET_U8, normalised as :672) or float32 in [-1,1].

@@ -14,3 +14,13 @@ for _ in range(int(os.environ.get("PSTEPS", 6))):
     step.forward(); step.backward(gm)
 torch.cuda.synchronize()
 print("ok")
+if os.environ.get("PFUSED"):
+    from gaussigan_b200.plan import SilhouetteLossStep
+    fs = SilhouetteLossStep(B, K, n, dev)
+    fs.bind(*step._inputs)
+    tgt = rp.synth_target_masks(B, n)
+    raw = ((tgt.reshape(B, n, n) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).to(dev)
+    for _ in range(int(os.environ.get("PSTEPS", 6))):
+        fs.loss_backward(raw)
+    torch.cuda.synchronize()
+    print("fused ok", fs.loss())

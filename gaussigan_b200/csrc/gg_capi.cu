@@ -2,11 +2,21 @@
 // device selection, error reporting.  No compute here.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "gg_common.cuh"
 #include "gg_launch.h"
 
 namespace gg {
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *v = std::getenv("GG_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
 namespace api {
 
 thread_local char g_err[512] = "";

@@ -100,6 +100,40 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
   return r;
 }
 
+// ---- programmatic dependent launch (PDL).  Every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may become resident while the previous kernel of the
+// stream drains, run their index arithmetic, and block in pdl_wait() until that kernel has completed and its
+// memory is visible.  No global memory is touched before pdl_wait(); pdl_launch_dependents() right after it lets
+// the NEXT kernel do the same with respect to this one.  Hides the launch gap and the first wave's prologue in the
+// 3-4 kernel chains of a step (each kernel is only 10-30 us at the reference's batch sizes).  GG_PDL=0 disables.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
+// same, but the wait is made to depend on already-computed values so the compiler cannot sink the index
+// arithmetic that produced them below it
+__device__ __forceinline__ void pdl_enter_after(int i0, int i1, float f0, float f1) {
+  asm volatile("griddepcontrol.wait;" ::"r"(i0), "r"(i1), "f"(f0), "f"(f1) : "memory");
+  pdl_launch_dependents();
+}
+
+bool pdl_enabled();   // gg_capi.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ void st_f4(float *p, float a, float b, float c, float d) {
   *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
 }

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) mask_l1_loss_bwd_kernel(const float *__re
                                                                const void *__restrict__ target, size_t N4,
                                                                float inv_n, float *__restrict__ gmask,
                                                                float *__restrict__ partials) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   __shared__ float red[8];
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N4; i += (size_t)gridDim.x * blockDim.x) {
@@ -63,8 +64,8 @@ cudaError_t launch_mask_l1_loss_bwd(const float *mask, const void *target, int k
   size_t N = (size_t)B * n * n;
   if (N & 3) return cudaErrorInvalidValue;
   float inv_n = 1.0f / (float)N;
-  if (kind == 0) mask_l1_loss_bwd_kernel<0><<<npartials, 256, 0, st>>>(mask, target, N / 4, inv_n, gmask, partials);
-  else mask_l1_loss_bwd_kernel<1><<<npartials, 256, 0, st>>>(mask, target, N / 4, inv_n, gmask, partials);
+  if (kind == 0) launch_pdl(mask_l1_loss_bwd_kernel<0>, dim3(npartials), dim3(256), 0, st, mask, target, N / 4, inv_n, gmask, partials);
+  else launch_pdl(mask_l1_loss_bwd_kernel<1>, dim3(npartials), dim3(256), 0, st, mask, target, N / 4, inv_n, gmask, partials);
   return cudaGetLastError();
 }
 
@@ -88,6 +89,7 @@ struct CycleArgs {
 
 template <int RPT>
 __global__ void __launch_bounds__(kThreads) cycle_l1_fused_kernel(const __grid_constant__ CycleArgs a) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   __shared__ float4 spa[kCycKBlock * 2], spb[kCycKBlock * 2];
   __shared__ float stage[kWarps][kCycKC * 2 * GG_MOMENTS][33];
   __shared__ float warpsum[kWarps][kCycKBlock * 2 * GG_MOMENTS];
@@ -212,9 +214,9 @@ cudaError_t launch_cycle_l1_fused(const float *params_a, const float *params_b, 
   a.loss_partials = loss_partials; a.B = B; a.K = K; a.T = T; a.KB = (K + kCycKBlock - 1) / kCycKBlock;
   a.inv_n = 1.0f / ((float)B * (float)n * (float)n * (float)K);
   dim3 grid((unsigned)((size_t)B * T), (unsigned)a.KB);
-  if (rpt == 1) cycle_l1_fused_kernel<1><<<grid, kThreads, 0, st>>>(a);
-  else if (rpt == 4) cycle_l1_fused_kernel<4><<<grid, kThreads, 0, st>>>(a);
-  else cycle_l1_fused_kernel<2><<<grid, kThreads, 0, st>>>(a);
+  if (rpt == 1) launch_pdl(cycle_l1_fused_kernel<1>, dim3(grid), dim3(kThreads), 0, st, a);
+  else if (rpt == 4) launch_pdl(cycle_l1_fused_kernel<4>, dim3(grid), dim3(kThreads), 0, st, a);
+  else launch_pdl(cycle_l1_fused_kernel<2>, dim3(grid), dim3(kThreads), 0, st, a);
   return cudaGetLastError();
 }
 
@@ -240,6 +242,7 @@ __device__ __forceinline__ void put_rgb(void *out, int out_u8, size_t pix, float
 __global__ void __launch_bounds__(256) colorize_params_kernel(const float *__restrict__ params,
                                                               const float *__restrict__ colors, int K, int n,
                                                               float step, void *out, int out_u8) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   extern __shared__ float4 sm[];          // [K][2] params, then [K] colours (float4, w unused)
   float4 *sp = sm, *sc = sm + 2 * K;
   const int b = blockIdx.y;
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(256) colorize_params_kernel(const float *__res
 __global__ void __launch_bounds__(256) colorize_maps_kernel(const float *__restrict__ maps,
                                                             const float *__restrict__ colors, size_t npix, int K,
                                                             void *out, int out_u8) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
   const float *m = maps + pix * K;
@@ -284,13 +288,13 @@ cudaError_t launch_colorize_params(const float *params, const float *colors, int
                                    int out_u8, cudaStream_t st) {
   dim3 grid((unsigned)(((size_t)n * n + 255) / 256), (unsigned)B);
   const float step = n > 1 ? (1.0f - (-1.0f)) / (float)(n - 1) : 0.0f;
-  colorize_params_kernel<<<grid, 256, (size_t)K * 3 * sizeof(float4), st>>>(params, colors, K, n, step, out, out_u8);
+  launch_pdl(colorize_params_kernel, dim3(grid), dim3(256), (size_t)K * 3 * sizeof(float4), st, params, colors, K, n, step, out, out_u8);
   return cudaGetLastError();
 }
 
 cudaError_t launch_colorize_maps(const float *maps, const float *colors, size_t npix, int K, void *out, int out_u8,
                                  cudaStream_t st) {
-  colorize_maps_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(maps, colors, npix, K, out, out_u8);
+  launch_pdl(colorize_maps_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, st, maps, colors, npix, K, out, out_u8);
   return cudaGetLastError();
 }
 

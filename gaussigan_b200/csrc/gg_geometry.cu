@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(128) sigma_from_frame_fwd_kernel(const float *
                                                                    const float *__restrict__ v1r,
                                                                    const float *__restrict__ ur, int N,
                                                                    double *__restrict__ sigma) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const F3 a = {v0r[3 * i], v0r[3 * i + 1], v0r[3 * i + 2]}, b = {v1r[3 * i], v1r[3 * i + 1], v1r[3 * i + 2]};
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(128) sigma_from_frame_bwd_kernel(const float *
                                                                    const double *__restrict__ gsigma, int N,
                                                                    float *__restrict__ dv0, float *__restrict__ dv1,
                                                                    float *__restrict__ du) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const V3 a = {v0r[3 * i], v0r[3 * i + 1], v0r[3 * i + 2]}, b = {v1r[3 * i], v1r[3 * i + 1], v1r[3 * i + 2]};
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(128) deform_fwd_kernel(const float *__restrict
                                                          const float *__restrict__ theta_raw, int B, int K,
                                                          float *__restrict__ mus, double *__restrict__ sigmas,
                                                          float *__restrict__ theta) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B && theta) theta[i] = __fmul_rn(theta_raw[i], 180.0f);       // :458
   if (i >= B * K) return;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(128) deform_bwd_kernel(const float *__restrict
                                                          float *__restrict__ dmu_t, float *__restrict__ dsc,
                                                          float *__restrict__ dang, float *__restrict__ dcmu,
                                                          double *__restrict__ dU, double *__restrict__ dS) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B && dtheta_raw) dtheta_raw[i] = gtheta ? __fmul_rn(gtheta[i], 180.0f) : 0.f;
   if (i >= B * K) return;
@@ -277,24 +281,24 @@ __global__ void __launch_bounds__(128) deform_bwd_kernel(const float *__restrict
 // -------------------------------------------------------------------------------------- launchers
 cudaError_t launch_sigma_from_frame_fwd(const float *v0, const float *v1, const float *u, int N, double *sigma,
                                         cudaStream_t st) {
-  sigma_from_frame_fwd_kernel<<<(N + 127) / 128, 128, 0, st>>>(v0, v1, u, N, sigma);
+  launch_pdl(sigma_from_frame_fwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, v0, v1, u, N, sigma);
   return cudaGetLastError();
 }
 cudaError_t launch_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, const double *gsigma, int N,
                                         float *dv0, float *dv1, float *du, cudaStream_t st) {
-  sigma_from_frame_bwd_kernel<<<(N + 127) / 128, 128, 0, st>>>(v0, v1, u, gsigma, N, dv0, dv1, du);
+  launch_pdl(sigma_from_frame_bwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, v0, v1, u, gsigma, N, dv0, dv1, du);
   return cudaGetLastError();
 }
 cudaError_t launch_deform_fwd(const float *mu_t, const float *sc, const float *ang, const float *cmu, const double *U,
                               const double *S, const float *theta_raw, int B, int K, float *mus, double *sigmas,
                               float *theta, cudaStream_t st) {
-  deform_fwd_kernel<<<(B * K + 127) / 128, 128, 0, st>>>(mu_t, sc, ang, cmu, U, S, theta_raw, B, K, mus, sigmas, theta);
+  launch_pdl(deform_fwd_kernel, dim3((B * K + 127) / 128), dim3(128), 0, st, mu_t, sc, ang, cmu, U, S, theta_raw, B, K, mus, sigmas, theta);
   return cudaGetLastError();
 }
 cudaError_t launch_deform_bwd(const float *sc, const float *ang, const double *U, const double *S, const float *gmus,
                               const double *gsig, const float *gtheta, int B, int K, float *dtheta_raw, float *dmu_t,
                               float *dsc, float *dang, float *dcmu, double *dU, double *dS, cudaStream_t st) {
-  deform_bwd_kernel<<<(B * K + 127) / 128, 128, 0, st>>>(sc, ang, U, S, gmus, gsig, gtheta, B, K, dtheta_raw, dmu_t, dsc,
+  launch_pdl(deform_bwd_kernel, dim3((B * K + 127) / 128), dim3(128), 0, st, sc, ang, U, S, gmus, gsig, gtheta, B, K, dtheta_raw, dmu_t, dsc,
                                                          dang, dcmu, dU, dS);
   return cudaGetLastError();
 }

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(128) project_fwd_kernel(
     const float *__restrict__ rotx, const float *__restrict__ roty, const float *__restrict__ rotz,
     double tx, double ty, double tz, double focal, int B, int K,
     double *__restrict__ mu2d, double *__restrict__ sigma2d, float *__restrict__ params) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * K) return;
   int b = idx / K;
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     const float *__restrict__ partials, int T, const double *__restrict__ gmu2d_in,
     const double *__restrict__ gsigma2d_in, float *__restrict__ dmus, double *__restrict__ dsigma,
     float *__restrict__ drot) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   __shared__ double red[3][128];
   const int b = blockIdx.x;
   Cam cam;
@@ -389,6 +391,7 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
 __global__ void __launch_bounds__(128) conic_fwd_kernel(const void *__restrict__ mu2d,
                                                         const void *__restrict__ sigma2d, int is_f64,
                                                         int N, float *__restrict__ params) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N) return;
   double mu[2], sg[4];
@@ -413,6 +416,7 @@ __global__ void __launch_bounds__(128) conic_bwd_kernel(const void *__restrict__
                                                         int B, int K, const float *__restrict__ partials,
                                                         int T, double *__restrict__ dmu2d,
                                                         double *__restrict__ dsigma2d) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * K) return;
   int b = idx / K, k = idx - b * K;
@@ -444,7 +448,7 @@ cudaError_t launch_project_fwd(const float *mus, const void *sigma, int f64, con
                                const float *rz, double tx, double ty, double tz, double focal, int B, int K,
                                double *mu2d, double *sigma2d, float *params, cudaStream_t st) {
   int N = B * K;
-  project_fwd_kernel<<<(N + 127) / 128, 128, 0, st>>>(mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B, K, mu2d,
+  launch_pdl(project_fwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B, K, mu2d,
                                                       sigma2d, params);
   return cudaGetLastError();
 }
@@ -454,20 +458,20 @@ cudaError_t launch_project_bwd(const float *mus, const void *sigma, int f64, con
                                const float *partials, int T, const double *gmu2d, const double *gsigma2d,
                                float *dmus, double *dsigma, float *drot, cudaStream_t st) {
   int threads = K >= 128 ? 128 : ((K + 31) / 32) * 32;
-  project_bwd_kernel<<<B, threads, 0, st>>>(mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B, K, partials, T,
+  launch_pdl(project_bwd_kernel, dim3(B), dim3(threads), 0, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B, K, partials, T,
                                             gmu2d, gsigma2d, dmus, dsigma, drot);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conic_fwd(const void *mu2d, const void *sigma2d, int f64, int N, float *params, cudaStream_t st) {
-  conic_fwd_kernel<<<(N + 127) / 128, 128, 0, st>>>(mu2d, sigma2d, f64, N, params);
+  launch_pdl(conic_fwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, mu2d, sigma2d, f64, N, params);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conic_bwd(const void *mu2d, const void *sigma2d, int f64, int B, int K, const float *partials,
                              int T, double *dmu2d, double *dsigma2d, cudaStream_t st) {
   int N = B * K;
-  conic_bwd_kernel<<<(N + 127) / 128, 128, 0, st>>>(mu2d, sigma2d, f64, B, K, partials, T, dmu2d, dsigma2d);
+  launch_pdl(conic_bwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, mu2d, sigma2d, f64, B, K, partials, T, dmu2d, dsigma2d);
   return cudaGetLastError();
 }
 

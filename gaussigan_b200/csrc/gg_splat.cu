@@ -35,6 +35,7 @@ namespace gg {
 // OUT: 0 = mask only, 1 = NCHW maps (+ mask when given), 2 = NHWC maps, scalar stores (+ mask)
 template <int RPT, int OUT>
 __global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_constant__ SplatArgs a) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   extern __shared__ float4 sp[];   // [K][2]
   const int b = blockIdx.x / a.T;  // a.T = tiles per batch element in this launch
   const int tile = blockIdx.x - b * a.T;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_
 //          never touch HBM (optionally the mask is written out through s.mask).  Requires K <= kKBlock.
 template <int RPT, int GIN>
 __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_constant__ SplatArgs a) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   __shared__ float4 sp[kKBlock * 2];
   __shared__ float stage[kWarps][kStageCols][33];
   __shared__ float warpsum[kWarps][kKBlock * GG_MOMENTS];
@@ -358,6 +360,7 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
 template <bool WITH_MASK>
 __global__ void __launch_bounds__(kThreads) splat_fwd_quad_kernel(const __grid_constant__ SplatArgs a,
                                                                   int kq_shift) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   const int b = blockIdx.x / a.T;
   const int tile = blockIdx.x - b * a.T;
   const ScaleDesc &s = a.sc[find_scale(a, tile)];
@@ -413,6 +416,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quad_kernel(const __grid_c
 template <bool WITH_GMASK>
 __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_kernel(const __grid_constant__ SplatArgs a,
                                                                   int kq_shift) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   __shared__ float wsum[kWarps][32 * 4 * GG_MOMENTS];   // [warp][kq][i][moment], K*5 <= 640 floats used
 
   const int b = blockIdx.x / a.T;
@@ -646,9 +650,9 @@ static cudaError_t launch_fwd_strip(const SplatArgs &a, int out_mode, int B, cud
   dim3 grid((unsigned)((size_t)B * a.T));
   size_t smem = (size_t)a.K * GG_PARAM_STRIDE * sizeof(float);
   switch (out_mode) {
-    case 0: splat_fwd_strip_kernel<RPT, 0><<<grid, kThreads, smem, st>>>(a); break;
-    case 1: splat_fwd_strip_kernel<RPT, 1><<<grid, kThreads, smem, st>>>(a); break;
-    default: splat_fwd_strip_kernel<RPT, 2><<<grid, kThreads, smem, st>>>(a); break;
+    case 0: launch_pdl(splat_fwd_strip_kernel<RPT, 0>, dim3(grid), dim3(kThreads), smem, st, a); break;
+    case 1: launch_pdl(splat_fwd_strip_kernel<RPT, 1>, dim3(grid), dim3(kThreads), smem, st, a); break;
+    default: launch_pdl(splat_fwd_strip_kernel<RPT, 2>, dim3(grid), dim3(kThreads), smem, st, a); break;
   }
   return cudaGetLastError();
 }
@@ -657,10 +661,10 @@ template <int RPT>
 static cudaError_t launch_bwd_strip(const SplatArgs &a, int gin_mode, int B, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)B * a.T), (unsigned)((a.K + kKBlock - 1) / kKBlock));
   switch (gin_mode) {
-    case 0: splat_bwd_strip_kernel<RPT, 0><<<grid, kThreads, 0, st>>>(a); break;
-    case 1: splat_bwd_strip_kernel<RPT, 1><<<grid, kThreads, 0, st>>>(a); break;
-    case 3: splat_bwd_strip_kernel<RPT, 3><<<grid, kThreads, 0, st>>>(a); break;
-    default: splat_bwd_strip_kernel<RPT, 2><<<grid, kThreads, 0, st>>>(a); break;
+    case 0: launch_pdl(splat_bwd_strip_kernel<RPT, 0>, dim3(grid), dim3(kThreads), 0, st, a); break;
+    case 1: launch_pdl(splat_bwd_strip_kernel<RPT, 1>, dim3(grid), dim3(kThreads), 0, st, a); break;
+    case 3: launch_pdl(splat_bwd_strip_kernel<RPT, 3>, dim3(grid), dim3(kThreads), 0, st, a); break;
+    default: launch_pdl(splat_bwd_strip_kernel<RPT, 2>, dim3(grid), dim3(kThreads), 0, st, a); break;
   }
   return cudaGetLastError();
 }
@@ -691,8 +695,8 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
     a.params = params; a.B = B; a.K = K; a.T = pl.tiles_maps; a.layout = layout;
     if (pl.maps_quad) {
       dim3 grid((unsigned)((size_t)B * a.T));
-      if (pl.maps_any_mask) splat_fwd_quad_kernel<true><<<grid, kThreads, 0, st>>>(a, pl.kq_shift);
-      else splat_fwd_quad_kernel<false><<<grid, kThreads, 0, st>>>(a, pl.kq_shift);
+      if (pl.maps_any_mask) launch_pdl(splat_fwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
+      else launch_pdl(splat_fwd_quad_kernel<false>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
       err = cudaGetLastError();
     } else {
       int mode = layout == GG_LAYOUT_NCHW ? 1 : 2;
@@ -744,8 +748,8 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
       dim3 grid((unsigned)((size_t)B * a.T));
       // the quad kernel adds gmask to every channel only when a scale carries one; scales without a
       // gmask are handled by giving the kernel a per-scale NULL check
-      if (pl.maps_any_mask) splat_bwd_quad_kernel<true><<<grid, kThreads, 0, st>>>(a, pl.kq_shift);
-      else splat_bwd_quad_kernel<false><<<grid, kThreads, 0, st>>>(a, pl.kq_shift);
+      if (pl.maps_any_mask) launch_pdl(splat_bwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
+      else launch_pdl(splat_bwd_quad_kernel<false>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
       err = cudaGetLastError();
     } else {
       int mode = layout == GG_LAYOUT_NCHW ? 1 : 2;

@@ -47,7 +47,22 @@ __device__ __forceinline__ void stage_fast_consts(const float *__restrict__ gpar
     const float nE = __ldg(reinterpret_cast<const float *>(gp + 2 * k + 1));
     const float nAh = __fmul_rn(lo.z, h);
     const float nAhh = __fmul_rn(nAh, h);
-    const double c = exp2(2.0 * (double)lo.z * (double)h * (double)h);
+    // c = exp2(2 nA h^2), needed to ~half an ulp (its error is amplified 21x over a strip).  The argument is tiny at
+    // the reference's sizes (|delta| <= 0.03 at n = 256): 1 + p with a degree-6 Taylor polynomial p in float32 is
+    // as good as the float64 value rounded; larger arguments (coarse grids, thin Gaussians) take the float64 path.
+    const float delta = 2.0f * nAhh;
+    float c;
+    if (fabsf(delta) <= 0.125f) {
+      const float z = delta * 0.693147180559945f;
+      float q = fmaf(z, 1.0f / 6.0f, 1.0f);
+      q = fmaf(z * 0.2f, q, 1.0f);
+      q = fmaf(z * 0.25f, q, 1.0f);
+      q = fmaf(z * (1.0f / 3.0f), q, 1.0f);
+      q = fmaf(z * 0.5f, q, 1.0f);
+      c = fmaf(z, q, 1.0f);
+    } else {
+      c = (float)exp2(2.0 * (double)lo.z * (double)h * (double)h);
+    }
     float tmax = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -58,7 +73,7 @@ __device__ __forceinline__ void stage_fast_consts(const float *__restrict__ gpar
     const float slope = fabsf(2.0f * nAh) * (tmax + 8.0f * h);
     const bool steep = !(slope <= kMaxSlope);          // NaN -> steep
     sc[3 * k + 0] = make_float4(lo.x, lo.y, lo.z, -lo.w);
-    sc[3 * k + 1] = make_float4(nE, 2.0f * nAh, nAhh, (float)c);
+    sc[3 * k + 1] = make_float4(nE, 2.0f * nAh, nAhh, c);
     sc[3 * k + 2] = make_float4(steep ? 1.f : 0.f, 0.f, 0.f, 0.f);
   }
 }
@@ -141,20 +156,23 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_mask_fast_kernel(const __g
   const ScaleDesc &s = a.sc[find_scale(a, tile)];
   const int K = a.K, n = s.n;
   const float h = s.step;
-  {
-    float x_lo, x_hi, y_lo, y_hi;
-    tile_extent(s, tile - s.tile_begin, x_lo, x_hi, y_lo, y_hi);
-    stage_fast_consts(a.params + (size_t)b * K * GG_PARAM_STRIDE, K, h, x_lo, x_hi, y_lo, y_hi, sc);
-  }
-  __syncthreads();
-
   const StripPos pos = strip_pos(s, tile - s.tile_begin);   // contiguous strips: colB = colA + 4
-  if (!pos.valid) return;
   const float x0 = grid_coord(pos.colA, h);
   f32x2 y[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p)
     y[p] = pack2(grid_coord(pos.row0 + (2 * p) * s.rpp, h), grid_coord(pos.row0 + (2 * p + 1) * s.rpp, h));
+  float x_lo, x_hi, y_lo, y_hi;
+  tile_extent(s, tile - s.tile_begin, x_lo, x_hi, y_lo, y_hi);
+
+  {  // everything above is index arithmetic; global memory is first touched below
+    float ya, yb;
+    unpack2(y[NP - 1], ya, yb);
+    pdl_enter_after(pos.colA, pos.row0, x0 + x_hi, ya + yb + y_lo);
+  }
+  stage_fast_consts(a.params + (size_t)b * K * GG_PARAM_STRIDE, K, h, x_lo, x_hi, y_lo, y_hi, sc);
+  __syncthreads();
+  if (!pos.valid) return;
 
   f32x2 acc[NP][8];
 #pragma unroll
@@ -208,19 +226,6 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_mask_fast_kernel(const __g
   const int k0 = blockIdx.y * kKBlock;
   const int kn = min(kKBlock, K - k0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
-    float x_lo, x_hi, y_lo, y_hi;
-    tile_extent(s, tile - s.tile_begin, x_lo, x_hi, y_lo, y_hi);
-    stage_fast_consts(a.params + ((size_t)b * K + k0) * GG_PARAM_STRIDE, kn, h, x_lo, x_hi, y_lo, y_hi, sc);
-  }
-  if (FUSED && a.target_kind == GG_TARGET_U8) {
-    // 0.5 * ((raw / 127.5 - 1) + 1), op by op in float32 as the reference (:672, :787): one division per
-    // thread instead of one per pixel
-    const float v = (float)threadIdx.x;
-    lut[threadIdx.x] = __fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(v, 127.5f), 1.0f), 1.0f), 0.5f);
-  }
-  __syncthreads();
-
   const StripPos pos = strip_pos(s, tile - s.tile_begin);
   const float x0 = grid_coord(pos.colA, h);
   f32x2 y[NP];
@@ -234,16 +239,34 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_mask_fast_kernel(const __g
 #pragma unroll
   for (int p = 0; p < NP; ++p) y[p] = pack2(grid_coord(row[2 * p], h), grid_coord(row[2 * p + 1], h));
 
+  float x_lo, x_hi, y_lo, y_hi;
+  tile_extent(s, tile - s.tile_begin, x_lo, x_hi, y_lo, y_hi);
+
+  {  // everything above is index arithmetic; global memory is first touched below
+    float ya, yb;
+    unpack2(y[NP - 1], ya, yb);
+    pdl_enter_after(pos.colA, row[2 * NP - 1], x0 + x_hi, ya + yb + y_lo);
+  }
   float gm[2 * NP][8];     // upstream gradient dL/dmask of this thread's pixels
   float lsum = 0.f;
-  if (!FUSED) {
+  if (!FUSED) {   // issued before the constants are staged: the two global round trips overlap
 #pragma unroll
     for (int r = 0; r < 2 * NP; ++r) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) gm[r][j] = 0.f;
       if (rv[r]) load8c(s.mask + ((size_t)b * n + row[r]) * n, pos.colA, n, gm[r]);
     }
-  } else {
+  }
+  stage_fast_consts(a.params + ((size_t)b * K + k0) * GG_PARAM_STRIDE, kn, h, x_lo, x_hi, y_lo, y_hi, sc);
+  if (FUSED && a.target_kind == GG_TARGET_U8) {
+    // 0.5 * ((raw / 127.5 - 1) + 1), op by op in float32 as the reference (:672, :787): one division per
+    // thread instead of one per pixel
+    const float v = (float)threadIdx.x;
+    lut[threadIdx.x] = __fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(v, 127.5f), 1.0f), 1.0f), 0.5f);
+  }
+  __syncthreads();
+
+  if (FUSED) {
     // ---- forward pass: the silhouette of this thread's strips
     f32x2 acc[NP][8];
 #pragma unroll
@@ -396,19 +419,19 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_mask_fast_kernel(const __g
 cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)B * a.T));
   size_t smem = (size_t)a.K * 3 * sizeof(float4);
-  if (rpt == 4) splat_fwd_mask_fast_kernel<2><<<grid, kThreads, smem, st>>>(a);
-  else splat_fwd_mask_fast_kernel<1><<<grid, kThreads, smem, st>>>(a);
+  if (rpt == 4) launch_pdl(splat_fwd_mask_fast_kernel<2>, dim3(grid), dim3(kThreads), smem, st, a);
+  else launch_pdl(splat_fwd_mask_fast_kernel<1>, dim3(grid), dim3(kThreads), smem, st, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)B * a.T), (unsigned)((a.K + kKBlock - 1) / kKBlock));
   if (fused) {
-    if (rpt == 4) splat_bwd_mask_fast_kernel<2, true><<<grid, kThreads, 0, st>>>(a);
-    else splat_bwd_mask_fast_kernel<1, true><<<grid, kThreads, 0, st>>>(a);
+    if (rpt == 4) launch_pdl(splat_bwd_mask_fast_kernel<2, true>, dim3(grid), dim3(kThreads), 0, st, a);
+    else launch_pdl(splat_bwd_mask_fast_kernel<1, true>, dim3(grid), dim3(kThreads), 0, st, a);
   } else {
-    if (rpt == 4) splat_bwd_mask_fast_kernel<2, false><<<grid, kThreads, 0, st>>>(a);
-    else splat_bwd_mask_fast_kernel<1, false><<<grid, kThreads, 0, st>>>(a);
+    if (rpt == 4) launch_pdl(splat_bwd_mask_fast_kernel<2, false>, dim3(grid), dim3(kThreads), 0, st, a);
+    else launch_pdl(splat_bwd_mask_fast_kernel<1, false>, dim3(grid), dim3(kThreads), 0, st, a);
   }
   return cudaGetLastError();
 }

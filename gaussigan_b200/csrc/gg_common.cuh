@@ -134,6 +134,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// keep a value in its register: stops the compiler from re-deriving cheap loop invariants (a grid coordinate is an
+// I2F + constant-bank load + FMUL + FADD) inside the hot loop to save a register
+__device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
+__device__ __forceinline__ f32x2 pin2(f32x2 v) { asm volatile("" : "+l"(v)); return v; }
+
 __device__ __forceinline__ void st_f4(float *p, float a, float b, float c, float d) {
   *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
 }

@@ -157,11 +157,11 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_mask_fast_kernel(const __g
   const int K = a.K, n = s.n;
   const float h = s.step;
   const StripPos pos = strip_pos(s, tile - s.tile_begin);   // contiguous strips: colB = colA + 4
-  const float x0 = grid_coord(pos.colA, h);
+  const float x0 = pin(grid_coord(pos.colA, h));
   f32x2 y[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p)
-    y[p] = pack2(grid_coord(pos.row0 + (2 * p) * s.rpp, h), grid_coord(pos.row0 + (2 * p + 1) * s.rpp, h));
+    y[p] = pin2(pack2(grid_coord(pos.row0 + (2 * p) * s.rpp, h), grid_coord(pos.row0 + (2 * p + 1) * s.rpp, h)));
   float x_lo, x_hi, y_lo, y_hi;
   tile_extent(s, tile - s.tile_begin, x_lo, x_hi, y_lo, y_hi);
 
@@ -212,9 +212,9 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_mask_fast_kernel(const __g
 //                against the target gives dL/dmask = -sign(0.5 (t + 1) - m) / N (mask/mask_gen_dynamic.py:785-787)
 //                and the loss partial; then the same CTA runs the backward.  K <= kKBlock.
 template <int NP, bool FUSED>
-__global__ void __launch_bounds__(kThreads) splat_bwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
+__global__ void __launch_bounds__(kThreads, NP == 1 ? 3 : 1) splat_bwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
   __shared__ float4 sc[kKBlock * 3];
-  __shared__ float stage[kWarps][kStageCols][33];
+  __shared__ __align__(16) float stage[kWarps][kStageCols][kStagePad];
   __shared__ float warpsum[kWarps][kKBlock * GG_MOMENTS];
   __shared__ float lut[FUSED ? 256 : 1];
 
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_mask_fast_kernel(const __g
   const int kn = min(kKBlock, K - k0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const StripPos pos = strip_pos(s, tile - s.tile_begin);
-  const float x0 = grid_coord(pos.colA, h);
+  const float x0 = pin(grid_coord(pos.colA, h));
   f32x2 y[NP];
   int row[2 * NP];
   bool rv[2 * NP];
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_mask_fast_kernel(const __g
     rv[r] = pos.valid && row[r] < n;
   }
 #pragma unroll
-  for (int p = 0; p < NP; ++p) y[p] = pack2(grid_coord(row[2 * p], h), grid_coord(row[2 * p + 1], h));
+  for (int p = 0; p < NP; ++p) y[p] = pin2(pack2(grid_coord(row[2 * p], h), grid_coord(row[2 * p + 1], h)));
 
   float x_lo, x_hi, y_lo, y_hi;
   tile_extent(s, tile - s.tile_begin, x_lo, x_hi, y_lo, y_hi);
@@ -395,11 +395,15 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_mask_fast_kernel(const __g
       __syncwarp();
       const int ncols = cc + GG_MOMENTS;
       const int cbase = (kk / kKC) * kStageCols;
-      if (lane < ncols) {
-        float acc = 0.f;
+      if (lane < ncols) {   // 8 LDS.128, four independent chains, fixed order
+        const float4 *rowp = reinterpret_cast<const float4 *>(&stage[warp][lane][0]);
+        float4 acc = rowp[0];
 #pragma unroll
-        for (int l = 0; l < 32; ++l) acc += stage[warp][lane][l];
-        warpsum[warp][cbase + lane] = acc;
+        for (int l = 1; l < 8; ++l) {
+          const float4 v = rowp[l];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        warpsum[warp][cbase + lane] = (acc.x + acc.y) + (acc.z + acc.w);
       }
       __syncwarp();
     }

@@ -8,6 +8,8 @@ namespace gg {
 
 static constexpr int kKC = 6;                      // Gaussians staged per warp-flush (5*kKC <= 32 columns)
 static constexpr int kStageCols = kKC * GG_MOMENTS;
+static constexpr int kStagePad = 36;               // row stride of the per-warp transpose buffer: 16-byte aligned rows,
+                                                   // conflict-free for the column writes and for LDS.128 row reads
 
 __device__ __forceinline__ int find_scale(const SplatArgs &a, int tile) {
   int si = 0;

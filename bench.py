@@ -193,9 +193,35 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---- R consecutive steps (one per buffer set) captured into ONE graph: the programmatic-dependent-launch
+    # edges between kernels then also span step boundaries; the remainder of the step count replays single steps
+    def capture_chain(steps_fn):
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            steps_fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            steps_fn()
+        return g
+
+    def all_sets_once():
+        for st_, gm_, _, _ in sets:
+            st_.forward()
+            st_.backward(gm_)
+
+    chain = capture_chain(all_sets_once)
+
+    def run_steps(nsteps):
+        for _ in range(nsteps // R):
+            chain.replay()
+        for i in range(nsteps % R):
+            sets[i][0].graph.replay()
+
     # ---- timed region: W warm-up steps, then exactly K steps, device-timed, max over ranks
-    for i in range(max(3, args.warmup)):
-        sets[i % R][0].graph.replay()
+    run_steps(max(3, args.warmup))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -204,8 +230,7 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e0.record()
-    for i in range(args.steps):
-        sets[i % R][0].graph.replay()
+    run_steps(args.steps)
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -257,11 +282,23 @@ def run_gpu(args):
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get("splat_bwd_mask_dram_bytes_per_launch")
+    # executed FP32-pipe work of the forward-differenced kernels, counted in their SASS inner loops:
+    # backward 48 packed + 6 scalar FP32-pipe instructions per (Gaussian, 2 rows x 8 px) = 6.4 lane-ops per
+    # (pixel, Gaussian); forward 27 packed + 4 scalar = 3.6.  The pipe retires 128 lane-ops/clk/SM.
+    EXEC_BWD, EXEC_FWD = 6.4, 3.6
     roofline = {
-        "kernel": "gg::splat_bwd_strip_kernel (mask gradient -> per-Gaussian moments)", "bound": "fp32_issue",
-        "achieved": ach / 1e12, "peak": issue_peak / 1e12, "unit": "T lane-slots/s (17 algorithmic issue slots per pixel-Gaussian)",
+        "kernel": "gg::splat_bwd_mask_fast_kernel (mask gradient -> per-Gaussian moments, forward-differenced strips)",
+        "bound": "fp32_pipe",
+        "achieved": ach / 1e12, "peak": issue_peak / 1e12,
+        "unit": "T lane-slots/s (17 algorithmic issue slots per pixel-Gaussian, SURVEY.md 8d)",
         "frac": ach / issue_peak, "traffic": traffic, "us_per_launch": us_bwd,
         "peak_source": f"148 SMs x 128 FP32 lanes x sm_max_mhz ({peaks['source']} MEASURED_PEAKS.json); no tensor cores: not a contraction",
+        "note": "frac > 1 is expected: the kernel forward-differences the Gaussians along each strip, so it executes "
+                "6.4 FP32 lane-ops + 0.25 MUFU.EX2 per pixel-Gaussian instead of the 17 slots of the algorithmic count",
+        "executed": {"fp32_lane_ops_per_pixel_gaussian": EXEC_BWD,
+                     "frac_of_fp32_pipe_peak": EXEC_BWD * pxk / (us_bwd * 1e-6) / issue_peak,
+                     "forward_fp32_lane_ops_per_pixel_gaussian": EXEC_FWD,
+                     "forward_frac_of_fp32_pipe_peak": EXEC_FWD * pxk / (us_fwd * 1e-6) / issue_peak},
         "hbm": {"achieved": bytes_bwd / (us_bwd * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": bytes_bwd / (us_bwd * 1e-6) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": bytes_bwd,
                 "peak_source": peaks["source"]},
@@ -282,13 +319,23 @@ def run_gpu(args):
             raw = ((tgt.reshape(B, n, n) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).to(dev)
             fs.capture_loss(raw)
             fsets.append((fs, raw))
-        for i in range(5):
-            fsets[i % R][0].graph.replay()
+        def all_fused_once():
+            for fs_, raw_ in fsets:
+                fs_.loss_backward(raw_)
+
+        fchain = capture_chain(all_fused_once)
+
+        def run_fused(nsteps):
+            for _ in range(nsteps // R):
+                fchain.replay()
+            for i in range(nsteps % R):
+                fsets[i][0].graph.replay()
+
+        run_fused(2 * R + 1)
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(args.steps):
-            fsets[i % R][0].graph.replay()
+        run_fused(args.steps)
         b.record()
         barrier()
         fms = a.elapsed_time(b)
@@ -299,7 +346,7 @@ def run_gpu(args):
         fused = {"value": world * B / (fms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": fms / args.steps,
                  "launches_per_step": SilhouetteLossStep.LAUNCHES_PER_STEP,
                  "note": "mask_recon_loss_bis fused into the splat kernel: the silhouette and dL/dmask never reach HBM"}
-        del fsets
+        del fsets, fchain
     except Exception as exc:                      # pragma: no cover
         fused = {"value": None, "error": repr(exc)}
 
@@ -366,7 +413,7 @@ def run_gpu(args):
                                    "projection in float64, splat in float32",
                        "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": f"{R} rotating input/output sets = {rot_bytes / 1e6:.0f} MB > 126 MB L2",
-                       "step": "one CUDA-graph replay: project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd"},
+                       "step": "project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd; 8 steps per CUDA-graph replay, kernels chained by programmatic dependent launch"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "fused_loss": fused,
             "allreduce": allreduce,
             "gpu_launches": args.steps * SilhouetteStep.LAUNCHES_PER_STEP,

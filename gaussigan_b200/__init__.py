@@ -5,7 +5,7 @@ Only the reference's data-parallel hot path lives here: th
 C ABI (``include/gaussigan.h``), with this package as the host-side mirror of the reference's Python
 interface.  Importing it loads ``lib/libgaussigan_sm100.so`` and fails loudly if it is missing.
 """
-from ._lib import GaussiganError, lib as _capi  # noqa: F401  (import = load the shared library)
+from ._lib import GaussiganError, lib as _capi, set_fast_mask, set_pdl  # noqa: F401  (import = load the shared library)
 from .renderer import (REFERENCE_SIZES, get_gaussian_maps_2d, get_landmarks, get_landmarks_infer,
                        get_landmarks_with_mask, project, render_silhouette)
 
@@ -14,7 +14,7 @@ from .consumers import (colorize_gaussians, colorize_landmark_maps, gm_cycle_los
 from .geometry import deform, sigma_from_frame  # noqa: E402
 from .interchange import decoder_feed, load_reference_gaussians, save_reference_gaussians  # noqa: E402
 
-__all__ = ["deform", "sigma_from_frame", "colorize_gaussians", "colorize_landmark_maps", "gm_cycle_loss", "mask_recon_loss_bis", "turntable",
+__all__ = ["set_fast_mask", "set_pdl", "deform", "sigma_from_frame", "colorize_gaussians", "colorize_landmark_maps", "gm_cycle_loss", "mask_recon_loss_bis", "turntable",
            "decoder_feed", "load_reference_gaussians", "save_reference_gaussians",
            "REFERENCE_SIZES", "GaussiganError", "get_gaussian_maps_2d", "get_landmarks", "get_landmarks_infer",
            "get_landmarks_with_mask", "project", "render_silhouette"]

@@ -42,6 +42,7 @@ SIGNATURES = {
     "gg_version": (_i, []),
     "gg_last_error": (C.c_char_p, []),
     "gg_set_fast_mask": (_i, [_i]),
+    "gg_set_pdl": (_i, [_i]),
     "gg_project_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "gg_project_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _vp, _i, _vp, _vp,
                             _vp, _vp, _vp, _i, _vp]),
@@ -89,3 +90,15 @@ def int_array(values):
 def ptr_array(ptrs):
     """Host array of device pointers; ``None``/0 entries become NULL."""
     return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) if p else None for p in ptrs])
+
+
+def set_fast_mask(enable: bool) -> bool:
+    """Mask-only launches: forward-differenced strips (True, default) or one exponential per pixel (False).
+    Returns the previous setting (``gg_set_fast_mask``)."""
+    return bool(lib.gg_set_fast_mask(int(bool(enable))))
+
+
+def set_pdl(enable: bool) -> bool:
+    """Programmatic dependent launch on/off for every kernel of the library (``gg_set_pdl``); returns the previous
+    setting."""
+    return bool(lib.gg_set_pdl(int(bool(enable))))

@@ -9,12 +9,18 @@
 
 namespace gg {
 
+static int g_pdl = -1;
 bool pdl_enabled() {
-  static const bool on = [] {
+  if (g_pdl < 0) {
     const char *v = std::getenv("GG_PDL");
-    return !(v && v[0] == '0');
-  }();
-  return on;
+    g_pdl = (v && v[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+int set_pdl(int enable) {
+  const int prev = pdl_enabled() ? 1 : 0;
+  g_pdl = enable ? 1 : 0;
+  return prev;
 }
 
 namespace api {
@@ -73,6 +79,8 @@ int gg_version(void) { return GG_VERSION; }
 const char *gg_last_error(void) { return g_err; }
 
 int gg_set_fast_mask(int enable) { return gg::set_fast_mask(enable); }
+
+int gg_set_pdl(int enable) { return gg::set_pdl(enable); }
 
 int gg_project_fwd(const float *mus, const void *sigma, int sigma_is_f64, const float *rotx, const float *roty,
                    const float *rotz, double tx, double ty, double tz, double focal, int B, int K, double *mu2d,

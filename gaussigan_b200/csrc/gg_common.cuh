@@ -117,6 +117,7 @@ __device__ __forceinline__ void pdl_enter_after(int i0, int i1, float f0, float 
 }
 
 bool pdl_enabled();   // gg_capi.cu
+int set_pdl(int enable);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -169,12 +169,11 @@ __device__ void stage_params(const double mu[2], const double sg[4], float *out)
   reinterpret_cast<float4 *>(out)[1] = hi;
 }
 
-// per-tile partial moments (shear coordinates t = dx + r dy) -> d mu2d, d sigma2d
-__device__ void conic_adjoint(const double mu[2], const double sg[4], const float *partials, int T,
-                              size_t tile_stride, double gmu[2], double gsg[4]) {
-  double Tm[GG_MOMENTS] = {0, 0, 0, 0, 0};
-  // fixed summation order (deterministic); loads are issued 8 tiles at a time so the T round trips to L2
-  // overlap instead of serialising (measured: 3200 -> ~900 cycles at T = 16)
+// fixed-order float64 sum of one Gaussian's T per-tile partial moments (deterministic); loads are issued 8 tiles at
+// a time so the T round trips to L2 overlap instead of serialising
+__device__ __forceinline__ void sum_partials(const float *partials, int T, size_t tile_stride, double Tm[GG_MOMENTS]) {
+#pragma unroll
+  for (int j = 0; j < GG_MOMENTS; ++j) Tm[j] = 0.0;
   for (int t0 = 0; t0 < T; t0 += 8) {
     float v[8][GG_MOMENTS];
 #pragma unroll
@@ -187,6 +186,11 @@ __device__ void conic_adjoint(const double mu[2], const double sg[4], const floa
 #pragma unroll
       for (int j = 0; j < GG_MOMENTS; ++j) Tm[j] += (double)v[u][j];
   }
+}
+
+// summed moments (shear coordinates t = dx + r dy) -> d mu2d, d sigma2d (accumulated into gmu, gsg)
+__device__ void conic_adjoint(const double mu[2], const double sg[4], const double Tm[GG_MOMENTS], double gmu[2],
+                              double gsg[4]) {
   double det2 = sg[0] * sg[3] - sg[1] * sg[2];
   double idet = 1.0 / det2;
   double P[4] = {sg[3] * idet, -sg[1] * idet, -sg[2] * idet, sg[0] * idet};
@@ -251,8 +255,12 @@ __global__ void __launch_bounds__(128) project_fwd_kernel(
   stage_params(p.mu2d, p.sig2d, params + (size_t)idx * GG_PARAM_STRIDE);
 }
 
-// one CTA per batch element; threads stride over its K Gaussians; d(angles) is reduced over K in
-// shared memory in a fixed order.
+// One CTA (128 threads) per batch element, Gaussians in chunks of 128.  Per chunk: (1) all threads sum the
+// per-tile partial moments column by column ([T][K][5] in global memory: coalesced, T independent loads in flight
+// per thread, fixed order) into shared memory, while the Gaussians' own inputs are already on their way;
+// (2) one thread per Gaussian runs the float64 adjoint.  d(angles) is reduced over K in shared memory in a
+// fixed order.  The kernel is a dependent float64 chain (~900 DFMA-class instructions per Gaussian at ~8 cycles):
+// launch-latency bound, so the point of (1) is to take the global round trips and the T-sum off that chain.
 __global__ void __launch_bounds__(128) project_bwd_kernel(
     const float *__restrict__ mus, const void *__restrict__ sigma, int sigma_is_f64,
     const float *__restrict__ rotx, const float *__restrict__ roty, const float *__restrict__ rotz,
@@ -260,32 +268,58 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     const float *__restrict__ partials, int T, const double *__restrict__ gmu2d_in,
     const double *__restrict__ gsigma2d_in, float *__restrict__ dmus, double *__restrict__ dsigma,
     float *__restrict__ drot) {
-  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   __shared__ double red[3][128];
+  __shared__ double Tm_s[128 * GG_MOMENTS];
   const int b = blockIdx.x;
-  Cam cam;
-  make_cam(rotx[b], roty[b], rotz[b], cam);
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
+  const float rxd = __ldg(rotx + b), ryd = __ldg(roty + b), rzd = __ldg(rotz + b);
   const double t[3] = {tx, ty, tz};
   const double f = (double)(float)focal;
   double Rbar[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  Cam cam;
+  bool have_cam = false;
 
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const size_t idx = (size_t)b * K + k;
+  for (int kb = 0; kb < K; kb += 128) {
+    const int kn = min(128, K - kb);
+    const int k = kb + (int)threadIdx.x;
+    const bool active = (int)threadIdx.x < kn;
+    const size_t idx = (size_t)b * K + (active ? k : kb);
     Proj p;
-    load_sigma(sigma, sigma_is_f64, idx, p.S);
+    load_sigma(sigma, sigma_is_f64, idx, p.S);                     // in flight during the column sums
 #pragma unroll
-    for (int i = 0; i < 3; ++i) p.mu[i] = (double)mus[idx * 3 + i];
-    project_one(cam, t, f, p);
-
+    for (int i = 0; i < 3; ++i) p.mu[i] = (double)__ldg(mus + idx * 3 + i);
     double gmu[2] = {0, 0}, gsg[4] = {0, 0, 0, 0};
     if (gmu2d_in) { gmu[0] = gmu2d_in[idx * 2]; gmu[1] = gmu2d_in[idx * 2 + 1]; }
     if (gsigma2d_in) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) gsg[i] = gsigma2d_in[idx * 4 + i];
     }
-    if (partials && T > 0)
-      conic_adjoint(p.mu2d, p.sig2d, partials + ((size_t)b * T * K + k) * GG_MOMENTS, T,
-                    (size_t)K * GG_MOMENTS, gmu, gsg);
+    const bool have_partials = partials && T > 0;
+    if (have_partials) {
+      const float *base = partials + ((size_t)b * T * K + kb) * GG_MOMENTS;
+      const size_t tile_stride = (size_t)K * GG_MOMENTS;
+      for (int c = threadIdx.x; c < kn * GG_MOMENTS; c += 128) {
+        double acc = 0.0;
+        for (int t0 = 0; t0 < T; t0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = (t0 + u < T) ? __ldg(base + (size_t)(t0 + u) * tile_stride + c) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc += (double)v[u];
+        }
+        Tm_s[c] = acc;
+      }
+    }
+    if (!have_cam) { make_cam(rxd, ryd, rzd, cam); have_cam = true; }
+    __syncthreads();
+    if (active) {
+    project_one(cam, t, f, p);
+    if (have_partials) {
+      double Tm[GG_MOMENTS];
+#pragma unroll
+      for (int j = 0; j < GG_MOMENTS; ++j) Tm[j] = Tm_s[threadIdx.x * GG_MOMENTS + j];
+      conic_adjoint(p.mu2d, p.sig2d, Tm, gmu, gsg);
+    }
 
     // ---- adjoint of: sigma2d = q * adj(M33), q = -dM / d33^2; mu2d = f (d31, -d23) / d33
     const double *M = p.M;
@@ -360,6 +394,8 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j = 0; j < 3; ++j) Rbar[i * 3 + j] += t1[i * 3 + j] + t2[i * 3 + j] + mbar[i] * p.mu[j];
+    }   // active
+    __syncthreads();   // Tm_s is rewritten by the next chunk
   }
 
   // ---- R = RX RY RZ (float32 in the forward; adjoint evaluated in float64 on the same float32 values)
@@ -435,7 +471,9 @@ __global__ void __launch_bounds__(128) conic_bwd_kernel(const void *__restrict__
     for (int i = 0; i < 4; ++i) sg[i] = s[i];
   }
   double gmu[2] = {0, 0}, gsg[4] = {0, 0, 0, 0};
-  conic_adjoint(mu, sg, partials + ((size_t)b * T * K + k) * GG_MOMENTS, T, (size_t)K * GG_MOMENTS, gmu, gsg);
+  double Tm[GG_MOMENTS];
+  sum_partials(partials + ((size_t)b * T * K + k) * GG_MOMENTS, T, (size_t)K * GG_MOMENTS, Tm);
+  conic_adjoint(mu, sg, Tm, gmu, gsg);
   if (dmu2d) { dmu2d[(size_t)idx * 2] = gmu[0]; dmu2d[(size_t)idx * 2 + 1] = gmu[1]; }
   if (dsigma2d) {
 #pragma unroll
@@ -457,7 +495,7 @@ cudaError_t launch_project_bwd(const float *mus, const void *sigma, int f64, con
                                const float *rz, double tx, double ty, double tz, double focal, int B, int K,
                                const float *partials, int T, const double *gmu2d, const double *gsigma2d,
                                float *dmus, double *dsigma, float *drot, cudaStream_t st) {
-  int threads = K >= 128 ? 128 : ((K + 31) / 32) * 32;
+  const int threads = 128;
   launch_pdl(project_bwd_kernel, dim3(B), dim3(threads), 0, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B, K, partials, T,
                                             gmu2d, gsigma2d, dmus, dsigma, drot);
   return cudaGetLastError();

@@ -124,6 +124,13 @@ GG_API int gg_splat_bwd(const float *params, int B, int K, int nscales, const in
  * previous setting.  Environment GG_PRECISE_MASK=1 selects 0 at load time. */
 GG_API int gg_set_fast_mask(int enable);
 
+/* Programmatic dependent launch.  1 (default): every kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and blocks in griddepcontrol.wait before its first global
+ * memory access, so its CTAs become resident and run their index arithmetic while the previous kernel of the
+ * stream drains (works eagerly and under stream capture; results are identical).  0: plain launches.
+ * Process-wide; returns the previous setting.  Environment GG_PDL=0 selects 0 at load time. */
+GG_API int gg_set_pdl(int enable);
+
 /* ---- direct consumer: sum-composite L1 loss ------------------------------------------------------
  * Replaces `m_recon_loss_bis` (mask/mask_gen_dynamic.py:785-787): loss = mean|0.5*(target+1) - mask| and its
  * gradient w.r.t. mask.  target [B,n,n] is uint8 (GG_TARGET_U8, normalised as :672) or float32 in [-1,1].

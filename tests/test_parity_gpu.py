@@ -524,3 +524,100 @@ def test_config3_full_cuda_pipeline(gg, cuda_device):
     names = ["v0", "v1", "u", "cannmu", "mu_t", "scale", "rx", "ry", "rz", "theta"]
     for a, b, nm in zip(go, gr, names):
         assert_close_norm(a, b, 5 * GRAD_RTOL, "C3 pipeline grad " + nm)
+
+
+# ------------------------------------------------------------ forward-differenced mask kernels / PDL
+@pytest.fixture
+def restore_modes(gg):
+    yield
+    gg.set_fast_mask(True)
+    gg.set_pdl(True)
+
+
+def _mask_and_grads(gg, d, n, gm):
+    lv = {k: d[k].clone().requires_grad_(True) for k in ("mus", "sigma", "roty")}
+    m = gg.render_silhouette(lv["mus"], lv["sigma"], d["rotx"], lv["roty"], d["rotz"], 0, 0, -2., size=n)
+    m.backward(gm)
+    return m.detach(), {k: v.grad for k, v in lv.items()}
+
+
+@pytest.mark.parametrize("n", [256, 128, 100, 64, 33, 32])
+def test_fast_and_direct_mask_arithmetic_vs_oracle(gg, cuda_device, restore_modes, n):
+    """Mask-only launches: the forward-differenced kernels (default) and the one-exponential-per-pixel kernels
+    against the float64 oracle, forward and gradients, on the reference's activation ranges."""
+    B, K = 6, 16
+    inp = rp.synth_inputs(B, K, seed=40 + n, angle=30.0)
+    lv = _leaves(inp)
+    ref = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0, 0, -2., sizes=(n,))[0].sum(-1)
+    gm = torch.randn(B, n, n, generator=torch.Generator().manual_seed(n))
+    (ref * gm).sum().backward()
+    d = _dev(inp, cuda_device)
+    errs = {}
+    for fast in (True, False):
+        gg.set_fast_mask(fast)
+        m, g = _mask_and_grads(gg, d, n, gm.to(cuda_device))
+        errs[fast] = max_rel(m, ref)
+        assert_close_norm(m, ref, FWD_RTOL if fast else 2e-6, f"mask fast={fast} n={n}")
+        for k in ("mus", "sigma", "roty"):
+            assert_close_norm(g[k], lv[k].grad, GRAD_RTOL, f"grad {k} fast={fast} n={n}")
+    assert errs[True] < 3e-6, errs        # measured ~6e-7: an order of magnitude inside the 1e-5 tolerance
+
+
+def test_steep_gaussians_fall_back_to_direct_evaluation(gg, cuda_device, restore_modes):
+    """Sub-pixel-thin, very elongated and far off-screen Gaussians: the recurrence's steepness guard must route
+    them to the direct form -- finite everywhere and equal to the oracle, forward and backward."""
+    B, K, n = 2, 6, 64
+    mus = torch.tensor([[[0.0, 0, 0], [0.4, -0.3, 0.1], [2.5, 0, 0], [0, -2.5, 0.2], [-0.2, 0.2, 0], [0.1, 0.1, 0.1]]] * B)
+    mus = mus.view(B, K, 1, 3).float()
+    sig = torch.eye(3, dtype=torch.float64).view(1, 1, 3, 3).repeat(B, K, 1, 1) * 0.02
+    sig[:, 0] *= 1e-3                                    # far thinner than a pixel
+    sig[:, 1, 0, 0] *= 1e-3                              # needle along y
+    sig[:, 4] *= 4.0
+    sig[:, 5, 0, 1] = sig[:, 5, 1, 0] = 0.015            # tilted
+    rot = (torch.tensor([[20.0], [-35.0]]), torch.tensor([[10.0], [160.0]]), torch.tensor([[0.0], [5.0]]))
+    lv = [t.clone().requires_grad_(True) for t in (mus, sig)]
+    ref = rp.get_landmarks(lv[0], lv[1], rot[0], rot[1], rot[2], 0, 0, -2., sizes=(n,))[0].sum(-1)
+    gm = torch.randn(B, n, n, generator=torch.Generator().manual_seed(2))
+    (ref * gm).sum().backward()
+    for fast in (True, False):
+        gg.set_fast_mask(fast)
+        dv = [t.to(cuda_device).requires_grad_(True) for t in (mus, sig)]
+        r = [t.to(cuda_device) for t in rot]
+        m = gg.render_silhouette(dv[0], dv[1], r[0], r[1], r[2], 0, 0, -2., size=n)
+        assert torch.isfinite(m).all()
+        assert_close_norm(m, ref, FWD_RTOL, f"steep mask fast={fast}")
+        m.backward(gm.to(cuda_device))
+        assert torch.isfinite(dv[0].grad).all() and torch.isfinite(dv[1].grad).all()
+        assert_close_norm(dv[0].grad, lv[0].grad, GRAD_RTOL, f"steep dmus fast={fast}")
+        assert_close_norm(dv[1].grad, lv[1].grad, GRAD_RTOL, f"steep dsigma fast={fast}")
+
+
+def test_programmatic_dependent_launch_changes_nothing(gg, cuda_device, restore_modes):
+    """Every kernel waits on its predecessor before touching memory: 40 back-to-back steps on changing inputs give
+    bit-identical results with PDL on and off (a missing wait would show up as a race here)."""
+    from gaussigan_b200.plan import SilhouetteLossStep, SilhouetteStep
+    B, K, n = 16, 16, 128
+    sets = []
+    for i in range(4):
+        d = _dev(rp.synth_inputs(B, K, seed=900 + i), cuda_device)
+        sets.append((d["mus"].reshape(B, K, 3).contiguous(), d["sigma"],
+                     *(d[k].reshape(B).contiguous() for k in ("rotx", "roty", "rotz")),
+                     torch.randn(B, n, n, device=cuda_device),
+                     (torch.rand(B, n, n, device=cuda_device) * 255).to(torch.uint8)))
+    out = {}
+    for pdl in (True, False):
+        gg.set_pdl(pdl)
+        step, fstep = SilhouetteStep(B, K, n, cuda_device), SilhouetteLossStep(B, K, n, cuda_device)
+        acc = []
+        for it in range(40):
+            mus, sig, rx, ry, rz, gm, tgt = sets[it % 4]
+            step.forward(mus, sig, rx, ry, rz)
+            g = [t.clone() for t in step.backward(gm)]
+            fstep.bind(mus, sig, rx, ry, rz)
+            fg = [t.clone() for t in fstep.loss_backward(tgt)]
+            acc.append([step.mask.clone()] + g + fg + [fstep.loss_partials.clone()])
+        torch.cuda.synchronize()
+        out[pdl] = acc
+    for a, b in zip(out[True], out[False]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)

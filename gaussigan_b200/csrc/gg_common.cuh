@@ -30,6 +30,7 @@ struct ScaleDesc {
   int tile_begin;  // first tile index of this scale inside the launch
   int tiles;       // tiles of this scale per batch element
   int contig;      // 1: a strip is 8 CONSECUTIVE pixels (gg_splat_fast.cu); 0: two half-row quads (gg_strip.cuh)
+  int cta;         // threads per CTA this geometry was planned for (kThreads except in gg_splat_fast.cu)
   float step;      // float32 (2 / (n-1)), TF 1.12 LinSpace step (mask_gen_dynamic.py:121-122)
   float *maps;     // forward outputs / backward upstream gradients (const in the backward)
   float *mask;

@@ -537,13 +537,14 @@ int env_int(const char *name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-void strip_geometry(ScaleDesc &d, int n, int rpt, bool contig = false) {
+void strip_geometry(ScaleDesc &d, int n, int rpt, bool contig = false, int cta = kThreads) {
   d.n = n;
   d.contig = contig ? 1 : 0;
+  d.cta = cta;
   d.spr = ((n + 3) / 4 + 1) / 2;     // threads per row: half the quads, each thread takes quad s and s + spr
-  d.sprc = d.spr < kThreads ? d.spr : kThreads;
-  d.rpp = d.spr <= kThreads ? kThreads / d.spr : 1;
-  d.chunks = (d.spr + kThreads - 1) / kThreads;
+  d.sprc = d.spr < cta ? d.spr : cta;
+  d.rpp = d.spr <= cta ? cta / d.spr : 1;
+  d.chunks = (d.spr + cta - 1) / cta;
   d.rows_per_tile = d.rpp * rpt;
   d.tiles = ((n + d.rows_per_tile - 1) / d.rows_per_tile) * d.chunks;
   d.step = n > 1 ? (1.0f - (-1.0f)) / (float)(n - 1) : 0.0f;
@@ -552,6 +553,7 @@ void strip_geometry(ScaleDesc &d, int n, int rpt, bool contig = false) {
 void quad_geometry(ScaleDesc &d, int n, int KQ, int passes) {
   d.n = n;
   d.contig = 0;
+  d.cta = kThreads;
   d.spr = d.sprc = d.rpp = d.chunks = 0;
   int per_row = (n * KQ + kThreads - 1) / kThreads;       // passes a CTA needs for one row
   d.rows_per_tile = passes / per_row > 0 ? passes / per_row : 1;
@@ -576,6 +578,7 @@ bool quad_ok(int K, int *shift) {
 // exported for gg_fused.cu
 void make_strip_desc(ScaleDesc &d, int n, int rpt) { strip_geometry(d, n, rpt); }
 
+int fast_cta(bool backward, int rpt);
 cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st);
 cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st);
 
@@ -593,6 +596,14 @@ int set_fast_mask(int enable) {
 }
 
 int fwd_rpt() { static int v = env_int("GG_RPT_FWD", 2); return v; }
+// CTA size of the forward-differenced kernels (threads): tuned so that the CTAs of the reference's batch (64
+// images of 256 rows) fill whole waves of resident CTAs; GG_FAST_WARPS_FWD / GG_FAST_WARPS_BWD override (4, 5, 6, 8)
+int fast_cta(bool backward, int rpt) {
+  static int f = env_int("GG_FAST_WARPS_FWD", 8), b = env_int("GG_FAST_WARPS_BWD", 8);
+  int w = backward ? b : f;
+  if (rpt >= 4 || (w != 4 && w != 5 && w != 6)) w = 8;
+  return 32 * w;
+}
 int bwd_rpt() { static int v = env_int("GG_RPT_BWD", 2); return v; }
 int quad_passes(bool backward) {
   static int f = env_int("GG_QUAD_PASSES", 16), b = env_int("GG_QUAD_PASSES_BWD", 32);
@@ -626,7 +637,7 @@ static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool
       if (has_mask[i]) pl.maps_any_mask = true;
     } else if (has_mask[i]) {
       ScaleDesc &d = pl.strip_mask.sc[pl.strip_mask.nscales++];
-      if (fast_mask()) strip_geometry(d, sizes[i], rpt >= 4 ? 4 : 2, true);   // fast kernels work on row pairs
+      if (fast_mask()) strip_geometry(d, sizes[i], rpt >= 4 ? 4 : 2, true, fast_cta(backward, rpt));   // row pairs
       else strip_geometry(d, sizes[i], rpt);
       d.tile_begin = tb_mask;
       tb_mask += d.tiles;

@@ -33,6 +33,16 @@ namespace gg {
 
 namespace {
 
+#ifndef GG_BWD_KUNROLL
+#define GG_BWD_KUNROLL 1      // Gaussians processed per main-loop iteration of the backward (ILP vs registers)
+#endif
+#ifndef GG_BWD_MINBLOCKS
+#define GG_BWD_MINBLOCKS 3    // resident 256-thread CTAs per SM the backward is compiled for
+#endif
+#ifndef GG_FWD_KUNROLL
+#define GG_FWD_KUNROLL 0      // 0 = leave it to the compiler
+#endif
+constexpr int kBwdKUnroll = GG_BWD_KUNROLL;
 constexpr float kMaxSlope = 13.0f;     // largest |d(exponent)/d(pixel)| the recurrence is trusted with
 
 // Per-Gaussian constants of one CTA (its scale fixes h): 3 x float4 in shared memory
@@ -42,7 +52,7 @@ constexpr float kMaxSlope = 13.0f;     // largest |d(exponent)/d(pixel)| the rec
 __device__ __forceinline__ void stage_fast_consts(const float *__restrict__ gparams, int kn, float h, float x_lo,
                                                   float x_hi, float y_lo, float y_hi, float4 *sc) {
   const float4 *gp = reinterpret_cast<const float4 *>(gparams);
-  for (int k = threadIdx.x; k < kn; k += kThreads) {
+  for (int k = threadIdx.x; k < kn; k += blockDim.x) {
     const float4 lo = __ldg(gp + 2 * k);
     const float nE = __ldg(reinterpret_cast<const float *>(gp + 2 * k + 1));
     const float nAh = __fmul_rn(lo.z, h);
@@ -138,7 +148,7 @@ __device__ __forceinline__ void load8c(const float *rowp, int col0, int n, float
 __device__ __forceinline__ void tile_extent(const ScaleDesc &s, int tile_local, float &x_lo, float &x_hi, float &y_lo,
                                             float &y_hi) {
   const int rt = tile_local / s.chunks, ch = tile_local - rt * s.chunks;
-  const int c_lo = ch * kThreads * 8, c_hi = min(s.n, c_lo + kThreads * 8) - 1;
+  const int c_lo = ch * s.cta * 8, c_hi = min(s.n, c_lo + s.cta * 8) - 1;
   const int r_lo = rt * s.rows_per_tile, r_hi = min(s.n, r_lo + s.rows_per_tile) - 1;
   x_lo = grid_coord(c_lo, s.step); x_hi = grid_coord(c_hi, s.step);
   y_lo = grid_coord(r_lo, s.step); y_hi = grid_coord(r_hi, s.step);
@@ -148,8 +158,8 @@ __device__ __forceinline__ void tile_extent(const ScaleDesc &s, int tile_local, 
 
 // ================================================================================== forward (mask)
 // NP = row pairs per thread (rows per thread = 2 NP, spaced s.rpp apart)
-template <int NP>
-__global__ void __launch_bounds__(kThreads) splat_fwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
+template <int NP, int NW>
+__global__ void __launch_bounds__(NW * 32) splat_fwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
   extern __shared__ float4 sc[];   // [K][3]
   const int b = blockIdx.x / a.T;
   const int tile = blockIdx.x - b * a.T;
@@ -211,11 +221,12 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_mask_fast_kernel(const __g
 // FUSED = true : m_recon_loss_bis in one launch -- a forward pass builds the silhouette in registers, the residual
 //                against the target gives dL/dmask = -sign(0.5 (t + 1) - m) / N (mask/mask_gen_dynamic.py:785-787)
 //                and the loss partial; then the same CTA runs the backward.  K <= kKBlock.
-template <int NP, bool FUSED>
-__global__ void __launch_bounds__(kThreads, NP == 1 ? 3 : 1) splat_bwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
+// NW = warps per CTA; the register cap keeps 80 registers per thread at every CTA size
+template <int NP, bool FUSED, int NW>
+__global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW : 1) splat_bwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
   __shared__ float4 sc[kKBlock * 3];
-  __shared__ __align__(16) float stage[kWarps][kStageCols][kStagePad];
-  __shared__ float warpsum[kWarps][kKBlock * GG_MOMENTS];
+  __shared__ __align__(16) float stage[NW][kStageCols][kStagePad];
+  __shared__ float warpsum[NW][kKBlock * GG_MOMENTS];
   __shared__ float lut[FUSED ? 256 : 1];
 
   const int b = blockIdx.x / a.T;
@@ -261,8 +272,8 @@ __global__ void __launch_bounds__(kThreads, NP == 1 ? 3 : 1) splat_bwd_mask_fast
   if (FUSED && a.target_kind == GG_TARGET_U8) {
     // 0.5 * ((raw / 127.5 - 1) + 1), op by op in float32 as the reference (:672, :787): one division per
     // thread instead of one per pixel
-    const float v = (float)threadIdx.x;
-    lut[threadIdx.x] = __fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(v, 127.5f), 1.0f), 1.0f), 0.5f);
+    for (int i = threadIdx.x; i < 256; i += NW * 32)
+      lut[i] = __fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn((float)i, 127.5f), 1.0f), 1.0f), 0.5f);
   }
   __syncthreads();
 
@@ -337,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, NP == 1 ? 3 : 1) splat_bwd_mask_fast
     if (threadIdx.x == 0) {
       float tot = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) tot += warpsum[w][0];
+      for (int w = 0; w < NW; ++w) tot += warpsum[w][0];
       a.loss_partials[(size_t)b * a.T + tile] = tot;
     }
     __syncthreads();
@@ -355,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, NP == 1 ? 3 : 1) splat_bwd_mask_fast
       W2[p][j] = pack2((ga * xi) * xi, (gb * xi) * xi);
     }
 
+#pragma unroll kBwdKUnroll
   for (int kk = 0; kk < kn; ++kk) {
     const float4 c0 = sc[3 * kk], c1 = sc[3 * kk + 1];
     const bool steep = sc[3 * kk + 2].x != 0.f;
@@ -410,33 +422,42 @@ __global__ void __launch_bounds__(kThreads, NP == 1 ? 3 : 1) splat_bwd_mask_fast
   }
   __syncthreads();
   float *out = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K + k0) * GG_MOMENTS;
-  for (int c = threadIdx.x; c < kn * GG_MOMENTS; c += kThreads) {
+  for (int c = threadIdx.x; c < kn * GG_MOMENTS; c += NW * 32) {
     float acc = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) acc += warpsum[w][c];
+    for (int w = 0; w < NW; ++w) acc += warpsum[w][c];
     out[c] = acc;
   }
 }
 
 // ====================================================================================== launchers
-// rpt = rows per thread of the plan (2 or 4; fast_rpt() in gg_splat.cu clamps)
+// rpt = rows per thread of the plan (2 or 4); the CTA size comes from the plan's geometry (sc[0].cta)
 cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)B * a.T));
   size_t smem = (size_t)a.K * 3 * sizeof(float4);
-  if (rpt == 4) launch_pdl(splat_fwd_mask_fast_kernel<2>, dim3(grid), dim3(kThreads), smem, st, a);
-  else launch_pdl(splat_fwd_mask_fast_kernel<1>, dim3(grid), dim3(kThreads), smem, st, a);
+  const int cta = a.sc[0].cta;
+  if (rpt == 4) launch_pdl(splat_fwd_mask_fast_kernel<2, 8>, grid, dim3(256), smem, st, a);
+  else if (cta == 128) launch_pdl(splat_fwd_mask_fast_kernel<1, 4>, grid, dim3(128), smem, st, a);
+  else if (cta == 160) launch_pdl(splat_fwd_mask_fast_kernel<1, 5>, grid, dim3(160), smem, st, a);
+  else if (cta == 192) launch_pdl(splat_fwd_mask_fast_kernel<1, 6>, grid, dim3(192), smem, st, a);
+  else launch_pdl(splat_fwd_mask_fast_kernel<1, 8>, grid, dim3(256), smem, st, a);
   return cudaGetLastError();
+}
+
+template <bool FUSED>
+static void launch_bwd_fast_t(const SplatArgs &a, dim3 grid, int rpt, cudaStream_t st) {
+  const int cta = a.sc[0].cta;
+  if (rpt == 4) launch_pdl(splat_bwd_mask_fast_kernel<2, FUSED, 8>, grid, dim3(256), 0, st, a);
+  else if (cta == 128) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 4>, grid, dim3(128), 0, st, a);
+  else if (cta == 160) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 5>, grid, dim3(160), 0, st, a);
+  else if (cta == 192) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 6>, grid, dim3(192), 0, st, a);
+  else launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 8>, grid, dim3(256), 0, st, a);
 }
 
 cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)B * a.T), (unsigned)((a.K + kKBlock - 1) / kKBlock));
-  if (fused) {
-    if (rpt == 4) launch_pdl(splat_bwd_mask_fast_kernel<2, true>, dim3(grid), dim3(kThreads), 0, st, a);
-    else launch_pdl(splat_bwd_mask_fast_kernel<1, true>, dim3(grid), dim3(kThreads), 0, st, a);
-  } else {
-    if (rpt == 4) launch_pdl(splat_bwd_mask_fast_kernel<2, false>, dim3(grid), dim3(kThreads), 0, st, a);
-    else launch_pdl(splat_bwd_mask_fast_kernel<1, false>, dim3(grid), dim3(kThreads), 0, st, a);
-  }
+  if (fused) launch_bwd_fast_t<true>(a, grid, rpt, st);
+  else launch_bwd_fast_t<false>(a, grid, rpt, st);
   return cudaGetLastError();
 }
 

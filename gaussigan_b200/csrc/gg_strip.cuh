@@ -35,7 +35,7 @@ __device__ __forceinline__ StripPos strip_pos(const ScaleDesc &s, int tile_local
   int ch = tile_local - rt * s.chunks;
   int rp = threadIdx.x / s.sprc;
   int sc = threadIdx.x - rp * s.sprc;
-  int strip = ch * kThreads + sc;
+  int strip = ch * s.cta + sc;
   p.colA = s.contig ? strip * 8 : strip * 4;
   p.colB = s.contig ? strip * 8 + 4 : (strip + s.spr) * 4;
   p.row0 = rt * s.rows_per_tile + rp;

@@ -31,6 +31,28 @@ template<int MODE> __global__ void __launch_bounds__(256) k(float* out, float a,
         asm volatile("fma.rn.f32x2 %0, %1, %2, %3;":"=l"(r):"l"(x),"l"(y),"l"(z));
         asm volatile("mov.b64 {%0,%1}, %2;":"=f"(v[i]),"=f"(v[i+1]):"l"(r));
       }
+    } else if(MODE==9 || MODE==10 || MODE==11){ // FMUL2 / FADD2 / FFMA2 with a zero addend (a packed multiply on the FMA path)
+      #pragma unroll
+      for(int i=0;i<16;i+=2){
+        unsigned long long x,y,z,r;
+        asm volatile("mov.b64 %0, {%1,%2};":"=l"(x):"f"(v[i]),"f"(v[i+1]));
+        asm volatile("mov.b64 %0, {%1,%1};":"=l"(y):"f"(a));
+        if(MODE==9) asm volatile("mul.rn.f32x2 %0, %1, %2;":"=l"(r):"l"(x),"l"(y));
+        else if(MODE==10) asm volatile("add.rn.f32x2 %0, %1, %2;":"=l"(r):"l"(x),"l"(y));
+        else { asm volatile("mov.b64 %0, {%1,%1};":"=l"(z):"f"(0.0f)); asm volatile("fma.rn.f32x2 %0, %1, %2, %3;":"=l"(r):"l"(x),"l"(y),"l"(z)); }
+        asm volatile("mov.b64 {%0,%1}, %2;":"=f"(v[i]),"=f"(v[i+1]):"l"(r));
+      }
+    } else if(MODE==12){ // the backward strip mix: 20 FMUL2 + 25 FFMA2 + 1 FADD2 per 4 MUFU
+      #pragma unroll
+      for(int i=0;i<16;i+=2){
+        unsigned long long x,y,z,r;
+        asm volatile("mov.b64 %0, {%1,%2};":"=l"(x):"f"(v[i]),"f"(v[i+1]));
+        asm volatile("mov.b64 %0, {%1,%1};":"=l"(y):"f"(a));
+        asm volatile("mov.b64 %0, {%1,%1};":"=l"(z):"f"(b));
+        if((i&2)==0) asm volatile("mul.rn.f32x2 %0, %1, %2;":"=l"(r):"l"(x),"l"(y));
+        else asm volatile("fma.rn.f32x2 %0, %1, %2, %3;":"=l"(r):"l"(x),"l"(y),"l"(z));
+        asm volatile("mov.b64 {%0,%1}, %2;":"=f"(v[i]),"=f"(v[i+1]):"l"(r));
+      }
     } else if(MODE==5){ // 4 FFMA : 1 EX2 (x4)
       #pragma unroll
       for(int i=0;i<16;i+=4){ v[i]=fmaf(v[i],a,b); v[i+1]=fmaf(v[i+1],a,b); v[i+2]=fmaf(v[i+2],a,b); v[i+3]=ex2(fmaf(v[i+3],a,b)); }
@@ -67,6 +89,7 @@ template<int MODE> void run(const char* name, double ops_per_iter_thread, double
 }
 int main(){
   run<0>("FFMA",16,0); run<1>("FADD",16,0); run<2>("FMUL",16,0); run<3>("MUFU.EX2",16,16); run<4>("FFMA2 (lane-ops=2/instr)",16,0);
+  run<9>("FMUL2 (lane-ops=2/instr)",16,0); run<10>("FADD2 (lane-ops=2/instr)",16,0); run<11>("FFMA2 with zero addend",16,0); run<12>("FMUL2 : FFMA2 = 1 : 1",16,0);
   run<5>("4 FFMA : 1 EX2 (5 slots)",20,4); run<7>("6 FFMA: 1 EX2 (7 slots)",14,2); run<6>("8 FFMA : 1 EX2 (9 slots)",18,2); run<8>("fwd-loop shape (5 slots/px)",40,8);
   return 0;
 }

@@ -378,7 +378,7 @@ def run_gpu(args):
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
     e2e = None
     try:
-        host = HostSilhouetteStep(B, K, n, dev, depth=3)
+        host = HostSilhouetteStep(B, K, n, dev, depth=4)
         hsets = [host.make_host_inputs(s[2], s[3]) for s in sets[:min(R, 4)]]
         for i in range(3):
             host.submit(hsets[i % len(hsets)])
@@ -396,7 +396,22 @@ def run_gpu(args):
             t = torch.tensor([ems], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
+        # raw pinned-host -> device bandwidth for a transfer of this step's size: what bounds the e2e number
+        hb = torch.empty(host.h2d_bytes, dtype=torch.uint8).pin_memory()
+        db = torch.empty(host.h2d_bytes, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            db.copy_(hb, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(50):
+            db.copy_(hb, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        h2d_us = c0.elapsed_time(c1) / 50 * 1e3
         e2e = {"value": world * B / (ems / args.steps * 1e-3), "unit": UNIT,
+               "h2d_copy_alone_us": h2d_us, "h2d_copy_alone_gbs": host.h2d_bytes / (h2d_us * 1e-6) / 1e9,
+               "bound": "PCIe host->device copy of the uint8 target masks (4.19 MB/step): e2e ms_per_step vs h2d_copy_alone_us",
                "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
                "ms_per_step": ems / args.steps, "api": "gaussigan_b200.host.HostSilhouetteStep.submit (pinned host buffers)",
                "launches_per_step": host.LAUNCHES_PER_STEP}

@@ -1,6 +1,7 @@
 // gg_host.cu -- the host-buffer entry point: one call = H2D copies + the whole fwd/loss/bwd chain +
 // D2H copies, all asynchronous on the caller's stream.  This is the form a host-language binding of the
 // reference would use (the reference feeds numpy arrays through session.run, mask/infer_masks.py:435-456).
+#include <cstdlib>
 #include <cstring>
 #include "gg_common.cuh"
 #include "gg_launch.h"
@@ -38,9 +39,28 @@ StepLayout step_layout(int B, int K, int n, int target_kind) {
   return L;
 }
 
+// device-usable alias of a pinned host pointer (UVA), or NULL when the memory is pageable / unknown
+template <typename T>
+static T *mapped_or_null(T *host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+  return reinterpret_cast<T *>(const_cast<void *>(static_cast<const void *>(at.devicePointer)));
+}
+
+static bool zero_copy_enabled() {
+  static const bool on = [] {
+    const char *v = std::getenv("GG_ZEROCOPY");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace gg
 
 using namespace gg::api;
+using gg::mapped_or_null;
+using gg::zero_copy_enabled;
 
 extern "C" {
 
@@ -93,32 +113,57 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
     if (e__ != cudaSuccess) return cuda_fail(e__, what);    \
   } while (0)
   const size_t px = (size_t)B * n * n;
-  GG_TRY(cudaMemcpyAsync(d_mus, mus_host, (size_t)B * K * 3 * 4, cudaMemcpyHostToDevice, st), "H2D mus");
-  GG_TRY(cudaMemcpyAsync(d_sigma, sigma_host, (size_t)B * K * 9 * 8, cudaMemcpyHostToDevice, st), "H2D sigma");
-  GG_TRY(cudaMemcpyAsync(d_rot, rotx_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D rotx");
-  GG_TRY(cudaMemcpyAsync(d_rot + B, roty_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D roty");
-  GG_TRY(cudaMemcpyAsync(d_rot + 2 * (size_t)B, rotz_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D rotz");
-  GG_TRY(cudaMemcpyAsync(d_target, target_host, px * (target_kind == GG_TARGET_U8 ? 1 : 4), cudaMemcpyHostToDevice, st),
-         "H2D target");
-  GG_TRY(gg::launch_project_fwd(d_mus, d_sigma, 1, d_rot, d_rot + B, d_rot + 2 * (size_t)B, tx, ty, tz, focal, B, K,
+  // The Gaussians, the camera and the gradients are ~90 KB per step in nine arrays: when the caller's buffers are
+  // pinned (cudaHostAlloc / cudaHostRegister, device-accessible through UVA) the two projection kernels read and
+  // write them in place over PCIe and the nine small copies disappear from the copy-engine queues; only the target
+  // mask (the bulk of the bytes) goes through the DMA engine.  Pageable buffers take the copy path.
+  const float *k_mus = mapped_or_null(mus_host);
+  const double *k_sigma = mapped_or_null(sigma_host);
+  const float *k_rx = mapped_or_null(rotx_host), *k_ry = mapped_or_null(roty_host), *k_rz = mapped_or_null(rotz_host);
+  const bool in_place_in = zero_copy_enabled() && k_mus && k_sigma && k_rx && k_ry && k_rz;
+  if (!in_place_in) {
+    GG_TRY(cudaMemcpyAsync(d_mus, mus_host, (size_t)B * K * 3 * 4, cudaMemcpyHostToDevice, st), "H2D mus");
+    GG_TRY(cudaMemcpyAsync(d_sigma, sigma_host, (size_t)B * K * 9 * 8, cudaMemcpyHostToDevice, st), "H2D sigma");
+    GG_TRY(cudaMemcpyAsync(d_rot, rotx_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D rotx");
+    GG_TRY(cudaMemcpyAsync(d_rot + B, roty_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D roty");
+    GG_TRY(cudaMemcpyAsync(d_rot + 2 * (size_t)B, rotz_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D rotz");
+    k_mus = d_mus; k_sigma = d_sigma; k_rx = d_rot; k_ry = d_rot + B; k_rz = d_rot + 2 * (size_t)B;
+  }
+  // Experimental (GG_ZEROCOPY_TARGET=1): the splat kernel reads the target mask from pinned host memory as well
+  const void *k_target = d_target;
+  {
+    static const bool zc_target = [] { const char *v = std::getenv("GG_ZEROCOPY_TARGET"); return v && v[0] == '1'; }();
+    const void *m = zc_target ? mapped_or_null(target_host) : nullptr;
+    if (m) k_target = m;
+    else
+      GG_TRY(cudaMemcpyAsync(d_target, target_host, px * (target_kind == GG_TARGET_U8 ? 1 : 4), cudaMemcpyHostToDevice,
+                             st), "H2D target");
+  }
+  GG_TRY(gg::launch_project_fwd(k_mus, k_sigma, 1, k_rx, k_ry, k_rz, tx, ty, tz, focal, B, K,
                                 nullptr, nullptr, d_params, st), "project_fwd");
   if (K <= 64) {
-    GG_TRY(gg::launch_silhouette_loss_fused(d_params, d_target, target_kind, B, K, n, mask_host ? d_mask : nullptr,
+    GG_TRY(gg::launch_silhouette_loss_fused(d_params, k_target, target_kind, B, K, n, mask_host ? d_mask : nullptr,
                                             d_part, d_loss, L.T, st), "silhouette_loss_fused");
   } else {
     float *masks[1] = {d_mask};
     GG_TRY(gg::launch_splat_fwd(d_params, B, K, 1, sizes, nullptr, masks, GG_LAYOUT_NHWC, st), "splat_fwd");
-    GG_TRY(gg::launch_mask_l1_loss_bwd(d_mask, d_target, target_kind, B, n, d_gmask, d_loss, GG_LOSS_PARTIALS, st),
+    GG_TRY(gg::launch_mask_l1_loss_bwd(d_mask, k_target, target_kind, B, n, d_gmask, d_loss, GG_LOSS_PARTIALS, st),
            "mask_l1_loss_bwd");
     const float *gmasks[1] = {d_gmask};
     GG_TRY(gg::launch_splat_bwd(d_params, B, K, 1, sizes, nullptr, gmasks, GG_LAYOUT_NHWC, d_part, L.T, st), "splat_bwd");
   }
-  GG_TRY(gg::launch_project_bwd(d_mus, d_sigma, 1, d_rot, d_rot + B, d_rot + 2 * (size_t)B, tx, ty, tz, focal, B, K,
-                                d_part, L.T, nullptr, nullptr, d_dmus, d_dsig, d_drot, st), "project_bwd");
+  float *k_dmus = mapped_or_null(dmus_host), *k_drot = mapped_or_null(drot_host);
+  double *k_dsig = mapped_or_null(dsigma_host);
+  const bool in_place_out = zero_copy_enabled() && k_dmus && k_dsig && k_drot;
+  GG_TRY(gg::launch_project_bwd(k_mus, k_sigma, 1, k_rx, k_ry, k_rz, tx, ty, tz, focal, B, K, d_part, L.T, nullptr,
+                                nullptr, in_place_out ? k_dmus : d_dmus, in_place_out ? k_dsig : d_dsig,
+                                in_place_out ? k_drot : d_drot, st), "project_bwd");
   GG_TRY(cudaMemcpyAsync(loss_partials_host, d_loss, (size_t)L.nloss * 4, cudaMemcpyDeviceToHost, st), "D2H loss");
-  GG_TRY(cudaMemcpyAsync(dmus_host, d_dmus, (size_t)B * K * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H dmus");
-  GG_TRY(cudaMemcpyAsync(dsigma_host, d_dsig, (size_t)B * K * 9 * 8, cudaMemcpyDeviceToHost, st), "D2H dsigma");
-  GG_TRY(cudaMemcpyAsync(drot_host, d_drot, (size_t)B * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H drot");
+  if (!in_place_out) {
+    GG_TRY(cudaMemcpyAsync(dmus_host, d_dmus, (size_t)B * K * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H dmus");
+    GG_TRY(cudaMemcpyAsync(dsigma_host, d_dsig, (size_t)B * K * 9 * 8, cudaMemcpyDeviceToHost, st), "D2H dsigma");
+    GG_TRY(cudaMemcpyAsync(drot_host, d_drot, (size_t)B * 3 * 4, cudaMemcpyDeviceToHost, st), "D2H drot");
+  }
   if (mask_host) GG_TRY(cudaMemcpyAsync(mask_host, d_mask, px * 4, cudaMemcpyDeviceToHost, st), "D2H mask");
 #undef GG_TRY
   return GG_OK;

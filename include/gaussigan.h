@@ -200,7 +200,10 @@ GG_API int gg_deform_bwd(const float *scale, const float *ang, const double *U, 
  * caller and private to this call until the stream has drained.  mask_host may be NULL (silhouette not
  * copied back).  sigma_host is float64 [B,K,3,3].  loss_partials_host receives
  * gg_silhouette_step_loss_count(B, K, n) floats; loss = sum(partials) / (B*n*n).  For K <= 64 the step is three
- * launches (projection, fused splat+loss+backward, projection adjoint), otherwise five. */
+ * launches (projection, fused splat+loss+backward, projection adjoint), otherwise five.  When the Gaussian / camera /
+ * gradient buffers are pinned, the projection kernels read and write them in place over PCIe (no copies for those
+ * ~90 KB; GG_ZEROCOPY=0 forces copies); the target mask always goes through the copy engine.  As with any
+ * asynchronous copy, host inputs must stay untouched until the stream has passed this call. */
 GG_API size_t gg_silhouette_step_workspace_bytes(int B, int K, int n, int target_kind);
 GG_API int gg_silhouette_step_loss_count(int B, int K, int n);
 GG_API int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, const float *rotx_host,

@@ -579,6 +579,7 @@ bool quad_ok(int K, int *shift) {
 void make_strip_desc(ScaleDesc &d, int n, int rpt) { strip_geometry(d, n, rpt); }
 
 int fast_cta(bool backward, int rpt);
+cudaError_t launch_splat_bwd_quad_tma(const SplatArgs &a, int B, int kq_shift, bool any_mask, cudaStream_t st);
 cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st);
 cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st);
 
@@ -759,9 +760,14 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
       dim3 grid((unsigned)((size_t)B * a.T));
       // the quad kernel adds gmask to every channel only when a scale carries one; scales without a
       // gmask are handled by giving the kernel a per-scale NULL check
-      if (pl.maps_any_mask) launch_pdl(splat_bwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
-      else launch_pdl(splat_bwd_quad_kernel<false>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
-      err = cudaGetLastError();
+      static const bool use_tma = env_int("GG_TMA_BWD", 1) != 0;
+      if (use_tma) {
+        err = launch_splat_bwd_quad_tma(a, B, pl.kq_shift, pl.maps_any_mask, st);
+      } else {
+        if (pl.maps_any_mask) launch_pdl(splat_bwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
+        else launch_pdl(splat_bwd_quad_kernel<false>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
+        err = cudaGetLastError();
+      }
     } else {
       int mode = layout == GG_LAYOUT_NCHW ? 1 : 2;
       err = rpt == 1 ? launch_bwd_strip<1>(a, mode, B, st) : rpt == 4 ? launch_bwd_strip<4>(a, mode, B, st)

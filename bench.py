@@ -380,7 +380,9 @@ def run_gpu(args):
     try:
         host = HostSilhouetteStep(B, K, n, dev, depth=4)
         hsets = [host.make_host_inputs(s[2], s[3]) for s in sets[:min(R, 4)]]
-        for i in range(3):
+        # the first transfers out of freshly pinned buffers run at a fraction of the steady PCIe rate on this pool's
+        # hosts (measured: 390 us per 4 MiB for the first ~100 copies, ~110 us after): warm the path up properly
+        for i in range(max(200, args.warmup)):
             host.submit(hsets[i % len(hsets)])
         host.drain()
         barrier()

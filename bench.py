@@ -401,7 +401,7 @@ def run_gpu(args):
         # raw pinned-host -> device bandwidth for a transfer of this step's size: what bounds the e2e number
         hb = torch.empty(host.h2d_bytes, dtype=torch.uint8).pin_memory()
         db = torch.empty(host.h2d_bytes, dtype=torch.uint8, device=dev)
-        for _ in range(3):
+        for _ in range(150):
             db.copy_(hb, non_blocking=True)
         torch.cuda.synchronize(dev)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

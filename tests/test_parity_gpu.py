@@ -621,3 +621,35 @@ def test_programmatic_dependent_launch_changes_nothing(gg, cuda_device, restore_
     for a, b in zip(out[True], out[False]):
         for x, y in zip(a, b):
             assert torch.equal(x, y)
+
+
+def test_batches_beyond_one_grid_dimension(gg, cuda_device):
+    """More than 65535 batch elements in one call (beyond one grid dimension): tiny images, the
+    first and last batch elements against the oracle, forward, fused loss and gradients."""
+    from gaussigan_b200.plan import SilhouetteLossStep
+    B, K, n = 65535 + 9, 2, 8
+    base = rp.synth_inputs(16, K, seed=5)
+    rep = (B + 15) // 16
+    inp = {k: v.repeat(rep, *([1] * (v.dim() - 1)))[:B].contiguous() for k, v in base.items()}
+    inp["roty"] = (inp["roty"] + torch.arange(B, dtype=torch.float32).view(B, 1) * 1e-3).contiguous()   # all different
+    d = _dev(inp, cuda_device)
+    lv = {k: d[k].clone().requires_grad_(True) for k in ("mus", "sigma", "roty")}
+    m = gg.render_silhouette(lv["mus"], lv["sigma"], d["rotx"], lv["roty"], d["rotz"], 0, 0, -2., size=n)
+    gm = torch.randn(B, n, n, generator=torch.Generator().manual_seed(1))
+    m.backward(gm.to(cuda_device))
+    sel = torch.cat([torch.arange(0, 5), torch.arange(65530, 65540), torch.arange(B - 5, B)])
+    sub_in = {k: v[sel].clone().requires_grad_(True) for k, v in inp.items()}
+    ref = rp.get_landmarks(sub_in["mus"], sub_in["sigma"], sub_in["rotx"], sub_in["roty"], sub_in["rotz"], 0, 0, -2.,
+                           sizes=(n,))[0].sum(-1)
+    (ref * gm[sel]).sum().backward()
+    assert_close_norm(m[sel.to(cuda_device)], ref, FWD_RTOL, "big-batch mask")
+    for k in ("mus", "sigma", "roty"):
+        assert_close_norm(lv[k].grad[sel.to(cuda_device)], sub_in[k].grad, GRAD_RTOL, f"big-batch grad {k}")
+    # fused loss kernel on the same batch: loss equals the mean over all images of the unfused residual
+    tgt = (torch.rand(B, n, n, generator=torch.Generator().manual_seed(2)) * 255).to(torch.uint8)
+    step = SilhouetteLossStep(B, K, n, cuda_device)
+    step.bind(d["mus"].reshape(B, K, 3).contiguous(), d["sigma"], *(d[k].reshape(B).contiguous() for k in ("rotx", "roty", "rotz")))
+    step.loss_backward(tgt.to(cuda_device))
+    t01 = ((tgt.float() / 127.5 - 1.0) + 1.0) * 0.5
+    want = float((t01.to(cuda_device) - m.detach()).abs().double().mean())
+    assert abs(step.loss() - want) <= 1e-6 * abs(want)

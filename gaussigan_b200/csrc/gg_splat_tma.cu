@@ -4,9 +4,9 @@
 // [B,n,n,K] maps (mask/mask_gen_dynamic.py:141, the tensors the generator consumes at :523-529) are reduced to
 // five moments per Gaussian.  The kernel is HBM-read bound (4 K bytes per pixel, ~45 instructions per 16 bytes),
 // and with plain loads a thread can only keep a few 128-bit loads in flight in registers: measured 2.6 TB/s of the
-// 6.5 TB/s the part delivers.  Here the rows of a tile -- contiguous in NHWC -- are streamed into a 4-stage shared
-// memory ring by cp.async.bulk (one elected thread, completion on an mbarrier), 16 KB per stage, so 64 KB per CTA
-// are in flight independent of the register file; the compute threads read their quad with one LDS.128.
+// 6.5 TB/s the part delivers.  Here the rows of a tile -- contiguous in NHWC -- are streamed into shared-memory
+// rings by cp.async.bulk (completion on mbarriers), 64 KB per CTA in flight independent of the register file; the
+// compute threads read their quad with one LDS.128.
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
 #include "gg_launch.h"
@@ -15,9 +15,13 @@ namespace gg {
 
 namespace {
 
-constexpr int kQStages = 4;                    // ring depth
-constexpr int kQBatch = 4 * kThreads;          // quads (16-byte chunks: one pixel x 4 Gaussians) per stage = 16 KB
-constexpr int kStageBytes = kQBatch * 16;
+#ifndef GG_TMA_STAGES
+#define GG_TMA_STAGES 4
+#endif
+#ifndef GG_TMA_MINBLOCKS
+#define GG_TMA_MINBLOCKS 2
+#endif
+constexpr int kQStages = GG_TMA_STAGES;        // ring depth
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -49,11 +53,19 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 
 }  // namespace
 
+// One ring PER WARP: a warp streams its own 128-quad (2 KB) slices of the tile, its lane 0 issues the bulk copies and
+// the warp waits on its own mbarriers -- no CTA-wide synchronisation inside the loop, warps drift freely.
+// The tile (rows [row_begin, row_end) of one image) is one contiguous span of quads in NHWC; slice j of the span is
+// handled by warp (j mod 8) and lies inside one image row because quads_per_row is a multiple of 128 (checked by
+// the launcher; other shapes take the register-staged kernel).
+constexpr int kWarpQuads = 128;                        // quads per warp slice = 4 per lane
+constexpr int kWarpStageBytes = kWarpQuads * 16;       // 2 KB
+
 template <bool WITH_GMASK>
-__global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_tma_kernel(const __grid_constant__ SplatArgs a,
+__global__ void __launch_bounds__(kThreads, GG_TMA_MINBLOCKS) splat_bwd_quad_tma_kernel(const __grid_constant__ SplatArgs a,
                                                                          int kq_shift) {
-  extern __shared__ __align__(128) unsigned char ring[];       // [kQStages][kStageBytes]
-  __shared__ __align__(8) uint64_t full[kQStages];
+  extern __shared__ __align__(128) unsigned char ring[];       // [kWarps][kQStages][kWarpStageBytes]
+  __shared__ __align__(8) uint64_t full[kWarps][kQStages];
   __shared__ float wsum[kWarps][32 * 4 * GG_MOMENTS];          // [warp][kq][i][moment], K*5 <= 640 floats used
 
   const int b = blockIdx.x / a.T;
@@ -66,28 +78,28 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_tma_kernel(const _
   const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
   const int row_end = min(n, row_begin + s.rows_per_tile);
   const int quads_per_row = n << kq_shift;
-  const int nb = (quads_per_row + kQBatch - 1) / kQBatch;      // batches per row
-  const int nbatches = (row_end - row_begin) * nb;
+  const int slices_per_row = quads_per_row / kWarpQuads;
+  const int nslices = (row_end - row_begin) * slices_per_row;           // of the whole tile
+  const int my_slices = nslices > warp ? (nslices - warp + kWarps - 1) / kWarps : 0;   // slices warp, warp+8, ...
 
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < kQStages; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < kQStages; ++i) mbar_init(&full[warp][i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   pdl_enter();   // global memory is first touched below
-  __syncthreads();
+  __syncwarp();
 
-  const float *gbase = s.maps + (size_t)b * n * n * K;
-  auto issue = [&](int i) {   // thread 0 only
-    const int row = row_begin + i / nb;
-    const int q0 = (i - (i / nb) * nb) * kQBatch;
-    const unsigned bytes = (unsigned)min(kQBatch, quads_per_row - q0) * 16u;
+  const float *gtile = s.maps + ((size_t)b * n + row_begin) * n * K;     // the tile's contiguous span
+  unsigned char *wring = ring + (size_t)warp * kQStages * kWarpStageBytes;
+  auto issue = [&](int i) {   // lane 0 only: i-th slice of this warp
     const int st = i % kQStages;
-    mbar_expect_tx(&full[st], bytes);
-    bulk_g2s(ring + (size_t)st * kStageBytes, gbase + ((size_t)row * n * K + (size_t)q0 * 4), bytes, &full[st]);
+    mbar_expect_tx(&full[warp][st], kWarpStageBytes);
+    bulk_g2s(wring + (size_t)st * kWarpStageBytes, gtile + (size_t)(warp + i * kWarps) * kWarpQuads * 4, kWarpStageBytes,
+             &full[warp][st]);
   };
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < min(kQStages, nbatches); ++i) issue(i);
+  if (lane == 0) {
+    for (int i = 0; i < min(kQStages, my_slices); ++i) issue(i);
   }
 
   float mux[4], muy[4], nA[4], nr[4], nE[4];
@@ -107,11 +119,28 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_tma_kernel(const _
 
   const bool use_gmask = WITH_GMASK && s.mask != nullptr;
   float dy[4], sh[4], e[4], S0[4], S1[4], S2[4];
-  for (int i = 0; i < nbatches; ++i) {
-    const int rb = i / nb, ib = i - rb * nb;
-    const int row = row_begin + rb;
-    const int q0 = ib * kQBatch;
-    if (ib == 0) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) dy[g] = sh[g] = e[g] = S0[g] = S1[g] = S2[g] = 0.f;
+  int cur_row = -1;
+  auto fold_row = [&]() {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      T[g][0] += S2[g];
+      T[g][3] += S1[g];
+      T[g][1] = fmaf(dy[g], S1[g], T[g][1]);
+      const float d0 = dy[g] * S0[g];
+      T[g][4] += d0;
+      T[g][2] = fmaf(dy[g], d0, T[g][2]);
+    }
+  };
+  for (int i = 0; i < my_slices; ++i) {
+    const int slice = warp + i * kWarps;
+    const int rrel = slice / slices_per_row;
+    const int row = row_begin + rrel;
+    const int q0 = (slice - rrel * slices_per_row) * kWarpQuads;      // first quad of the slice inside its row
+    if (row != cur_row) {
+      if (cur_row >= 0) fold_row();
+      cur_row = row;
       const float y = grid_coord(row, s.step);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -124,18 +153,19 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_tma_kernel(const _
     const float *mrow = use_gmask ? s.mask + ((size_t)b * n + row) * n : nullptr;
     float gmv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int qq = q0 + u * kThreads + (int)threadIdx.x;
-      gmv[u] = (use_gmask && qq < quads_per_row) ? __ldg(mrow + (qq >> kq_shift)) : 0.f;
-    }
+    for (int u = 0; u < 4; ++u) gmv[u] = use_gmask ? __ldg(mrow + ((q0 + u * 32 + lane) >> kq_shift)) : 0.f;
     const int st = i % kQStages;
-    mbar_wait(&full[st], (unsigned)((i / kQStages) & 1));
-    const float4 *sq = reinterpret_cast<const float4 *>(ring + (size_t)st * kStageBytes);
+    mbar_wait(&full[warp][st], (unsigned)((i / kQStages) & 1));
+    const float4 *sq = reinterpret_cast<const float4 *>(wring + (size_t)st * kWarpStageBytes);
+    float4 Gq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Gq[u] = sq[u * 32 + lane];
+    __syncwarp();                                    // every lane has its data in registers: the stage is free
+    if (lane == 0 && i + kQStages < my_slices) issue(i + kQStages);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int qq = q0 + u * kThreads + (int)threadIdx.x;
-      float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (qq < quads_per_row) G = sq[u * kThreads + threadIdx.x];
+      const int qq = q0 + u * 32 + lane;
+      const float4 G = Gq[u];
       const float x = grid_coord(qq >> kq_shift, s.step);
       const f32x2 x2 = pack2(x, x);
       const f32x2 gm2 = pack2(gmv[u], gmv[u]);
@@ -157,20 +187,8 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_tma_kernel(const _
       unpack2(s1a, S1[0], S1[1]); unpack2(s1b, S1[2], S1[3]);
       unpack2(s2a, S2[0], S2[1]); unpack2(s2b, S2[2], S2[3]);
     }
-    if (ib == nb - 1) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        T[g][0] += S2[g];
-        T[g][3] += S1[g];
-        T[g][1] = fmaf(dy[g], S1[g], T[g][1]);
-        const float d0 = dy[g] * S0[g];
-        T[g][4] += d0;
-        T[g][2] = fmaf(dy[g], d0, T[g][2]);
-      }
-    }
-    __syncthreads();                                   // every thread is done with stage `st`
-    if (threadIdx.x == 0 && i + kQStages < nbatches) issue(i + kQStages);
   }
+  if (cur_row >= 0) fold_row();
   // lanes that share kq (stride KQ) -> butterfly; then lanes 0..KQ-1 hold the warp totals
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -190,9 +208,16 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_tma_kernel(const _
   }
 }
 
+// shapes the bulk-copy kernel handles: every warp slice (128 quads) inside one row
+bool splat_bwd_quad_tma_ok(const SplatArgs &a, int kq_shift) {
+  for (int i = 0; i < a.nscales; ++i)
+    if (((a.sc[i].n << kq_shift) % kWarpQuads) != 0) return false;
+  return true;
+}
+
 cudaError_t launch_splat_bwd_quad_tma(const SplatArgs &a, int B, int kq_shift, bool any_mask, cudaStream_t st) {
   static bool configured_dev[64] = {};
-  const size_t smem = (size_t)kQStages * kStageBytes;
+  const size_t smem = (size_t)kWarps * kQStages * kWarpStageBytes;
   int dev = 0;
   cudaGetDevice(&dev);
   bool &configured = configured_dev[dev & 63];

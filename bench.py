@@ -193,7 +193,7 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- R consecutive steps (one per buffer set) captured into ONE graph: the programmatic-dependent-launch
+    # ---- R * ROUNDS consecutive steps (cycling through the buffer sets) captured into ONE graph: the programmatic-dependent-launch
     # edges between kernels then also span step boundaries; the remainder of the step count replays single steps
     def capture_chain(steps_fn):
         side = torch.cuda.Stream(dev)
@@ -207,18 +207,21 @@ def run_gpu(args):
             steps_fn()
         return g
 
+    ROUNDS = 4                      # passes over the R buffer sets per graph: R * ROUNDS steps per replay
+
     def all_sets_once():
-        for st_, gm_, _, _ in sets:
-            st_.forward()
-            st_.backward(gm_)
+        for _ in range(ROUNDS):
+            for st_, gm_, _, _ in sets:
+                st_.forward()
+                st_.backward(gm_)
 
     chain = capture_chain(all_sets_once)
 
     def run_steps(nsteps):
-        for _ in range(nsteps // R):
+        for _ in range(nsteps // (R * ROUNDS)):
             chain.replay()
-        for i in range(nsteps % R):
-            sets[i][0].graph.replay()
+        for i in range(nsteps % (R * ROUNDS)):
+            sets[i % R][0].graph.replay()
 
     # ---- timed region: W warm-up steps, then exactly K steps, device-timed, max over ranks
     run_steps(max(3, args.warmup))
@@ -320,16 +323,17 @@ def run_gpu(args):
             fs.capture_loss(raw)
             fsets.append((fs, raw))
         def all_fused_once():
-            for fs_, raw_ in fsets:
-                fs_.loss_backward(raw_)
+            for _ in range(ROUNDS):
+                for fs_, raw_ in fsets:
+                    fs_.loss_backward(raw_)
 
         fchain = capture_chain(all_fused_once)
 
         def run_fused(nsteps):
-            for _ in range(nsteps // R):
+            for _ in range(nsteps // (R * ROUNDS)):
                 fchain.replay()
-            for i in range(nsteps % R):
-                fsets[i][0].graph.replay()
+            for i in range(nsteps % (R * ROUNDS)):
+                fsets[i % R][0].graph.replay()
 
         run_fused(2 * R + 1)
         barrier()

@@ -298,7 +298,10 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     if (have_partials) {
       const float *base = partials + ((size_t)b * T * K + kb) * GG_MOMENTS;
       const size_t tile_stride = (size_t)K * GG_MOMENTS;
-      for (int c = threadIdx.x; c < kn * GG_MOMENTS; c += 128) {
+      // warps 1-3 take the columns, so that warp 0 (the Gaussians of a K <= 32 model) is already running the
+      // projection below when the sums land
+      for (int c = (int)threadIdx.x - 32; c < kn * GG_MOMENTS; c += 96) {
+        if (c < 0) break;
         double acc = 0.0;
         for (int t0 = 0; t0 < T; t0 += 8) {
           float v[8];
@@ -311,9 +314,9 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
       }
     }
     if (!have_cam) { make_cam(rxd, ryd, rzd, cam); have_cam = true; }
+    if (active) project_one(cam, t, f, p);
     __syncthreads();
     if (active) {
-    project_one(cam, t, f, p);
     if (have_partials) {
       double Tm[GG_MOMENTS];
 #pragma unroll

@@ -405,7 +405,7 @@ def run_gpu(args):
         # raw pinned-host -> device bandwidth for the target masks of one step, issued the way the e2e path issues them
         # (one copy per slot stream, four in flight): what bounds the e2e number
         hb = hsets[0].target
-        dbs = [torch.empty(hb.numel(), dtype=hb.dtype, device=dev) for _ in range(host.depth)]
+        dbs = [torch.empty(hb.shape, dtype=hb.dtype, device=dev) for _ in range(host.depth)]
         cur = torch.cuda.current_stream(dev)
 
         def copies(nrep):

@@ -382,11 +382,11 @@ def run_gpu(args):
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
     e2e = None
     try:
-        host = HostSilhouetteStep(B, K, n, dev, depth=4)
+        host = HostSilhouetteStep(B, K, n, dev, depth=6)
         hsets = [host.make_host_inputs(s[2], s[3]) for s in sets[:min(R, 4)]]
         # the first transfers out of freshly pinned buffers run at a fraction of the steady PCIe rate on this pool's
         # hosts (measured: 390 us per 4 MiB for the first ~100 copies, ~110 us after): warm the path up properly
-        for i in range(max(200, args.warmup)):
+        for i in range(max(1500, args.warmup)):
             host.submit(hsets[i % len(hsets)])
         host.drain()
         barrier()
@@ -403,7 +403,7 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         # raw pinned-host -> device bandwidth for the target masks of one step, issued the way the e2e path issues them
-        # (one copy per slot stream, four in flight): what bounds the e2e number
+        # (one copy per slot stream): what bounds the e2e number
         hb = hsets[0].target
         dbs = [torch.empty(hb.shape, dtype=hb.dtype, device=dev) for _ in range(host.depth)]
         cur = torch.cuda.current_stream(dev)

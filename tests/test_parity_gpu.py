@@ -653,3 +653,27 @@ def test_batches_beyond_one_grid_dimension(gg, cuda_device):
     t01 = ((tgt.float() / 127.5 - 1.0) + 1.0) * 0.5
     want = float((t01.to(cuda_device) - m.detach()).abs().double().mean())
     assert abs(step.loss() - want) <= 1e-6 * abs(want)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_buffer_step_many_gaussians_and_pageable_buffers(gg, cuda_device, pinned):
+    """K > 64 takes the five-launch path (splat, loss kernel, splat backward); pageable host buffers take the
+    copy path instead of the in-place (zero-copy) access of pinned ones.  Same numbers as the oracle either way."""
+    from gaussigan_b200.host import HostInputs, HostSilhouetteStep
+    B, K, n = 3, 80, 64
+    inp = rp.synth_inputs(B, K, seed=123)
+    tgt = rp.synth_target_masks(B, n, seed=8)
+    mask_ref, loss_ref, dmu_ref, dsig_ref, drot_ref = rp.render_loss_and_grads(inp, tgt, n)
+    host = HostSilhouetteStep(B, K, n, cuda_device, depth=2, want_mask=True)
+    assert host.LAUNCHES_PER_STEP == 5
+    h = host.make_host_inputs(inp, tgt)
+    if not pinned:
+        h = HostInputs(*(t.clone() for t in h))          # plain pageable copies
+        assert not h.mus.is_pinned()
+    res = host.submit(h).wait()
+    torch.cuda.synchronize()
+    assert abs(res.loss - float(loss_ref)) <= 2e-6 * abs(float(loss_ref))
+    assert_close_norm(res.mask, mask_ref, FWD_RTOL, "host K=80 mask")
+    assert_close_norm(res.dmus, dmu_ref.reshape(B, K, 3), GRAD_RTOL, "host K=80 dmus")
+    assert_close_norm(res.dsigma, dsig_ref, GRAD_RTOL, "host K=80 dsigma")
+    assert_close_norm(res.drot[:, 1], drot_ref.reshape(B), GRAD_RTOL, "host K=80 droty")

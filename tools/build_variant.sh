@@ -6,4 +6,4 @@ name=$1; shift
 mkdir -p variants
 cd "$(dirname "$0")/.."
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O3,-fvisibility=hidden --expt-relaxed-constexpr -shared "$@" \
-  -o variants/$name.so gaussigan_b200/csrc/*.cu -Xptxas -v 2>&1 | grep -E "error|quad_tma_kernelILb0" -A2 | grep -E "error|Used|spill"
+  -o variants/$name.so gaussigan_b200/csrc/*.cu -Xptxas -v 2>&1 | grep -E "error|bwd_mask_fast_kernelILi1ELb0ELi8" -A2 | grep -E "error|Used|spill"

@@ -11,10 +11,10 @@ from .renderer import (REFERENCE_SIZES, get_gaussian_maps_2d, get_landmarks, get
 
 from .consumers import (colorize_gaussians, colorize_landmark_maps, gm_cycle_loss, mask_recon_loss_bis,  # noqa: E402
                         turntable)
-from .geometry import deform, sigma_from_frame  # noqa: E402
+from .geometry import deform, sigma_from_frame, svd3  # noqa: E402
 from .interchange import decoder_feed, load_reference_gaussians, save_reference_gaussians  # noqa: E402
 
-__all__ = ["set_fast_mask", "set_pdl", "deform", "sigma_from_frame", "colorize_gaussians", "colorize_landmark_maps", "gm_cycle_loss", "mask_recon_loss_bis", "turntable",
+__all__ = ["set_fast_mask", "set_pdl", "svd3", "deform", "sigma_from_frame", "colorize_gaussians", "colorize_landmark_maps", "gm_cycle_loss", "mask_recon_loss_bis", "turntable",
            "decoder_feed", "load_reference_gaussians", "save_reference_gaussians",
            "REFERENCE_SIZES", "GaussiganError", "get_gaussian_maps_2d", "get_landmarks", "get_landmarks_infer",
            "get_landmarks_with_mask", "project", "render_silhouette"]

@@ -54,6 +54,8 @@ SIGNATURES = {
     "gg_silhouette_loss_fused": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_sigma_from_frame_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_sigma_from_frame_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "gg_svd3_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "gg_svd3_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_deform_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "gg_deform_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "gg_cycle_tiles": (_i, [_i]),

@@ -252,6 +252,25 @@ int gg_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, co
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_sigma_from_frame_bwd");
 }
 
+int gg_svd3_fwd(const double *A, int N, double *U, double *S, double *V, int device, void *stream) {
+  if (N < 0) return fail(GG_E_SHAPE, "N < 0");
+  if (N == 0) return GG_OK;
+  if (!A || !U || !S) return fail(GG_E_NULL, "gg_svd3_fwd: NULL pointer");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_svd3_fwd(A, N, U, S, V, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_svd3_fwd");
+}
+
+int gg_svd3_bwd(const double *U, const double *S, const double *V, const double *gU, const double *gS, int N, double *gA,
+                int device, void *stream) {
+  if (N < 0) return fail(GG_E_SHAPE, "N < 0");
+  if (N == 0) return GG_OK;
+  if (!U || !S || !V || !gA) return fail(GG_E_NULL, "gg_svd3_bwd: NULL pointer");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_svd3_bwd(U, S, V, gU, gS, N, gA, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_svd3_bwd");
+}
+
 int gg_deform_fwd(const float *mu_t, const float *scale, const float *ang, const float *cmu, const double *U,
                   const double *S, const float *theta_raw, int B, int K, float *mus, double *sigmas, float *theta,
                   int device, void *stream) {

@@ -279,6 +279,108 @@ __global__ void __launch_bounds__(128) deform_bwd_kernel(const float *__restrict
 }
 
 // -------------------------------------------------------------------------------------- launchers
+// ---------------------------------------------------------------------------------------------- 3x3 SVD
+// `S, U, _ = tf.linalg.svd(cannsigma)` (mask/mask_gen_dynamic.py:430).  One-sided (Hestenes) Jacobi in float64:
+// right rotations orthogonalise the columns, A V = U diag(S); singular values descending as LAPACK / TF return them;
+// column signs are arbitrary (they cancel in (R U) D (R U)^T).  General 3x3 input -- the reference's canonical
+// covariances are symmetric only up to 4e-8 (they are built in float32), and the factorisation of exactly that matrix
+// is what the oracle differentiates.  One thread per matrix; a kernel instead of cuSOLVER because torch.linalg.svd
+// synchronises with the host (its status check), which stalls the stream and keeps the dynamic-object step out of
+// CUDA graphs.
+__global__ void __launch_bounds__(128) svd3_fwd_kernel(const double *__restrict__ A, int N, double *__restrict__ U,
+                                                      double *__restrict__ S, double *__restrict__ Vout) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double Bm[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+  for (int j = 0; j < 9; ++j) Bm[j] = A[(size_t)i * 9 + j];
+  for (int sweep = 0; sweep < 16; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        al += Bm[r * 3 + p] * Bm[r * 3 + p];
+        be += Bm[r * 3 + q] * Bm[r * 3 + q];
+        ga += Bm[r * 3 + p] * Bm[r * 3 + q];
+      }
+      if (ga * ga <= 1e-34 * al * be) continue;            // columns orthogonal to ~1e-17
+      rotated = true;
+      const double zeta = (be - al) / (2.0 * ga);
+      const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double bp = Bm[r * 3 + p], bq = Bm[r * 3 + q];
+        Bm[r * 3 + p] = c * bp - sn * bq;
+        Bm[r * 3 + q] = sn * bp + c * bq;
+        const double vp = V[r * 3 + p], vq = V[r * 3 + q];
+        V[r * 3 + p] = c * vp - sn * vq;
+        V[r * 3 + q] = sn * vp + c * vq;
+      }
+    }
+    if (!rotated) break;
+  }
+  double sv[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sv[c] = sqrt(Bm[c] * Bm[c] + Bm[3 + c] * Bm[3 + c] + Bm[6 + c] * Bm[6 + c]);
+  int ord[3] = {0, 1, 2};
+  if (sv[ord[0]] < sv[ord[1]]) { int t = ord[0]; ord[0] = ord[1]; ord[1] = t; }
+  if (sv[ord[1]] < sv[ord[2]]) { int t = ord[1]; ord[1] = ord[2]; ord[2] = t; }
+  if (sv[ord[0]] < sv[ord[1]]) { int t = ord[0]; ord[0] = ord[1]; ord[1] = t; }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double sc = sv[ord[c]];
+    const double inv = sc > 0.0 ? 1.0 / sc : 0.0;
+    S[(size_t)i * 3 + c] = sc;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      U[(size_t)i * 9 + r * 3 + c] = Bm[r * 3 + ord[c]] * inv;
+      if (Vout) Vout[(size_t)i * 9 + r * 3 + c] = V[r * 3 + ord[c]];
+    }
+  }
+}
+
+// Backward for square, full-rank A with no gradient through V (the reference discards it: `S, U, _ = svd`):
+//   gA = U [ (skew(U^T gU) / E) diag(S) + diag(gS) ] V^T,   skew(X) = X - X^T,   E_ij = s_j^2 - s_i^2
+// gU, gS may each be NULL.  Terms with equal singular values are dropped.
+__global__ void __launch_bounds__(128) svd3_bwd_kernel(const double *__restrict__ U, const double *__restrict__ S,
+                                                      const double *__restrict__ V, const double *__restrict__ gU,
+                                                      const double *__restrict__ gS, int N, double *__restrict__ gA) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double Um[9], Vm[9], G[9], P[9], s[3];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    Um[j] = U[(size_t)i * 9 + j];
+    Vm[j] = V[(size_t)i * 9 + j];
+    G[j] = gU ? gU[(size_t)i * 9 + j] : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) s[j] = S[(size_t)i * 3 + j];
+  mm64(Um, G, P, true, false);                       // U^T gU
+  double gP[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (r == c) gP[r * 3 + c] = gS ? gS[(size_t)i * 3 + r] : 0.0;
+      else {
+        const double e = s[c] * s[c] - s[r] * s[r];
+        gP[r * 3 + c] = e != 0.0 ? (P[r * 3 + c] - P[c * 3 + r]) / e * s[c] : 0.0;
+      }
+    }
+  double T1[9], Gm[9];
+  mm64(Um, gP, T1, false, false);
+  mm64(T1, Vm, Gm, false, true);                     // U gP V^T
+#pragma unroll
+  for (int j = 0; j < 9; ++j) gA[(size_t)i * 9 + j] = Gm[j];
+}
+
 cudaError_t launch_sigma_from_frame_fwd(const float *v0, const float *v1, const float *u, int N, double *sigma,
                                         cudaStream_t st) {
   launch_pdl(sigma_from_frame_fwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, v0, v1, u, N, sigma);
@@ -300,6 +402,16 @@ cudaError_t launch_deform_bwd(const float *sc, const float *ang, const double *U
                               float *dsc, float *dang, float *dcmu, double *dU, double *dS, cudaStream_t st) {
   launch_pdl(deform_bwd_kernel, dim3((B * K + 127) / 128), dim3(128), 0, st, sc, ang, U, S, gmus, gsig, gtheta, B, K, dtheta_raw, dmu_t, dsc,
                                                          dang, dcmu, dU, dS);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_svd3_fwd(const double *A, int N, double *U, double *S, double *V, cudaStream_t st) {
+  launch_pdl(svd3_fwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, A, N, U, S, V);
+  return cudaGetLastError();
+}
+cudaError_t launch_svd3_bwd(const double *U, const double *S, const double *V, const double *gU, const double *gS, int N,
+                            double *gA, cudaStream_t st) {
+  launch_pdl(svd3_bwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, U, S, V, gU, gS, N, gA);
   return cudaGetLastError();
 }
 

@@ -50,6 +50,9 @@ cudaError_t launch_sigma_from_frame_fwd(const float *v0, const float *v1, const 
                                         cudaStream_t st);
 cudaError_t launch_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, const double *gsigma, int N,
                                         float *dv0, float *dv1, float *du, cudaStream_t st);
+cudaError_t launch_svd3_fwd(const double *A, int N, double *U, double *S, double *V, cudaStream_t st);
+cudaError_t launch_svd3_bwd(const double *U, const double *S, const double *V, const double *gU, const double *gS, int N,
+                            double *gA, cudaStream_t st);
 cudaError_t launch_deform_fwd(const float *mu_t, const float *sc, const float *ang, const float *cmu, const double *U,
                               const double *S, const float *theta_raw, int B, int K, float *mus, double *sigmas,
                               float *theta, cudaStream_t st);

@@ -2,8 +2,8 @@
 
 * ``sigma_from_frame(v0, v1, u)``  -- tail of ``get_musigma`` (mask/mask_gen_dynamic.py:383-401)
 * ``deform(mu_t, scale, rx, ry, rz, theta, cannmu, cannsigma)`` -- tail of the dynamic ``transform_mu_sigma``
-  (mask/mask_gen_dynamic.py:426-458); the SVD of the canonical covariances (:430) is ``torch.linalg.svd`` (it keeps
-  its own gradient), everything after it is one CUDA launch per direction.
+  (mask/mask_gen_dynamic.py:426-458); the SVD of the canonical covariances (:430) is a Jacobi kernel
+  (``svd3``; ``svd="torch"`` selects ``torch.linalg.svd``), everything after it is one CUDA launch per direction.
 
 Both take the OUTPUTS of the dense heads (the MLPs are out of scope) and are differentiable.
 """
@@ -47,6 +47,44 @@ def sigma_from_frame(v0_raw: torch.Tensor, v1_raw: torch.Tensor, u_raw: torch.Te
     return _SigmaFromFrame.apply(f(v0_raw), f(v1_raw), f(u_raw))
 
 
+class _SVD3(torch.autograd.Function):
+    """``S, U, _ = tf.linalg.svd(A)`` for 3x3 matrices (mask/mask_gen_dynamic.py:430) as a CUDA kernel: no host
+    synchronisation (``torch.linalg.svd`` checks cuSOLVER's status on the host), so it can live in a CUDA graph.
+    Returns ``(U, S)``; like the reference, V carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, A):
+        N = A.numel() // 9
+        U, V = torch.empty_like(A), torch.empty_like(A)
+        S = torch.empty(A.shape[:-2] + (3,), dtype=torch.float64, device=A.device)
+        check(lib.gg_svd3_fwd(A.data_ptr(), N, U.data_ptr(), S.data_ptr(), V.data_ptr(), A.device.index,
+                              _stream(A.device)), "gg_svd3_fwd")
+        ctx.save_for_backward(U, S, V)
+        ctx.set_materialize_grads(False)
+        return U, S
+
+    @staticmethod
+    def backward(ctx, gU, gS):
+        U, S, V = ctx.saved_tensors
+        N = U.numel() // 9
+        gU = None if gU is None else gU.to(torch.float64).contiguous()
+        gS = None if gS is None else gS.to(torch.float64).contiguous()
+        gA = torch.empty_like(U)
+        check(lib.gg_svd3_bwd(U.data_ptr(), S.data_ptr(), V.data_ptr(), _ptr(gU), _ptr(gS), N, gA.data_ptr(),
+                              U.device.index, _stream(U.device)), "gg_svd3_bwd")
+        return gA
+
+
+def svd3(A: torch.Tensor):
+    """``A [...,3,3]`` float64, CUDA -> ``(U [...,3,3], S [...,3])``, the left singular vectors and the singular values
+    (descending) of each matrix; differentiable (square full-rank formula, no gradient through V); never
+    synchronises with the host."""
+    _require_cuda(A)
+    if A.shape[-2:] != (3, 3):
+        raise ValueError("svd3 expects [...,3,3]")
+    return _SVD3.apply(A.to(torch.float64).contiguous())
+
+
 class _Deform(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mu_t, scale, ang, theta_raw, cmu, U, S):
@@ -81,14 +119,21 @@ class _Deform(torch.autograd.Function):
         return dmu_t, dsc, dang, dth, dcmu.sum(0), dU.sum(0), dS.sum(0)
 
 
-def deform(mu_t_raw, scale_raw, rx_raw, ry_raw, rz_raw, theta_raw, cannmu, cannsigma):
+def deform(mu_t_raw, scale_raw, rx_raw, ry_raw, rz_raw, theta_raw, cannmu, cannsigma, svd: str = "cuda"):
     """mask/mask_gen_dynamic.py:426-458.  Head outputs AFTER tanh: ``mu_t_raw [B,K*3]``, ``scale_raw [B,K*3]``,
     ``r*_raw [B,K]``, ``theta_raw [B,1]``; canonical ``cannmu [1,K,1,3]`` f32, ``cannsigma [1,K,3,3]`` f64.
-    Returns ``mus [B,K,1,3]`` f32, ``sigmas [B,K,3,3]`` f64, ``theta [B,1]`` f32 degrees -- ready for ``get_landmarks``."""
+    Returns ``mus [B,K,1,3]`` f32, ``sigmas [B,K,3,3]`` f64, ``theta [B,1]`` f32 degrees -- ready for ``get_landmarks``.
+    ``svd`` selects who factorises the canonical covariances (:430): the library's Jacobi kernel (default) or
+    ``torch.linalg.svd``; both give the same Sigma_b (column signs of U cancel)."""
     _require_cuda(mu_t_raw, scale_raw, rx_raw, ry_raw, rz_raw, theta_raw, cannmu, cannsigma)
     K = cannsigma.shape[-3]
     B = mu_t_raw.shape[0]
-    U, S, _ = torch.linalg.svd(cannsigma.to(torch.float64).reshape(K, 3, 3), full_matrices=True)      # :430
+    if svd == "cuda":        # :430, Jacobi kernel (graph-capturable)
+        U, S = svd3(cannsigma.to(torch.float64).reshape(K, 3, 3))
+    elif svd == "torch":     # :430, cuSOLVER through torch (synchronises with the host)
+        U, S, _ = torch.linalg.svd(cannsigma.to(torch.float64).reshape(K, 3, 3), full_matrices=True)
+    else:
+        raise ValueError("svd must be 'cuda' or 'torch'")
     ang = torch.stack([rx_raw.reshape(B, K), ry_raw.reshape(B, K), rz_raw.reshape(B, K)], dim=-1)
     f = lambda t: t.float().contiguous()
     mus, sig, theta = _Deform.apply(f(mu_t_raw.reshape(B, K, 3)), f(scale_raw.reshape(B, K, 3)), f(ang),

@@ -178,6 +178,14 @@ GG_API int gg_sigma_from_frame_fwd(const float *v0, const float *v1, const float
                                    int device, void *stream);
 GG_API int gg_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, const double *gsigma, int N,
                                    float *dv0, float *dv1, float *du, int device, void *stream);
+/* gg_svd3_*: `S, U, _ = tf.linalg.svd(cannsigma)` (mask/mask_gen_dynamic.py:430) for 3x3 matrices A [N,3,3] f64 ->
+ * U [N,3,3], S [N,3] (descending), V [N,3,3] (may be NULL) with A = U diag(S) V^T; column signs arbitrary, as in
+ * LAPACK.  One-sided Jacobi in float64; no host synchronisation (unlike cuSOLVER-backed torch.linalg.svd), so the
+ * dynamic-object step can be captured in a CUDA graph.  Backward (square full-rank, no gradient through V, as the
+ * reference discards it): gU, gS (either may be NULL) -> gA [N,3,3]; terms with equal singular values are dropped. */
+GG_API int gg_svd3_fwd(const double *A, int N, double *U, double *S, double *V, int device, void *stream);
+GG_API int gg_svd3_bwd(const double *U, const double *S, const double *V, const double *gU, const double *gS, int N,
+                       double *gA, int device, void *stream);
 /* gg_deform_*: tail of transform_mu_sigma (mask/mask_gen_dynamic.py:426-458).  Head outputs AFTER tanh, f32:
  * mu_t [B,K,3], scale [B,K,3], ang [B,K,3] (x,y,z), theta_raw [B]; canonical cmu [K,3] f32 and the SVD factors
  * U [K,3,3], S [K,3] (float64) of the canonical covariances (the SVD itself, :430, stays with the caller).

@@ -677,3 +677,53 @@ def test_host_buffer_step_many_gaussians_and_pageable_buffers(gg, cuda_device, p
     assert_close_norm(res.dmus, dmu_ref.reshape(B, K, 3), GRAD_RTOL, "host K=80 dmus")
     assert_close_norm(res.dsigma, dsig_ref, GRAD_RTOL, "host K=80 dsigma")
     assert_close_norm(res.drot[:, 1], drot_ref.reshape(B), GRAD_RTOL, "host K=80 droty")
+
+
+def test_svd3_kernel_vs_torch_svd(gg, cuda_device):
+    """The one-sided Jacobi 3x3 SVD kernel (mask/mask_gen_dynamic.py:430 without a host sync): singular values,
+    reconstruction and orthogonality to float64 round-off on the reference's slightly asymmetric covariances and on
+    general matrices; gradients of a sign-invariant function of (U, S) equal those through torch.linalg.svd; and
+    deform() gives the same Sigma_b and gradients with either factorisation."""
+    g = torch.Generator().manual_seed(3)
+    K = 16
+    th = lambda *s: torch.tanh(torch.randn(*s, generator=g))
+    sig_c = rp.sigma_from_frame(th(1, K, 3), th(1, K, 3), torch.randn(1, K, 3, generator=g)).reshape(K, 3, 3)
+    general = torch.randn(8, 3, 3, generator=g, dtype=torch.float64)
+    for mats in (sig_c, general):
+        A = mats.to(cuda_device)
+        U, S = gg.svd3(A)
+        Ut, St, Vh = torch.linalg.svd(mats)
+        assert (S.cpu() - St).abs().max() < 1e-13 and bool((S[:, :-1] >= S[:, 1:]).all())
+        assert (U.transpose(-1, -2) @ U - torch.eye(3, dtype=torch.float64, device=cuda_device)).abs().max() < 1e-13
+        # same left singular vectors up to sign
+        dots = (U.cpu() * Ut).sum(-2).abs()
+        assert (dots - 1).abs().max() < 1e-10
+    # gradient of a sign-invariant scalar: sum W * (U diag(sqrt(S)) M diag(sqrt(S)) U^T)
+    W = torch.randn(K, 3, 3, generator=g, dtype=torch.float64)
+    M = torch.diag(torch.tensor([1.3, 0.7, 2.1], dtype=torch.float64))
+
+    def f(U_, S_, W_, M_):
+        D = torch.diag_embed(S_.sqrt())
+        return (W_ * (U_ @ D @ M_ @ D @ U_.transpose(-1, -2))).sum()
+
+    a1 = sig_c.to(cuda_device).clone().requires_grad_(True)
+    f(*gg.svd3(a1), W.to(cuda_device), M.to(cuda_device)).backward()
+    a2 = sig_c.clone().requires_grad_(True)
+    U2, S2, _ = torch.linalg.svd(a2)
+    f(U2, S2, W, M).backward()
+    assert_close_norm(a1.grad, a2.grad, 1e-9, "svd3 gradient")
+    # deform() with either factorisation
+    B = 5
+    heads = [th(B, K * 3), th(B, K * 3), th(B, K), th(B, K), th(B, K), th(B, 1)]
+    cmu = th(1, K, 1, 3)
+    outs = {}
+    for mode in ("cuda", "torch"):
+        cs = sig_c.reshape(1, K, 3, 3).to(cuda_device).clone().requires_grad_(True)
+        hs = [h.to(cuda_device).clone().requires_grad_(True) for h in heads]
+        mus, sg, theta = gg.deform(*hs, cmu.to(cuda_device), cs, svd=mode)
+        (sg * torch.randn(sg.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64).to(cuda_device)).sum().backward()
+        outs[mode] = (sg.detach(), cs.grad, [h.grad for h in hs[:5]])
+    assert_close_norm(outs["cuda"][0], outs["torch"][0], 1e-11, "Sigma_b cuda vs torch svd")
+    assert_close_norm(outs["cuda"][1], outs["torch"][1], 1e-8, "d cannsigma")
+    for a, b in zip(outs["cuda"][2], outs["torch"][2]):
+        assert_close_norm(a, b, 1e-6, "head gradients")

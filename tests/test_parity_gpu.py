@@ -727,3 +727,45 @@ def test_svd3_kernel_vs_torch_svd(gg, cuda_device):
     assert_close_norm(outs["cuda"][1], outs["torch"][1], 1e-8, "d cannsigma")
     for a, b in zip(outs["cuda"][2], outs["torch"][2]):
         assert_close_norm(a, b, 1e-6, "head gradients")
+
+
+def test_config3_step_is_graph_capturable(gg, cuda_device):
+    """The whole dynamic-object step (frame -> Sigma_c, SVD, deformation, render, fused loss, backward) never touches
+    the host, so it can be captured in one CUDA graph; replays give the eager gradients bit for bit."""
+    B, K, n = 4, 16, 64
+    g = torch.Generator().manual_seed(12)
+    th = lambda *s: torch.tanh(torch.randn(*s, generator=g))
+    leaves = [t.to(cuda_device).requires_grad_(True) for t in
+              (th(1, K, 3), th(1, K, 3), torch.randn(1, K, 3, generator=g), th(1, K, 1, 3),
+               th(B, K * 3), th(B, K * 3), th(B, K), th(B, K), th(B, K), th(B, 1))]
+    tgt = rp.synth_target_masks(B, n, seed=9).to(cuda_device)
+
+    def step():
+        for t in leaves:
+            t.grad.zero_()
+        csig = gg.sigma_from_frame(*leaves[:3])
+        mus, sig, theta = gg.deform(*leaves[4:], leaves[3], csig)
+        z = torch.zeros_like(theta)
+        loss = gg.mask_recon_loss_bis(tgt, mus, sig, z, theta, z, 0, 0, -2., size=n)
+        loss.backward()
+        return loss
+
+    for t in leaves:
+        t.grad = torch.zeros_like(t)
+    side = torch.cuda.Stream(cuda_device)
+    side.wait_stream(torch.cuda.current_stream(cuda_device))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eager_loss = step().detach().clone()
+    torch.cuda.current_stream(cuda_device).wait_stream(side)
+    torch.cuda.synchronize()
+    eager = [t.grad.clone() for t in leaves]
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss = step()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(loss.detach(), eager_loss)
+    for a, b in zip(leaves, eager):
+        assert torch.equal(a.grad, b)

@@ -18,9 +18,12 @@
 //
 // Guard.  The recurrence is only used where the per-pixel change of the exponent is small,
 // |nA h (2 t + h)| <= 13 over the whole tile: then nothing can overflow and a strip whose first pixel
-// underflows (g_0 < 2^-126) stays below 2^-35 everywhere.  The test is made once per (CTA, Gaussian) from the
-// tile's corners (t is linear in the pixel position); Gaussians that fail it (sub-pixel-thin or very distant)
-// are evaluated directly, one exponential per pixel, by the whole CTA.
+// underflows (g_0 < 2^-126) stays below 2^-35 everywhere; and <= 3 wherever the Gaussian is visible (the rounding
+// error of the ratio grows with its exponent; the reference's range stays below 0.8); and only for |nA| <= 512,
+// because the recurrence steps by exactly h while the reference's float32 pixel grid deviates from uniform by up to
+// 1.8e-7, an error that grows like sqrt(|nA|) (the reference's range ends near 210).  The test is made once per
+// (CTA, Gaussian) from the tile's corners (t is linear in the pixel position); Gaussians that fail it (narrower than
+// ~2 pixels, or very distant) are evaluated directly, one exponential per pixel on the true grid, by the whole CTA.
 //
 // Backward.  The upstream gradient of a pixel is shared by all K Gaussians, so each thread forms
 // (Gbar, Gbar xi, Gbar xi^2) once per pixel (xi = j h, strip-local) and the per-(pixel, Gaussian) work is three
@@ -46,7 +49,9 @@ namespace {
 #define GG_FWD_KUNROLL 0      // 0 = leave it to the compiler
 #endif
 constexpr int kBwdKUnroll = GG_BWD_KUNROLL;
-constexpr float kMaxSlope = 13.0f;     // largest |d(exponent)/d(pixel)| the recurrence is trusted with
+constexpr float kMaxSlope = 13.0f;     // largest |d(exponent)/d(pixel)| the recurrence is trusted with (range safety)
+constexpr float kMaxVisibleSlope = 3.0f;   // ... and where the Gaussian is visible (accuracy)
+constexpr float kMaxSharpness = 512.0f;    // largest |nA| = a log2(e): bounds the error of stepping by exactly h
 
 // Per-Gaussian constants of one CTA (its scale fixes h): 3 x float4 in shared memory
 //   c0 = mu_x, mu_y, nA, -nr      c1 = nE, 2 nA h, nA h^2, c      c2 = steep flag (0/1), 0, 0, 0
@@ -84,7 +89,13 @@ __device__ __forceinline__ void stage_fast_consts(const float *__restrict__ gpar
     }
     // exponent slope over a strip: |b_j| <= |2 nA h| (|t| + 8 h)
     const float slope = fabsf(2.0f * nAh) * (tmax + 8.0f * h);
-    const bool steep = !(slope <= kMaxSlope);          // NaN -> steep
+    // accuracy: where the Gaussian is not negligible (exponent > -14) the slope is at most 2 h sqrt(14 |nA|); the
+    // rounding of the ratio's exponent grows with it ...
+    const float slope_vis = 2.0f * h * sqrtf(14.0f * fabsf(lo.z));
+    // ... and the recurrence steps by exactly h while the reference's float32 grid deviates from uniform by up to
+    // 1.8e-7: the resulting error peaks at 0.6 sqrt(|nA|) * 1.8e-7, i.e. 3e-6 at |nA| = 512 (the reference's range
+    // ends near 210)
+    const bool steep = !(slope <= kMaxSlope) || !(slope_vis <= kMaxVisibleSlope) || !(fabsf(lo.z) <= kMaxSharpness);
     sc[3 * k + 0] = make_float4(lo.x, lo.y, lo.z, -lo.w);
     sc[3 * k + 1] = make_float4(nE, 2.0f * nAh, nAhh, c);
     sc[3 * k + 2] = make_float4(steep ? 1.f : 0.f, 0.f, 0.f, 0.f);
@@ -100,15 +111,17 @@ __device__ __forceinline__ f32x2 ex2_2(f32x2 v) {
 
 // One Gaussian on one strip of a ROW PAIR: lanes of every f32x2 are the two rows, G[j] is pixel j of the strip.
 //   dy = y - mu_y;  t0 = (x_0 - mu_x) - nr dy;  e = nE dy^2   (per lane)
-__device__ __forceinline__ void eval_strip(const float4 &c0, const float4 &c1, bool steep, f32x2 t0, f32x2 e, float h,
-                                           f32x2 (&G)[8]) {
+__device__ __forceinline__ void eval_strip(const float4 &c0, const float4 &c1, bool steep, f32x2 t0, f32x2 e, f32x2 dy,
+                                           int col0, float h, f32x2 (&G)[8]) {
   const f32x2 nA = bc(c0.z);
   if (steep) {
-    // sub-pixel-thin or very distant Gaussian: one exponential per pixel, as gg_splat.cu does
+    // narrow or very distant Gaussian: one exponential per pixel on the reference's own float32 grid coordinates
+    // (not x_0 + j h: at this sharpness the 1e-7 non-uniformity of the grid matters), exactly as gg_splat.cu does
+    const f32x2 sh = fma2(bc(-c0.w), dy, bc(c0.x));          // mu_x + nr dy
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const f32x2 t = add2(t0, bc((float)j * h));
-      G[j] = ex2_2(fma2(mul2(nA, t), t, e));
+      const f32x2 t = sub2(bc(grid_coord(col0 + j, h)), sh);
+      G[j] = ex2_2(fma2(nA, mul2(t, t), e));
     }
     return;
   }
@@ -203,7 +216,7 @@ __global__ void __launch_bounds__(NW * 32) splat_fwd_mask_fast_kernel(const __gr
       const f32x2 t0 = fma2(bc(c0.w), dy, bc(xm));
       const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
       f32x2 G[8];
-      eval_strip(c0, c1, steep, t0, e, h, G);
+      eval_strip(c0, c1, steep, t0, e, dy, pos.colA, h, G);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[p][j] = add2(acc[p][j], G[j]);
     }
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
         const f32x2 t0 = fma2(bc(c0.w), dy, bc(xm));
         const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
         f32x2 G[8];
-        eval_strip(c0, c1, steep, t0, e, h, G);
+        eval_strip(c0, c1, steep, t0, e, dy, pos.colA, h, G);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[p][j] = add2(acc[p][j], G[j]);
       }
@@ -373,7 +386,10 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
   f32x2 W0[NP][8];
   float xi1[8], xi2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { xi1[j] = pin((float)j * h); xi2[j] = pin(xi1[j] * xi1[j]); }
+  for (int j = 0; j < 8; ++j) {   // offsets of the strip's pixels on the reference's float32 grid (j h to ~1e-7)
+    xi1[j] = pin(grid_coord(pos.colA + j, h) - x0);
+    xi2[j] = pin(xi1[j] * xi1[j]);
+  }
 #pragma unroll
   for (int p = 0; p < NP; ++p)
 #pragma unroll
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
       const f32x2 t0 = fma2(bc(c0.w), dy, bc(xm));
       const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
       f32x2 G[8];
-      eval_strip(c0, c1, steep, t0, e, h, G);
+      eval_strip(c0, c1, steep, t0, e, dy, pos.colA, h, G);
 #if GG_BWD_WFORM == 0
       f32x2 S0 = mul2(G[0], W0[p][0]), S1 = mul2(G[0], W1[p][0]), S2 = mul2(G[0], W2[p][0]);
 #pragma unroll

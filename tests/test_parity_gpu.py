@@ -769,3 +769,45 @@ def test_config3_step_is_graph_capturable(gg, cuda_device):
     assert torch.equal(loss.detach(), eager_loss)
     for a, b in zip(leaves, eager):
         assert torch.equal(a.grad, b)
+
+
+def test_randomised_shapes_and_scales_fast_mask_path(gg, cuda_device, restore_modes):
+    """Seeded sweep over image sizes, Gaussian sizes from about a pixel to larger than the frame (axis variances
+    3e-4 .. 0.6; the reference's own range is 0.01 .. 0.51, far sub-pixel Gaussians are beyond what a float32 raster
+    can resolve to 1e-5 in either arithmetic), off-screen centres, all three Euler angles, non-default translation
+    and focal: the forward-differenced kernels (with their steepness guard) stay inside the path's tolerances."""
+    rng = torch.Generator().manual_seed(2024)
+    worst_f, worst_g = 0.0, 0.0
+    for case in range(36):
+        B, K = 2, int(torch.randint(1, 9, (1,), generator=rng))
+        n = int(torch.randint(9, 200, (1,), generator=rng))
+        mus = ((torch.rand(B, K, 1, 3, generator=rng) - 0.5) * torch.tensor([3.0, 3.0, 1.0])).float()
+        # covariances: random rotation, axis variances log-uniform in [3e-4, 0.6]
+        q, _ = torch.linalg.qr(torch.randn(B, K, 3, 3, generator=rng, dtype=torch.float64))
+        lo, hi = torch.log(torch.tensor(3e-4, dtype=torch.float64)), torch.log(torch.tensor(0.6, dtype=torch.float64))
+        var = torch.exp(torch.rand(B, K, 3, generator=rng, dtype=torch.float64) * (hi - lo) + lo)
+        sig = (q * var[..., None, :]) @ q.transpose(-1, -2)
+        rot = [(torch.rand(B, 1, generator=rng) - 0.5) * a for a in (40.0, 360.0, 40.0)]
+        t = (float(torch.rand(1, generator=rng) - 0.5) * 0.4, float(torch.rand(1, generator=rng) - 0.5) * 0.4,
+             -2.0 - float(torch.rand(1, generator=rng)))
+        focal = 0.8 + float(torch.rand(1, generator=rng)) * 0.6
+        lv = [x.clone().requires_grad_(True) for x in (mus, sig, rot[1])]
+        ref = rp.get_landmarks(lv[0], lv[1], rot[0], lv[2], rot[2], *t, focal, sizes=(n,))[0].sum(-1)
+        if not torch.isfinite(ref).all() or float(ref.detach().abs().max()) < 1e-6:
+            continue                                         # degenerate geometry / empty frame: nothing to compare
+        gm = torch.randn(B, n, n, generator=rng)
+        (ref * gm).sum().backward()
+        dv = [x.to(cuda_device).requires_grad_(True) for x in (mus, sig, rot[1])]
+        m = gg.render_silhouette(dv[0], dv[1], rot[0].to(cuda_device), dv[2], rot[2].to(cuda_device), *t, focal, size=n)
+        m.backward(gm.to(cuda_device))
+        assert torch.isfinite(m).all(), f"case {case}"
+        ef = max_rel(m, ref)
+        worst_f = max(worst_f, ef)
+        assert ef <= FWD_RTOL, f"case {case} (n={n}, K={K}): forward {ef:.2e}"
+        for a, b, nm in zip(dv, lv, ("mus", "sigma", "roty")):
+            if float(b.grad.abs().max()) < 1e-12:
+                continue
+            eg = max_rel(a.grad, b.grad)
+            worst_g = max(worst_g, eg)
+            assert eg <= GRAD_RTOL, f"case {case} (n={n}, K={K}): grad {nm} {eg:.2e}"
+    print(f"worst forward {worst_f:.2e}, worst gradient {worst_g:.2e}")

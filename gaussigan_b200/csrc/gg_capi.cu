@@ -42,11 +42,11 @@ int cuda_fail(cudaError_t e, const char *where) {
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int set_device(int device) {
-  thread_local int current = -1;
-  if (device != current) {
+  // the caller (PyTorch, another library) may change the current device between calls: ask, do not remember
+  int current = -1;
+  if (cudaGetDevice(&current) != cudaSuccess || current != device) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    current = device;
   }
   return GG_OK;
 }

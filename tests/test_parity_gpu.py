@@ -811,3 +811,26 @@ def test_randomised_shapes_and_scales_fast_mask_path(gg, cuda_device, restore_mo
             worst_g = max(worst_g, eg)
             assert eg <= GRAD_RTOL, f"case {case} (n={n}, K={K}): grad {nm} {eg:.2e}"
     print(f"worst forward {worst_f:.2e}, worst gradient {worst_g:.2e}")
+
+
+def test_second_device_in_the_same_process(gg, cuda_device):
+    """Tensors on cuda:1 while cuda:0 is PyTorch's current device (and the other way round): the library follows the
+    tensors' device on every call.  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    B, K, n = 3, 8, 64
+    inp = rp.synth_inputs(B, K, seed=3)
+    outs = []
+    for dev_index, current in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        torch.cuda.set_device(current)
+        d = {k: v.to(f"cuda:{dev_index}") for k, v in inp.items()}
+        lv = {k: d[k].clone().requires_grad_(True) for k in ("mus", "sigma", "roty")}
+        m = gg.render_silhouette(lv["mus"], lv["sigma"], d["rotx"], lv["roty"], d["rotz"], 0, 0, -2., size=n)
+        m.sum().backward()
+        torch.cuda.synchronize(dev_index)
+        assert m.device.index == dev_index
+        outs.append((m.cpu(), lv["mus"].grad.cpu(), lv["sigma"].grad.cpu()))
+    torch.cuda.set_device(0)
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert torch.equal(a, b)

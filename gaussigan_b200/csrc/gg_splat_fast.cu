@@ -25,9 +25,9 @@
 // (CTA, Gaussian) from the tile's corners (t is linear in the pixel position); Gaussians that fail it (narrower than
 // ~2 pixels, or very distant) are evaluated directly, one exponential per pixel on the true grid, by the whole CTA.
 //
-// Backward.  The upstream gradient of a pixel is shared by all K Gaussians, so each thread forms
-// (Gbar, Gbar xi, Gbar xi^2) once per pixel (xi = j h, strip-local) and the per-(pixel, Gaussian) work is three
-// packed FMAs; the strip sums are re-centred to the sheared coordinate t per row.
+// Backward.  Strip sums are taken about the strip's first pixel, u = g Gbar; S0 += u; S1 += u xi; S2 += u xi^2 with
+// xi_j = x_j - x_0 on the reference's grid (four packed instructions per pixel pair, only Gbar in registers), and
+// re-centred to the sheared coordinate t = t0 + xi per row.
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
 #include "gg_launch.h"
@@ -41,9 +41,6 @@ namespace {
 #endif
 #ifndef GG_BWD_MINBLOCKS
 #define GG_BWD_MINBLOCKS 4    // resident 256-thread CTAs per SM the backward is compiled for
-#endif
-#ifndef GG_BWD_WFORM
-#define GG_BWD_WFORM 1        // 0: (Gbar, Gbar xi, Gbar xi^2) in registers (3 FFMA2/px); 1: only Gbar, xi as constants (4 ops/px)
 #endif
 #ifndef GG_FWD_KUNROLL
 #define GG_FWD_KUNROLL 0      // 0 = leave it to the compiler
@@ -369,20 +366,7 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
     }
     __syncthreads();
   }
-  // the upstream gradient of a pixel is shared by all Gaussians: Gbar, Gbar xi, Gbar xi^2 once (xi = j h)
-#if GG_BWD_WFORM == 0
-  f32x2 W0[NP][8], W1[NP][8], W2[NP][8];
-#pragma unroll
-  for (int p = 0; p < NP; ++p)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xi = (float)j * h;
-      const float ga = gm[2 * p][j], gb = gm[2 * p + 1][j];
-      W0[p][j] = pack2(ga, gb);
-      W1[p][j] = pack2(ga * xi, gb * xi);
-      W2[p][j] = pack2((ga * xi) * xi, (gb * xi) * xi);
-    }
-#else
+  // the upstream gradient of a pixel is shared by all Gaussians: packed once per row pair
   f32x2 W0[NP][8];
   float xi1[8], xi2[8];
 #pragma unroll
@@ -394,7 +378,6 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
   for (int p = 0; p < NP; ++p)
 #pragma unroll
     for (int j = 0; j < 8; ++j) W0[p][j] = pack2(gm[2 * p][j], gm[2 * p + 1][j]);
-#endif
 
 #pragma unroll kBwdKUnroll
   for (int kk = 0; kk < kn; ++kk) {
@@ -409,15 +392,6 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
       const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
       f32x2 G[8];
       eval_strip(c0, c1, steep, t0, e, dy, pos.colA, h, G);
-#if GG_BWD_WFORM == 0
-      f32x2 S0 = mul2(G[0], W0[p][0]), S1 = mul2(G[0], W1[p][0]), S2 = mul2(G[0], W2[p][0]);
-#pragma unroll
-      for (int j = 1; j < 8; ++j) {
-        S0 = fma2(G[j], W0[p][j], S0);
-        S1 = fma2(G[j], W1[p][j], S1);
-        S2 = fma2(G[j], W2[p][j], S2);
-      }
-#else
       f32x2 S0 = mul2(G[0], W0[p][0]);
       f32x2 u1 = mul2(G[1], W0[p][1]);
       f32x2 S1 = mul2(u1, bc(xi1[1])), S2 = mul2(u1, bc(xi2[1]));
@@ -429,7 +403,6 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
         S1 = fma2(u, bc(xi1[j]), S1);
         S2 = fma2(u, bc(xi2[j]), S2);
       }
-#endif
       // strip-local moments (about x_0) -> moments of t = t0 + xi, then the row weights
       const f32x2 m1 = fma2(t0, S0, S1);
       const f32x2 m2 = fma2(t0, add2(S1, m1), S2);

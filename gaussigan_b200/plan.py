@@ -171,3 +171,115 @@ class SilhouetteLossStep(SilhouetteStep):
             self.loss_backward(target)
         self.graph = g
         return g
+
+
+class DynamicObjectStep:
+    """Config 3 of BASELINE.json planned once: the dynamic-object mask step of the reference
+    (mask/mask_gen_dynamic.py:383-401 frame -> canonical covariances, :430 SVD, :426-458 per-frame deformation,
+    :707 render, :785-787 ``m_recon_loss_bis``) and its whole backward, as a fixed sequence of C-ABI launches on
+    pre-allocated buffers -- no autograd bookkeeping, no host synchronisation, capturable in one CUDA graph.
+
+        step = DynamicObjectStep(B, K, size, device)
+        step.bind(v0, v1, u_raw, cannmu, mu_t, scale, ang, theta_raw)    # static input tensors (head OUTPUTS, after tanh)
+        step.loss_backward(target)                                       # target [B,n,n] uint8 | float32 in [-1,1]
+        step.loss(); step.grads                                          # dict of gradients w.r.t. every bound input
+
+    Shapes: ``v0, v1, u_raw [K,3]`` f32 (canonical frame heads), ``cannmu [K,3]`` f32, ``mu_t, scale, ang [B,K,3]``
+    f32 (``ang`` = per-Gaussian Euler x,y,z), ``theta_raw [B]`` f32.  Gradients of the batch-shared canonical
+    parameters are the sums over the batch (the broadcast of :428, :455).
+    """
+
+    def __init__(self, B: int, K: int, size: int = 256, device="cuda", tx=0.0, ty=0.0, tz=-2.0, focal=1.0):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("gaussigan_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if K > 64:
+            raise ValueError("the fused loss kernel handles K <= 64")
+        self.B, self.K, self.n, self.dev = int(B), int(K), int(size), dev
+        self.t, self.focal = (float(tx), float(ty), float(tz)), float(focal)
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        e = torch.empty
+        # forward intermediates
+        self.csig, self.U, self.V, self.S = e((K, 3, 3), **f64), e((K, 3, 3), **f64), e((K, 3, 3), **f64), e((K, 3), **f64)
+        self.mus, self.sig, self.theta = e((B, K, 3), **f32), e((B, K, 3, 3), **f64), e((B,), **f32)
+        self.zeros = torch.zeros((B,), **f32)                      # rotx = rotz = 0 (:706-709)
+        self.params = e((B, K, GG_PARAM_STRIDE), **f32)
+        self._sizes, self._one, self._zero = int_array([size]), int_array([1]), int_array([0])
+        self.T = check(lib.gg_splat_bwd_tiles(K, 1, self._sizes, self._zero, self._one, LAYOUT_NHWC), "gg_splat_bwd_tiles")
+        self.partials = e((B, self.T, K, GG_MOMENTS), **f32)
+        self.loss_partials = e((B * self.T,), **f32)
+        # backward intermediates
+        self.dmus, self.dsig, self.drot = e((B, K, 3), **f32), e((B, K, 3, 3), **f64), e((B, 3), **f32)
+        self.gtheta = e((B,), **f32)
+        self.dcmu_b, self.dU_b, self.dS_b = e((B, K, 3), **f32), e((B, K, 3, 3), **f64), e((B, K, 3), **f64)
+        self.dU, self.dS, self.gcsig = e((K, 3, 3), **f64), e((K, 3), **f64), e((K, 3, 3), **f64)
+        self.grads = {"v0": e((K, 3), **f32), "v1": e((K, 3), **f32), "u_raw": e((K, 3), **f32), "cannmu": e((K, 3), **f32),
+                      "mu_t": e((B, K, 3), **f32), "scale": e((B, K, 3), **f32), "ang": e((B, K, 3), **f32),
+                      "theta_raw": e((B,), **f32)}
+        self._in = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    #: C-ABI launches per step (plus four tiny torch reductions / copies)
+    LAUNCHES_PER_STEP = 10
+
+    def bind(self, v0, v1, u_raw, cannmu, mu_t, scale, ang, theta_raw):
+        B, K = self.B, self.K
+        for t, shape in ((v0, (K, 3)), (v1, (K, 3)), (u_raw, (K, 3)), (cannmu, (K, 3)), (mu_t, (B, K, 3)),
+                         (scale, (B, K, 3)), (ang, (B, K, 3)), (theta_raw, (B,))):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
+        self._in = (v0, v1, u_raw, cannmu, mu_t, scale, ang, theta_raw)
+
+    def loss_backward(self, target: torch.Tensor):
+        assert self._in is not None, "bind() inputs first"
+        assert target.is_cuda and target.is_contiguous() and target.numel() == self.B * self.n * self.n
+        assert target.dtype in (torch.uint8, torch.float32)
+        v0, v1, u_raw, cannmu, mu_t, scale, ang, theta_raw = self._in
+        B, K, n, d = self.B, self.K, self.n, self.dev.index
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        p = lambda t: t.data_ptr()
+        g = self.grads
+        # ---- forward
+        check(lib.gg_sigma_from_frame_fwd(p(v0), p(v1), p(u_raw), K, p(self.csig), d, st), "gg_sigma_from_frame_fwd")
+        check(lib.gg_svd3_fwd(p(self.csig), K, p(self.U), p(self.S), p(self.V), d, st), "gg_svd3_fwd")
+        check(lib.gg_deform_fwd(p(mu_t), p(scale), p(ang), p(cannmu), p(self.U), p(self.S), p(theta_raw), B, K,
+                                p(self.mus), p(self.sig), p(self.theta), d, st), "gg_deform_fwd")
+        check(lib.gg_project_fwd(p(self.mus), p(self.sig), 1, p(self.zeros), p(self.theta), p(self.zeros), *self.t,
+                                 self.focal, B, K, None, None, p(self.params), d, st), "gg_project_fwd")
+        check(lib.gg_silhouette_loss_fused(p(self.params), p(target), 0 if target.dtype == torch.uint8 else 1, B, K, n,
+                                           None, p(self.partials), self.T, p(self.loss_partials), d, st),
+              "gg_silhouette_loss_fused")
+        # ---- backward
+        check(lib.gg_project_bwd(p(self.mus), p(self.sig), 1, p(self.zeros), p(self.theta), p(self.zeros), *self.t,
+                                 self.focal, B, K, p(self.partials), self.T, None, None, p(self.dmus), p(self.dsig),
+                                 p(self.drot), d, st), "gg_project_bwd")
+        self.gtheta.copy_(self.drot[:, 1])                          # d loss / d roty
+        check(lib.gg_deform_bwd(p(scale), p(ang), p(self.U), p(self.S), p(self.dmus), p(self.dsig), p(self.gtheta), B, K,
+                                p(g["theta_raw"]), p(g["mu_t"]), p(g["scale"]), p(g["ang"]), p(self.dcmu_b),
+                                p(self.dU_b), p(self.dS_b), d, st), "gg_deform_bwd")
+        torch.sum(self.dcmu_b, dim=0, out=g["cannmu"])              # canonical parameters are broadcast over the batch
+        torch.sum(self.dU_b, dim=0, out=self.dU)
+        torch.sum(self.dS_b, dim=0, out=self.dS)
+        check(lib.gg_svd3_bwd(p(self.U), p(self.S), p(self.V), p(self.dU), p(self.dS), K, p(self.gcsig), d, st),
+              "gg_svd3_bwd")
+        check(lib.gg_sigma_from_frame_bwd(p(v0), p(v1), p(u_raw), p(self.gcsig), K, p(g["v0"]), p(g["v1"]),
+                                          p(g["u_raw"]), d, st), "gg_sigma_from_frame_bwd")
+        return g
+
+    def loss(self) -> float:
+        return float(self.loss_partials.double().sum().item() / (self.B * self.n * self.n))
+
+    def capture(self, target: torch.Tensor) -> torch.cuda.CUDAGraph:
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self.loss_backward(target)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            self.loss_backward(target)
+        self.graph = gr
+        return gr

@@ -834,3 +834,33 @@ def test_second_device_in_the_same_process(gg, cuda_device):
     for o in outs[1:]:
         for a, b in zip(o, outs[0]):
             assert torch.equal(a, b)
+
+
+def test_planned_dynamic_object_step_equals_autograd_chain(gg, cuda_device):
+    """DynamicObjectStep (config 3 as a fixed launch sequence, graph-captured) against the autograd chain
+    sigma_from_frame -> deform -> mask_recon_loss_bis, which test_config3_full_cuda_pipeline pins to the oracle."""
+    from gaussigan_b200.plan import DynamicObjectStep
+    B, K, n = 5, 16, 96
+    g = torch.Generator().manual_seed(77)
+    th = lambda *s: torch.tanh(torch.randn(*s, generator=g)).to(cuda_device)
+    v0, v1, u_raw, cmu = th(K, 3), th(K, 3), torch.randn(K, 3, generator=g).to(cuda_device), th(K, 3)
+    mu_t, scale, ang, theta_raw = th(B, K, 3), th(B, K, 3), th(B, K, 3), th(B)
+    tgt = (torch.rand(B, n, n, generator=g) * 255).to(torch.uint8).to(cuda_device)
+    step = DynamicObjectStep(B, K, n, cuda_device)
+    step.bind(v0, v1, u_raw, cmu, mu_t, scale, ang, theta_raw)
+    step.capture(tgt)
+    for t in step.grads.values():
+        t.zero_()
+    step.graph.replay()
+    torch.cuda.synchronize()
+    # autograd chain on the same numbers
+    lv = [t.clone().requires_grad_(True) for t in (v0, v1, u_raw, cmu, mu_t, scale, ang, theta_raw)]
+    csig = gg.sigma_from_frame(lv[0].view(1, K, 3), lv[1].view(1, K, 3), lv[2].view(1, K, 3))
+    mus, sig, theta = gg.deform(lv[4].reshape(B, K * 3), lv[5].reshape(B, K * 3), lv[6][..., 0], lv[6][..., 1], lv[6][..., 2],
+                                lv[7].view(B, 1), lv[3].view(1, K, 1, 3), csig)
+    z = torch.zeros_like(theta)
+    loss = gg.mask_recon_loss_bis(tgt.float() / 127.5 - 1.0, mus, sig, z, theta, z, 0, 0, -2., size=n)
+    loss.backward()
+    assert abs(step.loss() - float(loss)) <= 1e-6 * abs(float(loss))
+    for name, ref in zip(("v0", "v1", "u_raw", "cannmu", "mu_t", "scale", "ang", "theta_raw"), lv):
+        assert_close_norm(step.grads[name], ref.grad, 1e-5, "planned dynamic step grad " + name)

@@ -56,3 +56,19 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(5): step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
+
+# ---- the same step as a planned launch sequence (gaussigan_b200.plan.DynamicObjectStep), one CUDA graph
+from gaussigan_b200.plan import DynamicObjectStep
+gth = torch.Generator().manual_seed(5)
+tt = lambda *s: torch.tanh(torch.randn(*s, generator=gth)).to(dev)
+ps = DynamicObjectStep(B, K, n, dev)
+ps.bind(tt(K, 3), tt(K, 3), torch.randn(K, 3, generator=gth).to(dev), tt(K, 3), tt(B, K, 3), tt(B, K, 3), tt(B, K, 3), tt(B))
+raw = ((tgt.reshape(B, n, n) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+ps.capture(raw)
+for _ in range(5): ps.graph.replay()
+torch.cuda.synchronize()
+a.record()
+for _ in range(N): ps.graph.replay()
+b.record(); torch.cuda.synchronize()
+us = a.elapsed_time(b) / N * 1e3
+print(f"C3 B={B}: {us:.1f} us/step = {B / us * 1e6:.0f} silhouettes/s (DynamicObjectStep, planned launches in one CUDA graph), loss {ps.loss():.6f}")

@@ -354,30 +354,63 @@ def run_gpu(args):
     except Exception as exc:                      # pragma: no cover
         fused = {"value": None, "error": repr(exc)}
 
-    # ---- training-time exchange: all-reduce of the shared (canonical-Gaussian) gradients after every step
+    # ---- training-time exchange: the shared (canonical-Gaussian) gradients summed over batch and ranks after every step.
+    # (a) gaussigan_b200.dist.P2PSharedGradReducer: one single-CTA kernel over NVLink peer memory, captured in the same
+    #     graph as the steps; (b) the same with a local torch sum + one NCCL all_reduce per step (eager).
     allreduce = None
     if world > 1:
-        from gaussigan_b200.dist import reduce_shared_grads
-        for i in range(3):
-            s0 = sets[i % R][0]
-            s0.graph.replay()
-            reduce_shared_grads([s0.dmus, s0.dsigma])
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(args.steps):
-            s0 = sets[i % R][0]
-            s0.graph.replay()
-            reduce_shared_grads([s0.dmus, s0.dsigma])
-        b.record()
-        barrier()
-        ams = a.elapsed_time(b)
-        t = torch.tensor([ams], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ams = float(t.item())
-        allreduce = {"value": world * B / (ams / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ams / args.steps,
-                     "payload_bytes": K * 3 * 8 + K * 9 * 8,
-                     "note": "value with one NCCL all_reduce(SUM) of the batch-summed canonical-Gaussian gradients per step"}
+        from gaussigan_b200.dist import P2PSharedGradReducer, reduce_shared_grads
+
+        def timed(run, nsteps):
+            run(2 * R * ROUNDS)
+            barrier()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            run(nsteps)
+            b_.record()
+            barrier()
+            t_ = torch.tensor([a_.elapsed_time(b_)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item()) / nsteps
+
+        def nccl_steps(nsteps):
+            for i in range(nsteps):
+                s0 = sets[i % R][0]
+                s0.graph.replay()
+                reduce_shared_grads([s0.dmus, s0.dsigma])
+
+        nsteps = (args.steps // (R * ROUNDS)) * (R * ROUNDS) or R * ROUNDS      # same count on every rank, whole graphs
+        ams = timed(nccl_steps, nsteps)
+        allreduce = {"nccl": {"value": world * B / (ams * 1e-3), "unit": UNIT, "ms_per_step": ams,
+                              "note": "local torch sum + one eager NCCL all_reduce(SUM) per step"},
+                     "payload_bytes": K * 12 * 8}
+        try:
+            red = P2PSharedGradReducer(K, dev)
+
+            def steps_with_exchange():
+                for _ in range(ROUNDS):
+                    for st_, gm_, _, _ in sets:
+                        st_.forward()
+                        st_.backward(gm_)
+                        red(st_.dmus, st_.dsigma)
+
+            pchain = capture_chain(steps_with_exchange)
+            dist.barrier()
+
+            def p2p_steps(nsteps_):
+                for _ in range(nsteps_ // (R * ROUNDS)):
+                    pchain.replay()
+
+            pms = timed(p2p_steps, nsteps)
+            red.check()
+            allreduce.update({"value": world * B / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms,
+                              "note": "every step followed by gg_shared_grad_allreduce_p2p (one kernel: local batch sum, "
+                                      "stores into the peers' slots over NVLink, flag exchange, rank-ordered sum), all in "
+                                      "the step graph"})
+            del pchain
+        except Exception as exc:                  # pragma: no cover - e.g. no peer access
+            allreduce.update({"value": allreduce["nccl"]["value"], "unit": UNIT, "ms_per_step": ams,
+                              "note": "P2P reducer unavailable (" + repr(exc)[:120] + "): NCCL number"})
 
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
     e2e = None

@@ -54,6 +54,8 @@ SIGNATURES = {
     "gg_silhouette_loss_fused": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_sigma_from_frame_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_sigma_from_frame_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "gg_p2p_buffer_bytes": (C.c_size_t, [_i, _i]),
+    "gg_shared_grad_allreduce_p2p": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
     "gg_svd3_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
     "gg_svd3_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_deform_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),

@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIBNAME = "libgaussigan_sm100.so"
-SOURCES = ["gg_capi.cu", "gg_project.cu", "gg_splat.cu", "gg_splat_fast.cu", "gg_splat_tma.cu", "gg_fused.cu", "gg_geometry.cu", "gg_host.cu"]
+SOURCES = ["gg_capi.cu", "gg_project.cu", "gg_splat.cu", "gg_splat_fast.cu", "gg_splat_tma.cu", "gg_fused.cu", "gg_geometry.cu", "gg_host.cu", "gg_p2p.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -252,6 +252,22 @@ int gg_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, co
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_sigma_from_frame_bwd");
 }
 
+size_t gg_p2p_buffer_bytes(int K, int world) {
+  if (K <= 0 || world <= 0) return 0;
+  return gg::p2p_buffer_bytes(K, world);
+}
+
+int gg_shared_grad_allreduce_p2p(const float *dmus, const double *dsigma, int B, int K, const void *peers_dev, int world,
+                                 int rank, double *out, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(GG_E_SHAPE, "bad world/rank (%d/%d)", world, rank);
+  if (!dmus || !dsigma || !peers_dev || !out) return fail(GG_E_NULL, "gg_shared_grad_allreduce_p2p: NULL pointer");
+  if (int r = set_device(device)) return r;
+  cudaError_t e = gg::launch_shared_grad_allreduce(dmus, dsigma, B, K, reinterpret_cast<const unsigned long long *>(peers_dev),
+                                                   world, rank, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_shared_grad_allreduce_p2p");
+}
+
 int gg_svd3_fwd(const double *A, int N, double *U, double *S, double *V, int device, void *stream) {
   if (N < 0) return fail(GG_E_SHAPE, "N < 0");
   if (N == 0) return GG_OK;

@@ -60,6 +60,11 @@ cudaError_t launch_deform_bwd(const float *sc, const float *ang, const double *U
                               const double *gsig, const float *gtheta, int B, int K, float *dtheta_raw, float *dmu_t,
                               float *dsc, float *dang, float *dcmu, double *dU, double *dS, cudaStream_t st);
 
+size_t p2p_buffer_bytes(int K, int world);
+cudaError_t launch_shared_grad_allreduce(const float *dmus, const double *dsigma, int B, int K,
+                                         const unsigned long long *peers, int world, int rank, double *out,
+                                         cudaStream_t st);
+
 namespace api {   // error/validation helpers shared by the extern "C" translation units (gg_capi.cu)
 int fail(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *where);

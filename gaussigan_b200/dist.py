@@ -49,3 +49,53 @@ def reduce_shared_grads(per_sample_grads: Sequence[torch.Tensor], group=None) ->
         out.append(flat[off:off + n].reshape(g.shape).to(g.dtype))
         off += n
     return out
+
+
+class P2PSharedGradReducer:
+    """``reduce_shared_grads`` for the renderer's own gradients as ONE kernel over NVLink peer memory
+    (``gg_shared_grad_allreduce_p2p``, include/gaussigan.h): local batch sum + stores into every peer's receive slot +
+    flag exchange + rank-ordered sum.  ~10x less latency than an eager NCCL ``all_reduce`` at this payload
+    (12*K numbers), bit-identical on all ranks, replayable from a CUDA graph.
+
+        red = P2PSharedGradReducer(K, device)                  # collective: every rank of the group constructs it
+        dmu_sum, dsig_sum = red(dmus, dsigma)                  # [B,K,3] f32, [B,K,3,3] f64 -> [K,3], [K,3,3] float64
+
+    Needs ``torch.distributed`` initialised with NCCL on one node with peer access (NVLink / NVSwitch): the exchange
+    buffers come from ``torch.distributed._symmetric_memory``.  ``check()`` synchronises and raises if a peer timed out.
+    """
+
+    def __init__(self, K: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from ._lib import lib
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.K, self.dev = int(K), dev
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = int(lib.gg_p2p_buffer_bytes(self.K, self.world))
+        self.buf = symm_mem.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.buf.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                                      # nobody signals into a buffer that is still being zeroed
+        self.peers = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.out = torch.empty(12 * self.K, dtype=torch.float64, device=dev)
+
+    def __call__(self, dmus: torch.Tensor, dsigma: torch.Tensor):
+        from ._lib import check, lib
+        B = dmus.shape[0]
+        assert dmus.is_cuda and dmus.dtype == torch.float32 and dmus.is_contiguous() and dmus.numel() == B * self.K * 3
+        assert dsigma.dtype == torch.float64 and dsigma.is_contiguous() and dsigma.numel() == B * self.K * 9
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        check(lib.gg_shared_grad_allreduce_p2p(dmus.data_ptr(), dsigma.data_ptr(), B, self.K, self.peers.data_ptr(),
+                                               self.world, self.rank, self.out.data_ptr(), self.dev.index, st),
+              "gg_shared_grad_allreduce_p2p")
+        K = self.K
+        return self.out[:3 * K].view(K, 3), self.out[3 * K:].view(K, 3, 3)
+
+    def check(self) -> None:
+        torch.cuda.synchronize(self.dev)
+        err = int(self.buf.view(torch.int32)[1].item())
+        if err:
+            raise RuntimeError(f"gg_shared_grad_allreduce_p2p: a peer did not arrive in call {err}")

@@ -199,6 +199,21 @@ GG_API int gg_deform_bwd(const float *scale, const float *ang, const double *U, 
                          const double *gsig, const float *gtheta, int B, int K, float *dtheta_raw, float *dmu_t,
                          float *dscale, float *dang, float *dcmu, double *dU, double *dS, int device, void *stream);
 
+/* ---- training-time exchange over NVLink peer memory ------------------------------------------------------
+ * Gradient of the batch-shared canonical Gaussians (mask/mask_gen_dynamic.py:701-702 broadcast): sum of the
+ * per-sample gradients dmus [B,K,3] f32 and dsigma [B,K,3,3] f64 over the local batch and over all `world` ranks of
+ * one node, in ONE single-CTA kernel: local sum, direct stores into every peer's receive slot, flag exchange with
+ * system-scope release/acquire, rank-ordered final sum (bit-identical on all ranks).  `peers_dev` is a DEVICE array
+ * of `world` base addresses of the ranks' exchange buffers (peer-mapped, e.g. torch symmetric memory), each
+ * gg_p2p_buffer_bytes(K, world) bytes, zero-filled once before the first call (with a barrier across ranks).
+ * out [12*K] f64 = dmu sums [K,3] followed by dsigma sums [K,3,3].  Every rank must make the same sequence of calls.
+ * Replayable from a CUDA graph (the call counter lives in the buffer).  If a peer does not arrive within ~1 s the
+ * kernel stores the call number in word 1 of the rank's own buffer and returns without writing `out`. */
+GG_API size_t gg_p2p_buffer_bytes(int K, int world);
+GG_API int gg_shared_grad_allreduce_p2p(const float *dmus, const double *dsigma, int B, int K,
+                                        const void *peers_dev, int world, int rank, double *out, int device,
+                                        void *stream);
+
 /* ---- whole training-style step on HOST buffers ---------------------------------------------------
  * What a host-language binding of the reference would call (the reference feeds numpy arrays through
  * session.run, mask/infer_masks.py:435-456): H2D of the inputs, projection, splat (silhouette), L1 loss and its

@@ -864,3 +864,55 @@ def test_planned_dynamic_object_step_equals_autograd_chain(gg, cuda_device):
     assert abs(step.loss() - float(loss)) <= 1e-6 * abs(float(loss))
     for name, ref in zip(("v0", "v1", "u_raw", "cannmu", "mu_t", "scale", "ang", "theta_raw"), lv):
         assert_close_norm(step.grads[name], ref.grad, 1e-5, "planned dynamic step grad " + name)
+
+
+def test_p2p_shared_grad_reducer_single_rank(gg, cuda_device):
+    """gg_shared_grad_allreduce_p2p with a one-rank group (the 2- and 8-rank runs are tools/p2p_allreduce_check.py,
+    results in profiles/): local batch sum in float64 in batch order, slot/flag protocol over many calls (both slot
+    sets, epochs), CUDA-graph replay."""
+    import torch.distributed as dist
+    from gaussigan_b200.dist import P2PSharedGradReducer
+    created = False
+    if not dist.is_initialized():
+        os_env = __import__("os").environ
+        os_env.setdefault("MASTER_ADDR", "127.0.0.1")
+        os_env.setdefault("MASTER_PORT", "29611")
+        try:
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda_device)
+        except Exception as exc:                                   # pragma: no cover
+            pytest.skip(f"cannot create a one-rank NCCL group here: {exc!r}")
+        created = True
+    try:
+        try:
+            K, B = 16, 37
+            red = P2PSharedGradReducer(K, cuda_device)
+        except Exception as exc:                                   # pragma: no cover
+            pytest.skip(f"symmetric memory unavailable: {exc!r}")
+        g = torch.Generator().manual_seed(4)
+        for it in range(7):
+            dmus = torch.randn(B, K, 3, generator=g).to(cuda_device)
+            dsig = torch.randn(B, K, 3, 3, generator=g, dtype=torch.float64).to(cuda_device)
+            a, b = red(dmus, dsig)
+            red.check()
+            ra = torch.zeros(K, 3, dtype=torch.float64, device=cuda_device)
+            rb = torch.zeros(K, 3, 3, dtype=torch.float64, device=cuda_device)
+            for i in range(B):                                      # the kernel's order: batch ascending
+                ra += dmus[i].double()
+                rb += dsig[i]
+            assert torch.equal(a, ra) and torch.equal(b, rb)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(cuda_device)
+        side.wait_stream(torch.cuda.current_stream(cuda_device))
+        with torch.cuda.stream(side):
+            red(dmus, dsig)
+        torch.cuda.current_stream(cuda_device).wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph):
+            red(dmus, dsig)
+        for _ in range(5):
+            graph.replay()
+        red.check()
+        assert torch.equal(red.out[:3 * K].view(K, 3), ra)
+    finally:
+        if created:
+            dist.destroy_process_group()

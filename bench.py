@@ -157,7 +157,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from gaussigan_b200.plan import SilhouetteStep
     from gaussigan_b200.host import HostSilhouetteStep
-    from oracle import reference_port as rp       # synthetic-input generator + cpu_baseline leg only
+    from gaussigan_b200 import synth              # synthetic inputs; the oracle is used by the cpu_baseline leg only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -175,8 +175,8 @@ def run_gpu(args):
     R = args.rotate
     sets = []
     for r in range(R):
-        inp = rp.synth_inputs(B, K, seed=56 + 1000 * rank + r)
-        tgt = rp.synth_target_masks(B, n, seed=57 + 1000 * rank + r)
+        inp = synth.synth_inputs(B, K, seed=56 + 1000 * rank + r, device=dev)
+        tgt = synth.synth_target_masks(B, n, seed=57 + 1000 * rank + r)
         step = SilhouetteStep(B, K, n, dev)
         mus = inp["mus"].reshape(B, K, 3).contiguous().to(dev)
         sig = inp["sigma"].contiguous().to(dev)

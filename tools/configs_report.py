@@ -6,7 +6,7 @@ import torch
 import gaussigan_b200 as gg
 from gaussigan_b200.plan import SilhouetteStep, SilhouetteLossStep
 from gaussigan_b200._lib import lib, check, int_array, ptr_array, LAYOUT_NHWC, GG_PARAM_STRIDE
-from oracle import reference_port as rp
+from gaussigan_b200 import synth as rp
 dev = torch.device("cuda:0")
 
 def timeit(fn, reps):

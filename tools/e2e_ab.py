@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gaussigan_b200.host import HostSilhouetteStep
-from oracle import reference_port as rp
+from gaussigan_b200 import synth as rp
 dev = torch.device('cuda:0'); B, K, n = 64, 16, 256
 depth = int(os.environ.get("DEPTH", 4))
 inp = rp.synth_inputs(B, K, seed=56); tgt = rp.synth_target_masks(B, n)

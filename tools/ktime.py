@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gaussigan_b200.plan import SilhouetteStep
 from gaussigan_b200._lib import lib, check, int_array, ptr_array, LAYOUT_NHWC, LAYOUT_NCHW
-from oracle import reference_port as rp
+from gaussigan_b200 import synth as rp
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--B', type=int, default=64); ap.add_argument('--K', type=int, default=16); ap.add_argument('--n', type=int, default=256)

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gaussigan_b200.plan import SilhouetteStep
-from oracle import reference_port as rp
+from gaussigan_b200 import synth as rp
 B, K, n = int(os.environ.get("PB", 64)), 16, 256
 dev = torch.device("cuda:0")
 inp = rp.synth_inputs(B, K, seed=56)

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 from gaussigan_b200.plan import SilhouetteStep
 from gaussigan_b200.dist import shard_range
-from oracle import reference_port as rp
+from gaussigan_b200 import synth as rp
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import gaussigan_b200 as gg
-from oracle import reference_port as rp
+from gaussigan_b200 import synth as rp
 dev = torch.device("cuda:0")
 B, K, n = int(os.environ.get("B", 256)), 16, 256
 g = torch.Generator().manual_seed(33)

@@ -16,6 +16,11 @@ struct StepLayout {
 
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
+static size_t target_bytes(int B, int n, int target_kind) {
+  if (target_kind == GG_TARGET_BITS) return (size_t)B * n * ((n + 7) / 8);
+  return (size_t)B * n * n * (target_kind == GG_TARGET_U8 ? 1 : 4);
+}
+
 StepLayout step_layout(int B, int K, int n, int target_kind) {
   StepLayout L;
   size_t off = 0;
@@ -25,7 +30,7 @@ StepLayout step_layout(int B, int K, int n, int target_kind) {
   L.mus = take((size_t)B * K * 3 * 4);
   L.sigma = take((size_t)B * K * 9 * 8);
   L.rot = take((size_t)B * 3 * 4);
-  L.target = take((size_t)B * n * n * (target_kind == 0 ? 1 : 4));
+  L.target = take(target_bytes(B, n, target_kind));
   L.params = take((size_t)B * K * GG_PARAM_STRIDE * 4);
   L.mask = take((size_t)B * n * n * 4);
   L.gmask = take((size_t)B * n * n * 4);
@@ -83,7 +88,10 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
   const int sizes[1] = {n};
   if (int r = check_scales(K, 1, sizes)) return r;
   if (B == 0) return GG_OK;
-  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32) return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
+  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32 && target_kind != GG_TARGET_BITS)
+    return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
+  if (target_kind == GG_TARGET_BITS && (K > 64 || !gg::fast_mask()))
+    return fail(GG_E_SHAPE, "GG_TARGET_BITS: K <= 64 and the forward-differenced kernels only");
   if (((size_t)B * n * n) & 3) return fail(GG_E_SHAPE, "gg_silhouette_step_host: B*n*n must be a multiple of 4");
   if (!mus_host || !sigma_host || !rotx_host || !roty_host || !rotz_host || !target_host || !loss_partials_host ||
       !dmus_host || !dsigma_host || !drot_host || !workspace)
@@ -136,7 +144,7 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
     const void *m = zc_target ? mapped_or_null(target_host) : nullptr;
     if (m) k_target = m;
     else
-      GG_TRY(cudaMemcpyAsync(d_target, target_host, px * (target_kind == GG_TARGET_U8 ? 1 : 4), cudaMemcpyHostToDevice,
+      GG_TRY(cudaMemcpyAsync(d_target, target_host, gg::target_bytes(B, n, target_kind), cudaMemcpyHostToDevice,
                              st), "H2D target");
   }
   GG_TRY(gg::launch_project_fwd(k_mus, k_sigma, 1, k_rx, k_ry, k_rz, tx, ty, tz, focal, B, K,

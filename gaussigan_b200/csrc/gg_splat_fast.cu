@@ -340,6 +340,13 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
 #pragma unroll
           for (int j = 0; j < 8; ++j) tg[j] = (pos.colA + j < n) ? lut[__ldg(tp + pos.colA + j)] : 0.f;
         }
+      } else if (a.target_kind == GG_TARGET_BITS) {
+        // one byte = this thread's 8 pixels (strips start at multiples of 8); bit set -> 0.5 * (1 + 1) = 1
+        const unsigned char *tp = reinterpret_cast<const unsigned char *>(a.target) +
+                                  ((size_t)b * n + row[r]) * (size_t)((n + 7) >> 3);
+        const unsigned bits = pos.colA < n ? (unsigned)__ldg(tp + (pos.colA >> 3)) : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tg[j] = ((bits >> j) & 1u) ? 1.0f : 0.0f;
       } else {
         load8c(reinterpret_cast<const float *>(a.target) + off, pos.colA, n, tg);
 #pragma unroll

@@ -16,7 +16,7 @@ import torch
 
 from ._lib import check, lib
 
-GG_TARGET_U8, GG_TARGET_F32 = 0, 1
+GG_TARGET_U8, GG_TARGET_F32, GG_TARGET_BITS = 0, 1, 2
 GG_LOSS_PARTIALS = 296
 
 
@@ -62,7 +62,7 @@ class HostSilhouetteStep:
 
     def __init__(self, B: int, K: int, size: int = 256, device="cuda", depth: int = 2,
                  tx: float = 0.0, ty: float = 0.0, tz: float = -2.0, focal: float = 1.0,
-                 target_dtype: torch.dtype = torch.uint8, want_mask: bool = False):
+                 target_dtype: torch.dtype = torch.uint8, want_mask: bool = False, target_bits: bool = False):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("gaussigan_b200 runs on CUDA (sm_100a) only; there is no CPU path")
@@ -75,6 +75,10 @@ class HostSilhouetteStep:
         self.focal = float(focal)
         self.kind = GG_TARGET_U8 if target_dtype == torch.uint8 else GG_TARGET_F32
         self.target_dtype = target_dtype
+        if target_bits:          # binary masks, 1 bit per pixel (GG_TARGET_BITS): 8x fewer bytes over PCIe
+            if target_dtype != torch.uint8 or K > 64:
+                raise ValueError("target_bits needs uint8 storage and K <= 64")
+            self.kind = GG_TARGET_BITS
         self.ws_bytes = int(lib.gg_silhouette_step_workspace_bytes(self.B, self.K, self.n, self.kind))
         if self.ws_bytes <= 0:
             raise ValueError("bad B/K/size")
@@ -85,8 +89,9 @@ class HostSilhouetteStep:
         self.LAUNCHES_PER_STEP = 3 if self.K <= 64 else 5
         self.results = [StepResult(self.B, self.K, self.n, want_mask, self.nloss) for _ in range(self.depth)]
         self._next = 0
-        tb = 1 if self.kind == GG_TARGET_U8 else 4
-        self.h2d_bytes = B * K * 3 * 4 + B * K * 9 * 8 + 3 * B * 4 + B * size * size * tb
+        self.target_numel = B * size * ((size + 7) // 8) if self.kind == GG_TARGET_BITS else B * size * size
+        tb = 4 if self.kind == GG_TARGET_F32 else 1
+        self.h2d_bytes = B * K * 3 * 4 + B * K * 9 * 8 + 3 * B * 4 + self.target_numel * tb
         self.d2h_bytes = (self.nloss * 4 + B * K * 3 * 4 + B * K * 9 * 8 + B * 3 * 4
                           + (B * size * size * 4 if want_mask else 0))
 
@@ -94,7 +99,10 @@ class HostSilhouetteStep:
         """Pack oracle-style inputs (mus [B,K,1,3], sigma, rot [B,1], target [B,n,n,1] in {-1,+1}) into pinned buffers."""
         B, K, n = self.B, self.K, self.n
         t = target_pm1.reshape(B, n, n)
-        if self.kind == GG_TARGET_U8:
+        if self.kind == GG_TARGET_BITS:
+            assert bool(((t == 1) | (t == -1)).all()), "target_bits: the masks must be two-level (-1 / +1)"
+            t = torch.from_numpy(np.packbits((t > 0).numpy(), axis=-1, bitorder="little"))      # [B,n,ceil(n/8)]
+        elif self.kind == GG_TARGET_U8:
             t = ((t + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
         else:
             t = t.float()
@@ -110,7 +118,7 @@ class HostSilhouetteStep:
         B, K, n = self.B, self.K, self.n
         assert h.mus.dtype == torch.float32 and h.mus.numel() == B * K * 3 and h.mus.is_contiguous()
         assert h.sigma.dtype == torch.float64 and h.sigma.numel() == B * K * 9 and h.sigma.is_contiguous()
-        assert h.target.dtype == self.target_dtype and h.target.numel() == B * n * n and h.target.is_contiguous()
+        assert h.target.dtype == self.target_dtype and h.target.numel() == self.target_numel and h.target.is_contiguous()
         for r in (h.rotx, h.roty, h.rotz):
             assert r.dtype == torch.float32 and r.numel() == B and r.is_contiguous()
         assert not h.mus.is_cuda and not h.target.is_cuda, "HostSilhouetteStep takes HOST tensors"

@@ -136,10 +136,16 @@ class SilhouetteLossStep(SilhouetteStep):
         self.loss_partials = torch.empty(self.B * self.T, dtype=torch.float32, device=self.dev)
         self.want_mask = want_mask
 
-    def loss_backward(self, target: torch.Tensor):
-        assert target.is_cuda and target.is_contiguous() and target.numel() == self.B * self.n * self.n
-        assert target.dtype in (torch.uint8, torch.float32)
-        kind = 0 if target.dtype == torch.uint8 else 1
+    def loss_backward(self, target: torch.Tensor, bits: bool = False):
+        """``target`` [B,n,n] uint8 (raw 0..255) or float32 in [-1,1]; with ``bits=True`` a two-level mask packed one
+        bit per pixel, uint8 [B,n,ceil(n/8)] (``numpy.packbits(mask > 0, axis=-1, bitorder="little")``)."""
+        assert target.is_cuda and target.is_contiguous()
+        if bits:
+            assert target.dtype == torch.uint8 and target.numel() == self.B * self.n * ((self.n + 7) // 8)
+            kind = 2
+        else:
+            assert target.numel() == self.B * self.n * self.n and target.dtype in (torch.uint8, torch.float32)
+            kind = 0 if target.dtype == torch.uint8 else 1
         mus, sigma, rotx, roty, rotz = self._inputs
         st = self._stream()
         check(lib.gg_project_fwd(mus.data_ptr(), sigma.data_ptr(), self.sigma_f64, rotx.data_ptr(),

@@ -50,6 +50,11 @@ extern "C" {
 
 #define GG_TARGET_U8 0            /* target mask as the raw 8-bit image; mask = raw/127.5 - 1 (mask_gen_dynamic.py:672) */
 #define GG_TARGET_F32 1           /* target mask already in [-1, 1], float32 */
+#define GG_TARGET_BITS 2          /* BINARY target mask, 1 bit per pixel: rows of ceil(n/8) bytes, pixel j of a row is bit
+                                     (j & 7) of byte (j >> 3) (numpy.packbits(..., bitorder="little")); bit 1 = mask +1,
+                                     bit 0 = mask -1.  Lossless only for two-level masks; 8x fewer bytes than GG_TARGET_U8
+                                     on the host link.  gg_silhouette_loss_fused (forward-differenced kernels) and
+                                     gg_silhouette_step_host with K <= 64 only. */
 #define GG_LOSS_PARTIALS 296      /* per-CTA partial sums of |residual| written by gg_mask_l1_loss_bwd */
 
 #define GG_OK 0

@@ -916,3 +916,32 @@ def test_p2p_shared_grad_reducer_single_rank(gg, cuda_device):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [256, 100, 37])
+def test_bit_packed_binary_targets_equal_uint8_targets(gg, cuda_device, n):
+    """GG_TARGET_BITS (two-level masks, 1 bit per pixel) gives bit for bit the loss and gradients of the same masks as
+    uint8 images, through the planned fused step and through the host-buffer step."""
+    import numpy as np
+    from gaussigan_b200.host import HostSilhouetteStep
+    from gaussigan_b200.plan import SilhouetteLossStep
+    B, K = 4, 16
+    inp = rp.synth_inputs(B, K, seed=9)
+    tgt = rp.synth_target_masks(B, n, seed=n)                         # {-1,+1}
+    d = _dev(inp, cuda_device)
+    raw = ((tgt.reshape(B, n, n) + 1.0) * 127.5).round().to(torch.uint8)
+    packed = torch.from_numpy(np.packbits((tgt.reshape(B, n, n) > 0).numpy(), axis=-1, bitorder="little"))
+    assert packed.shape == (B, n, (n + 7) // 8)
+    step = SilhouetteLossStep(B, K, n, cuda_device)
+    step.bind(d["mus"].reshape(B, K, 3).contiguous(), d["sigma"], *(d[k].reshape(B).contiguous() for k in ("rotx", "roty", "rotz")))
+    ref = [t.clone() for t in step.loss_backward(raw.to(cuda_device))] + [step.loss_partials.clone()]
+    out = [t.clone() for t in step.loss_backward(packed.contiguous().to(cuda_device), bits=True)] + [step.loss_partials.clone()]
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
+    hu = HostSilhouetteStep(B, K, n, cuda_device, depth=2)
+    hb = HostSilhouetteStep(B, K, n, cuda_device, depth=2, target_bits=True)
+    ru = hu.submit(hu.make_host_inputs(inp, tgt)).wait()
+    rb = hb.submit(hb.make_host_inputs(inp, tgt)).wait()
+    torch.cuda.synchronize()
+    assert hb.h2d_bytes < hu.h2d_bytes and ru.loss == rb.loss
+    assert torch.equal(ru.dmus, rb.dmus) and torch.equal(ru.dsigma, rb.dsigma) and torch.equal(ru.drot, rb.drot)

@@ -546,7 +546,7 @@ def run_gpu(args):
                                    "projection in float64, splat in float32",
                        "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": f"{R} rotating input/output sets = {rot_bytes / 1e6:.0f} MB > 126 MB L2",
-                       "step": "project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd; 8 steps per CUDA-graph replay, kernels chained by programmatic dependent launch"},
+                       "step": "project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd; 32 steps per CUDA-graph replay, kernels chained by programmatic dependent launch"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "e2e_binary_targets": e2e_bits,
             "fused_loss": fused, "two_chains": two_chains,
             "allreduce": allreduce,
@@ -560,7 +560,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="gaussigan_b200", choices=["gaussigan_b200", "reference"])
     ap.add_argument("--rotate", type=int, default=8, help="rotating buffer sets (inputs larger than L2)")

@@ -155,3 +155,76 @@ def load_reference_functions(path: str, names: Iterable[str], nb_landmarks: int,
         ns.update(extra_globals)
     exec(compile(mod, path, "exec"), ns)  # noqa: S102 -- executing the read-only reference, on purpose
     return {n: ns[n] for n in wanted}
+
+
+# ------------------------------------------------------------------------------------------------
+# Geometry tails: Model.get_musigma (:369-403) and Model.transform_mu_sigma (:405-460) are METHODS that mix the
+# dense heads (out of scope) with the tensor algebra of rows a6 / a7.  They are executed as they stand, with
+# ``tf.layers.dense`` replaced by a queue that hands out pre-drawn head pre-activations (hidden layers get zeros),
+# so that everything downstream of the heads -- tanh/sigmoid scalings, l2_normalize, cross products, concat order,
+# svd, diag, the Euler stacks, casts and matmuls -- is the reference's own code.
+class DenseQueue:
+    """Stand-in for ``tf.layers.dense``: returns ``activation(next queued pre-activation)``; layers whose width is
+    not a head width (the hidden NF*4 layers) return zeros."""
+
+    def __init__(self, head_widths, preacts):
+        self.head_widths = set(int(w) for w in head_widths)
+        self.preacts = list(preacts)
+        self.calls = []
+
+    def __call__(self, x, units, activation=None, name=None):
+        rows = x.shape[0]
+        units = int(units)
+        if units in self.head_widths:
+            p = self.preacts.pop(0)
+            assert tuple(p.shape) == (rows, units), (tuple(p.shape), rows, units)
+            self.calls.append(units)
+            return activation(p) if activation is not None else p
+        return torch.zeros(rows, units, dtype=torch.float32)
+
+
+def _svd(a, full_matrices=False, compute_uv=True, name=None):
+    U, S, Vh = torch.linalg.svd(a, full_matrices=full_matrices)
+    return S, U, Vh.transpose(-1, -2)          # TensorFlow's order: s, u, v
+
+
+def make_tf_geometry(dense: DenseQueue) -> types.SimpleNamespace:
+    from .reference_port import l2_normalize
+    tf = make_tf()
+    tf.layers = types.SimpleNamespace(dense=dense)
+    tf.nn = types.SimpleNamespace(tanh=torch.tanh, sigmoid=torch.sigmoid,
+                                  leaky_relu=lambda t: torch.nn.functional.leaky_relu(t, 0.2))
+    tf.math = types.SimpleNamespace(l2_normalize=lambda x, axis=-1, name=None: l2_normalize(x))
+    tf.linalg.cross = lambda a, b, name=None: torch.linalg.cross(a, b, dim=-1)
+    tf.linalg.diag = lambda d, name=None: torch.diag_embed(d)
+    tf.linalg.svd = _svd
+    tf.concat = lambda values, axis, name=None: torch.cat(list(values), dim=axis)
+    tf.sqrt = torch.sqrt
+    tf.squeeze = lambda t, axis=None, name=None: t.squeeze(tuple(axis) if isinstance(axis, (list, tuple)) else axis)
+    tf.get_variable = lambda name, shape=None, dtype=None, trainable=True, initializer=None: torch.ones(
+        [int(v) for v in shape], dtype=dtype)
+    tf.ones_initializer = None
+    tf.variable_scope = _name_scope
+    return tf
+
+
+def load_reference_methods(path: str, class_name: str, names: Iterable[str], nb_landmarks: int, dense: DenseQueue,
+                           NF: int = 64) -> Dict[str, object]:
+    """Compile the named methods of class ``class_name`` in reference file ``path`` as plain functions (decorators
+    dropped, ``self`` kept as the first parameter) against the geometry shim."""
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name]
+    if len(cls) != 1:
+        raise KeyError(f"{path}: class {class_name} not found exactly once")
+    wanted = set(names)
+    picked = [n for n in cls[0].body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    if {n.name for n in picked} != wanted:
+        raise KeyError(f"{path}: missing methods {sorted(wanted - {n.name for n in picked})}")
+    for n in picked:
+        n.decorator_list = []
+    mod = ast.Module(body=picked, type_ignores=[])
+    ns: Dict[str, object] = {"tf": make_tf_geometry(dense), "np": np, "nb_landmarks": int(nb_landmarks), "NF": int(NF),
+                             "argscope": _name_scope, "Conv2D": None, "Conv2DTranspose": None, "INLReLU": None}
+    exec(compile(mod, path, "exec"), ns)  # noqa: S102 -- executing the read-only reference, on purpose
+    return {n: ns[n] for n in wanted}

@@ -96,6 +96,33 @@ def raster_case(name, B, K, n, seed):
     print(name, tuple(g.shape))
 
 
+def geometry_case(name, B, K, seed):
+    """Rows a6 / a7: Model.get_musigma and Model.transform_mu_sigma executed as they stand (oracle/tf_shim.py feeds
+    pre-drawn head pre-activations through ``tf.layers.dense``); outputs and autograd gradients w.r.t. the
+    pre-activations are stored."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    pre_c = [rn(1, K * 3) for _ in range(4)]                                   # mus, v0, v1, u heads (call order)
+    pre_d = [rn(B, K * 3), rn(B, K * 3), rn(B, K), rn(B, K), rn(B, K), rn(B, 1)]   # mu_t, Sscale, rx, ry, rz, theta
+    lc = [p.clone().requires_grad_(True) for p in pre_c]
+    ld = [p.clone().requires_grad_(True) for p in pre_d]
+    path = os.path.join(REF, "mask/mask_gen_dynamic.py")
+    f1 = tf_shim.load_reference_methods(path, "Model", ["get_musigma"], K, tf_shim.DenseQueue([K * 3], lc))
+    cmu, csig = f1["get_musigma"](None)
+    f2 = tf_shim.load_reference_methods(path, "Model", ["transform_mu_sigma"], K, tf_shim.DenseQueue([K * 3, K, 1], ld))
+    mus, sigmas, theta = f2["transform_mu_sigma"](None, torch.zeros(B, 1, 1, 8), cmu, csig)
+    w = _weights([mus.shape, sigmas.shape, theta.shape], seed + 2)
+    ((mus * w[0]).sum() + (sigmas * w[1].double()).sum() + (theta * w[2]).sum()).backward()
+    out = {f"pre_c{i}": p.numpy() for i, p in enumerate(pre_c)}
+    out.update({f"pre_d{i}": p.numpy() for i, p in enumerate(pre_d)})
+    out.update(cannmu=cmu.detach().numpy(), cannsigma=csig.detach().numpy(), mus=mus.detach().numpy(),
+               sigmas=sigmas.detach().numpy(), theta=theta.detach().numpy(), wseed=np.int64(seed + 2))
+    out.update({f"grad_c{i}": p.grad.numpy() for i, p in enumerate(lc)})
+    out.update({f"grad_d{i}": p.grad.numpy() for i, p in enumerate(ld)})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (build container only)")
@@ -106,3 +133,4 @@ if __name__ == "__main__":
     train_case("train_k16", B=3, K=16, seed=11, angle=30.0, rxz_scale=0.0, t=(0.0, 0.0, -2.0), focal=1.0)
     infer_case("infer_k6", B=2, K=6, seed=56)
     raster_case("raster_k8", B=2, K=8, n=48, seed=21)
+    geometry_case("geometry_k8", B=3, K=8, seed=31)

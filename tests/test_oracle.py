@@ -183,3 +183,53 @@ def test_consumers():
     rgb = rp.colorize_landmark_maps(maps, colors)
     assert rgb.shape == (2, 8, 8, 3)
     assert torch.allclose(rgb[0, 3, 4], (maps[0, 3, 4, :, None] * colors).max(0).values)
+
+
+# ---------------------------------------------------------------------------- geometry tails (rows a6 / a7)
+def _geometry_port(g):
+    """The oracle port on the golden's head pre-activations; gradients w.r.t. the pre-activations by autograd."""
+    K = g["cannmu"].shape[1]
+    lc = [torch.from_numpy(g[f"pre_c{i}"]).clone().requires_grad_(True) for i in range(4)]
+    ld = [torch.from_numpy(g[f"pre_d{i}"]).clone().requires_grad_(True) for i in range(6)]
+    cmu = torch.tanh(lc[0]).reshape(1, K, 1, 3)                                    # mask/mask_gen_dynamic.py:378-379
+    csig = rp.sigma_from_frame(torch.tanh(lc[1]).reshape(1, K, 3), torch.tanh(lc[2]).reshape(1, K, 3), lc[3].reshape(1, K, 3))
+    t = [torch.tanh(p) for p in ld]
+    mus, sigmas, theta = rp.deform(t[0], t[1], t[2], t[3], t[4], t[5], cmu, csig)
+    return lc, ld, cmu, csig, mus, sigmas, theta
+
+
+def test_geometry_port_matches_reference_source_golden():
+    """sigma_from_frame + deform against Model.get_musigma / Model.transform_mu_sigma EXECUTED from the reference
+    source (tests/golden/make_golden.py: geometry_case)."""
+    g = load("geometry_k8")
+    lc, ld, cmu, csig, mus, sigmas, theta = _geometry_port(g)
+    assert torch.equal(cmu.detach(), torch.from_numpy(g["cannmu"])) and torch.equal(csig.detach(), torch.from_numpy(g["cannsigma"]))
+    assert torch.equal(mus.detach(), torch.from_numpy(g["mus"])) and torch.equal(theta.detach(), torch.from_numpy(g["theta"]))
+    assert_close_norm(sigmas, g["sigmas"], 1e-14, "sigmas")
+    w = weights_like([mus.shape, sigmas.shape, theta.shape], g["wseed"])
+    ((mus * w[0]).sum() + (sigmas * w[1].double()).sum() + (theta * w[2]).sum()).backward()
+    for i, p in enumerate(lc):
+        assert_close_norm(p.grad, g[f"grad_c{i}"], 1e-6, f"grad_c{i}")          # float32 head chain
+    for i, p in enumerate(ld):
+        assert_close_norm(p.grad, g[f"grad_d{i}"], 1e-6, f"grad_d{i}")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_geometry_port_matches_reference_source_live():
+    from oracle import tf_shim
+    K, B = 5, 4
+    gen = torch.Generator().manual_seed(77)
+    rn = lambda *s: torch.randn(*s, generator=gen)
+    pre_c = [rn(1, K * 3) for _ in range(4)]
+    pre_d = [rn(B, K * 3), rn(B, K * 3), rn(B, K), rn(B, K), rn(B, K), rn(B, 1)]
+    path = os.path.join(REF, "mask/mask_gen_dynamic.py")
+    f1 = tf_shim.load_reference_methods(path, "Model", ["get_musigma"], K, tf_shim.DenseQueue([K * 3], [p.clone() for p in pre_c]))
+    cmu, csig = f1["get_musigma"](None)
+    f2 = tf_shim.load_reference_methods(path, "Model", ["transform_mu_sigma"], K,
+                                        tf_shim.DenseQueue([K * 3, K, 1], [p.clone() for p in pre_d]))
+    mus, sigmas, theta = f2["transform_mu_sigma"](None, torch.zeros(B, 1, 1, 8), cmu, csig)
+    pc = rp.sigma_from_frame(torch.tanh(pre_c[1]).reshape(1, K, 3), torch.tanh(pre_c[2]).reshape(1, K, 3), pre_c[3].reshape(1, K, 3))
+    t = [torch.tanh(p) for p in pre_d]
+    pm, ps, pt = rp.deform(t[0], t[1], t[2], t[3], t[4], t[5], torch.tanh(pre_c[0]).reshape(1, K, 1, 3), pc)
+    assert torch.equal(pc, csig) and torch.equal(pm, mus) and torch.equal(pt, theta)
+    assert_close_norm(ps, sigmas, 1e-14, "sigmas")

@@ -945,3 +945,29 @@ def test_bit_packed_binary_targets_equal_uint8_targets(gg, cuda_device, n):
     torch.cuda.synchronize()
     assert hb.h2d_bytes < hu.h2d_bytes and ru.loss == rb.loss
     assert torch.equal(ru.dmus, rb.dmus) and torch.equal(ru.dsigma, rb.dsigma) and torch.equal(ru.drot, rb.drot)
+
+
+def test_geometry_kernels_vs_reference_source_golden(gg, cuda_device):
+    """sigma_from_frame, the 3x3 SVD kernel and deform (CUDA) against Model.get_musigma / Model.transform_mu_sigma
+    executed from the reference source (tests/golden/geometry_k8.npz), outputs and gradients w.r.t. the head
+    pre-activations."""
+    g = load("geometry_k8")
+    K = g["cannmu"].shape[1]
+    B = g["mus"].shape[0]
+    lc = [torch.from_numpy(g[f"pre_c{i}"]).to(cuda_device).requires_grad_(True) for i in range(4)]
+    ld = [torch.from_numpy(g[f"pre_d{i}"]).to(cuda_device).requires_grad_(True) for i in range(6)]
+    cmu = torch.tanh(lc[0]).reshape(1, K, 1, 3)
+    csig = gg.sigma_from_frame(torch.tanh(lc[1]).reshape(1, K, 3), torch.tanh(lc[2]).reshape(1, K, 3), lc[3].reshape(1, K, 3))
+    t = [torch.tanh(p) for p in ld]
+    mus, sigmas, theta = gg.deform(t[0], t[1], t[2], t[3], t[4], t[5], cmu, csig)
+    # float32 construction (:400) on top of tanh evaluated by torch on the GPU (1-2 ulp from the CPU's): ulp-level freedom
+    assert_close_norm(csig, g["cannsigma"], 1e-6, "cannsigma")
+    assert_close_norm(mus, g["mus"], 1e-6, "mus")
+    assert_close_norm(theta, g["theta"], 1e-6, "theta")
+    assert_close_norm(sigmas, g["sigmas"], 5e-6, "sigmas")
+    w = weights_like([mus.shape, sigmas.shape, theta.shape], g["wseed"])
+    ((mus * w[0].to(cuda_device)).sum() + (sigmas * w[1].double().to(cuda_device)).sum() + (theta * w[2].to(cuda_device)).sum()).backward()
+    for i, p in enumerate(lc):
+        assert_close_norm(p.grad, g[f"grad_c{i}"], GRAD_RTOL, f"grad_c{i}")
+    for i, p in enumerate(ld):
+        assert_close_norm(p.grad, g[f"grad_d{i}"], GRAD_RTOL, f"grad_d{i}")

@@ -7,7 +7,7 @@ it yields the reference's gradients.  Every function cites the reference
 
 PARITY UNPINNED against a running TensorFlow 1.12 (not installable here); pinned
 against the reference's own source executed through ``oracle/tf_shim.py`` (see
-``tests/golden/make_golden.py`` and ``tests/test_oracle_pinning.py``).
+``tests/golden/make_golden.py`` and ``tests/test_oracle.py``).
 
 Not imported by ``gaussigan_b200``; see ``oracle/__init__.py``.
 """

@@ -14,7 +14,7 @@ pure tensor algebra that use ~25 ``tf.*`` names.  This module
 
 The reference source is read from ``/root/reference`` at call time and is never
 copied into this repository.  Used by ``tests/golden/make_golden.py`` to create
-the committed golden vectors and by ``tests/test_oracle_pinning.py`` (skipped
+the committed golden vectors and by ``tests/test_oracle.py`` (skipped
 when ``/root/reference`` is absent, e.g. on the GPU box).
 
 What this pins and what it does not: op ORDER, transposes, gather indices,

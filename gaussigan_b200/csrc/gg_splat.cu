@@ -581,6 +581,8 @@ void make_strip_desc(ScaleDesc &d, int n, int rpt) { strip_geometry(d, n, rpt); 
 int fast_cta(bool backward, int rpt);
 cudaError_t launch_splat_bwd_quad_tma(const SplatArgs &a, int B, int kq_shift, bool any_mask, cudaStream_t st);
 bool splat_bwd_quad_tma_ok(const SplatArgs &a, int kq_shift);
+cudaError_t launch_splat_bwd_quad_fast(const SplatArgs &a, int B, int kq_shift, bool any_mask, cudaStream_t st);
+bool splat_bwd_quad_fast_ok(const SplatArgs &a);
 cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st);
 cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st);
 
@@ -762,7 +764,11 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
       // the quad kernel adds gmask to every channel only when a scale carries one; scales without a
       // gmask are handled by giving the kernel a per-scale NULL check
       static const bool use_tma = env_int("GG_TMA_BWD", 1) != 0;
-      if (use_tma && splat_bwd_quad_tma_ok(a, pl.kq_shift)) {
+      // forward-differenced strips (same switch as the silhouette kernels); direct form otherwise
+      static const bool use_fast = env_int("GG_FAST_MAPS_BWD", 1) != 0;
+      if (use_tma && use_fast && fast_mask() && splat_bwd_quad_fast_ok(a)) {
+        err = launch_splat_bwd_quad_fast(a, B, pl.kq_shift, pl.maps_any_mask, st);
+      } else if (use_tma && splat_bwd_quad_tma_ok(a, pl.kq_shift)) {
         err = launch_splat_bwd_quad_tma(a, B, pl.kq_shift, pl.maps_any_mask, st);
       } else {
         if (pl.maps_any_mask) launch_pdl(splat_bwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);

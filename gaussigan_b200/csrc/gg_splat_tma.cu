@@ -9,6 +9,7 @@
 // compute threads read their quad with one LDS.128.
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
+#include "gg_fast.cuh"
 #include "gg_launch.h"
 
 namespace gg {
@@ -206,6 +207,355 @@ __global__ void __launch_bounds__(kThreads, GG_TMA_MINBLOCKS) splat_bwd_quad_tma
     for (int w = 0; w < kWarps; ++w) acc += wsum[w][c];
     out[c] = acc;
   }
+}
+
+// =============================================================== forward-differenced NHWC maps backward
+// Same contract again, a quarter of the exponentials and half the issue slots: thread = (strip of 8 consecutive
+// pixels of a row, quad of 4 consecutive Gaussians).  Along the strip each Gaussian follows the recurrence of
+// gg_splat_fast.cu (g_{j+1} = g_j r_j, r_{j+1} = r_j c: two exponentials per strip instead of eight); the two lanes
+// of every FP32x2 register are two GAUSSIANS of the quad, which is how the 128-bit gradient quads arrive, so nothing
+// is repacked.
+//
+// A warp slice is 32 >> kq_shift strips = 4 KB of contiguous upstream gradient, one bulk copy; strips of a slice may
+// lie in different rows (n % 8 == 0 keeps a strip inside one row), so any n that is a multiple of 8 works, including
+// the 32 x 32 scale of the pyramid.  Bank conflicts: the 8 lanes of an LDS.128 phase are 8/KQ strips x KQ quads
+// reading the same pixel index j, and strips are 128 KQ bytes apart -- the same banks.  For KQ <= 4 odd strips
+// therefore run the recurrence BACKWARDS (from pixel 7, step -h: only the sign of one constant changes): at step i
+// even strips read pixel i, odd strips pixel 7 - i, which differ in parity, i.e. in the 64-byte half of the bank
+// window (conflict-free at K = 16; KQ >= 8 is conflict-free as it is).
+//
+// The kernel is PERSISTENT: every CTA (2 per SM) takes a contiguous range of the launch's (image, tile) items; a
+// warp's ring keeps running across items, the accumulators across the tiles of an image -- one reduction and one
+// partial-sum slot per (CTA, image), the slots of its other tiles are zero-filled -- and the per-Gaussian constants
+// are re-staged only where the image or the scale changes (double-buffered, staged one segment ahead).
+constexpr int kFastStageBytes = 4096;
+constexpr int kFastStages = 2;             // ring depth per warp (3 measured the same, 4 halves the resident CTAs)
+
+// One strip (8 pixels) of one quad of Gaussians by the recurrence, per lane pair p (lanes = two Gaussians):
+//   A = sum u_j,  Bs = sum (8 - j) u_j,  Cs = sum (8 - j)(9 - j)/2 u_j,   u_j = g_j Gbar_j
+// as running sums (A += u; Bs += A; Cs += Bs: three two-operand adds per pixel, no per-pixel coordinates in
+// registers).  They are the strip's moments about the point one step past its last pixel, on a uniform grid -- the
+// same assumption the recurrence itself makes, and the guard (|nA| <= 512, i.e. sigma >= 4.8 pixels at n = 256)
+// keeps the 1.8e-7 non-uniformity of the reference's float32 grid below 5e-6 of any first moment.
+// sp = the quad of the strip's first pixel in the order of traversal, dstride = +-KQ float4 per step.
+template <bool WITH_GMASK>
+__device__ __forceinline__ void strip_sums_recurrence(const float4 *sp, int dstride, const float (&gm)[8],
+                                                      f32x2 (&gg)[2], f32x2 (&rr)[2], const f32x2 (&cc)[2],
+                                                      f32x2 (&A)[2], f32x2 (&Bs)[2], f32x2 (&Cs)[2]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 G4 = sp[j * dstride];
+    f32x2 G[2] = {pack2(G4.x, G4.y), pack2(G4.z, G4.w)};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (WITH_GMASK) G[p] = add2(G[p], bc(gm[j]));
+      const f32x2 u = mul2(gg[p], G[p]);
+      if (j == 0) {
+        A[p] = Bs[p] = Cs[p] = u;
+      } else {
+        A[p] = add2(A[p], u);
+        Bs[p] = add2(Bs[p], A[p]);
+        Cs[p] = add2(Cs[p], Bs[p]);
+      }
+      if (j < 7) {
+        gg[p] = mul2(gg[p], rr[p]);
+        if (j < 6) rr[p] = mul2(rr[p], cc[p]);
+      }
+    }
+  }
+}
+
+// The same strip with one exponential per pixel on the reference's own float32 grid (quads that contain a narrow or
+// very distant Gaussian): S0 = sum u, S1 = sum u xi, S2 = sum u xi^2 about the strip's first pixel, xi_j = x_j - x_0
+// (exact), t_j = x_j - (mu_x + nr dy) formed exactly as the direct kernels do; nsh = -(mu_x + nr dy).
+template <bool WITH_GMASK>
+__device__ __forceinline__ void strip_sums_direct(const float4 *sp, int dstride, const float (&gm)[8], int cstart,
+                                                  int dir, float h, float x0, const f32x2 (&nA)[2],
+                                                  const f32x2 (&e)[2], const f32x2 (&nsh)[2], f32x2 (&S0)[2],
+                                                  f32x2 (&S1)[2], f32x2 (&S2)[2]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 G4 = sp[j * dstride];
+    f32x2 G[2] = {pack2(G4.x, G4.y), pack2(G4.z, G4.w)};
+    const float xj = grid_coord(cstart + dir * j, h);
+    const f32x2 xi = bc(xj - x0);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (WITH_GMASK) G[p] = add2(G[p], bc(gm[j]));
+      const f32x2 t = add2(bc(xj), nsh[p]);
+      const f32x2 u = mul2(ex2_2(fma2(nA[p], mul2(t, t), e[p])), G[p]);
+      const f32x2 v = mul2(u, xi);
+      S0[p] = j == 0 ? u : add2(S0[p], u);
+      S1[p] = j == 0 ? v : add2(S1[p], v);
+      S2[p] = j == 0 ? mul2(v, xi) : fma2(v, xi, S2[p]);
+    }
+  }
+}
+
+struct FastItem {            // what a warp needs to stream one (image, tile) item
+  const float *gtile;        // the tile's contiguous span of upstream gradients
+  int nstrips;               // 8-pixel strips in the tile
+  int my_slices;             // slices of this warp: warp, warp + 8, ...
+};
+
+__device__ __forceinline__ FastItem fast_item(const SplatArgs &a, int work, int warp, int spw) {
+  const int b = work / a.T, tile = work - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+  const int row_end = min(s.n, row_begin + s.rows_per_tile);
+  FastItem it;
+  it.gtile = s.maps + ((size_t)b * s.n + row_begin) * s.n * a.K;
+  it.nstrips = (row_end - row_begin) * (s.n >> 3);
+  const int nslices = (it.nstrips + spw - 1) / spw;
+  it.my_slices = nslices > warp ? (nslices - warp + kWarps - 1) / kWarps : 0;
+  return it;
+}
+
+// constants of one (image, scale) segment; the guard is evaluated over the whole image
+__device__ __forceinline__ void stage_segment_consts(const SplatArgs &a, int work, float4 *sc) {
+  const int b = work / a.T, tile = work - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const float lo = grid_coord(0, s.step), hi = grid_coord(s.n - 1, s.step);
+  stage_fast_consts(a.params + (size_t)b * a.K * GG_PARAM_STRIDE, a.K, s.step, lo, hi, lo, hi, sc);
+}
+
+// dynamic shared memory: [2][K][3] float4 constants | [kWarps][K][5] float warp sums | [kWarps][kFastStages] stages
+__host__ __device__ inline size_t fast_consts_bytes(int K) { return (((size_t)2 * K * 48) + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t fast_wsum_bytes(int K) {
+  return (((size_t)kWarps * K * GG_MOMENTS * 4) + 127) & ~(size_t)127;
+}
+
+template <bool WITH_GMASK>
+__global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const __grid_constant__ SplatArgs a,
+                                                                          int kq_shift, int nwork) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ __align__(8) uint64_t full[kWarps][kFastStages];
+
+  const int K = a.K;
+  const int KQ = 1 << kq_shift;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kq = lane & (KQ - 1);            // this thread's quad of Gaussians (fixed for the whole kernel)
+  const int sl = lane >> kq_shift;           // its strip inside a warp slice
+  const int spw = 32 >> kq_shift;            // strips per warp slice
+  const int chunk_bytes = 128 << kq_shift;   // one strip: 8 pixels x K floats
+  const bool flip = KQ <= 4 && (sl & 1);     // odd strips run from pixel 7 down to pixel 0
+  const int dir = flip ? -1 : 1;
+  float4 *sc_base = reinterpret_cast<float4 *>(dyn);
+  float *wsum = reinterpret_cast<float *>(dyn + fast_consts_bytes(K));
+  unsigned char *wring = dyn + fast_consts_bytes(K) + fast_wsum_bytes(K) + (size_t)warp * kFastStages * kFastStageBytes;
+  // this thread's first quad inside a stage, in its order of traversal
+  const unsigned sp_off = (unsigned)((((sl * 8 + (flip ? 7 : 0)) << kq_shift) + kq) * 16);
+  const int w_begin = (int)((long long)blockIdx.x * nwork / gridDim.x);
+  const int w_end = (int)((long long)(blockIdx.x + 1) * nwork / gridDim.x);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kFastStages; ++i) mbar_init(&full[warp][i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_enter();   // global memory is first touched below
+  __syncwarp();
+
+  // ---- issue cursor: runs kFastStages slices ahead of the consume cursor, across item boundaries
+  int iss_work = w_begin, iss_idx = 0, iss_stage = 0;
+  FastItem iss = {nullptr, 0, 0};
+  if (iss_work < w_end) iss = fast_item(a, iss_work, warp, spw);
+  auto issue_next = [&]() {
+    while (iss_work < w_end && iss_idx >= iss.my_slices) {
+      ++iss_work;
+      iss_idx = 0;
+      if (iss_work < w_end) iss = fast_item(a, iss_work, warp, spw);
+    }
+    if (iss_work >= w_end) return;
+    if (lane == 0) {
+      const int first = (warp + iss_idx * kWarps) * spw;
+      const unsigned bytes = (unsigned)(min(spw, iss.nstrips - first) * chunk_bytes);
+      mbar_expect_tx(&full[warp][iss_stage], bytes);
+      bulk_g2s(wring + (size_t)iss_stage * kFastStageBytes, iss.gtile + (size_t)first * 8 * K, bytes,
+               &full[warp][iss_stage]);
+    }
+    ++iss_idx;
+    iss_stage = iss_stage + 1 == kFastStages ? 0 : iss_stage + 1;
+  };
+#pragma unroll
+  for (int i = 0; i < kFastStages; ++i) issue_next();
+
+  if (w_begin < w_end) stage_segment_consts(a, w_begin, sc_base);
+
+  f32x2 mux[2], muy[2], nA[2], nnr[2], nE[2], rb[2], rc[2], cc[2];   // this thread's four Gaussians, two lane pairs
+  bool steep = false;
+  f32x2 T[2][GG_MOMENTS];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int j = 0; j < GG_MOMENTS; ++j) T[p][j] = pack2(0.f, 0.f);
+  int stage = 0;             // ring position and barrier phase of the consume cursor
+  unsigned phase = 0;
+  int seg_par = 0, prev_b = -1, prev_si = -1;
+
+  for (int work = w_begin; work < w_end; ++work) {
+    const int b = work / a.T, tile = work - b * a.T;
+    const int si = find_scale(a, tile);
+    const ScaleDesc &s = a.sc[si];
+    const int n = s.n;
+    const float h = s.step;
+    if (b != prev_b || si != prev_si) {   // new (image, scale) segment: its constants were staged one segment ago
+      prev_b = b; prev_si = si;
+      __syncthreads();
+      const float4 *sc = sc_base + (size_t)seg_par * 3 * K;
+      steep = false;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int k = 4 * kq + 2 * p;
+        const float4 u0 = sc[3 * k], u1 = sc[3 * k + 1], v0 = sc[3 * k + 3], v1 = sc[3 * k + 4];
+        mux[p] = pack2(u0.x, v0.x); muy[p] = pack2(u0.y, v0.y); nA[p] = pack2(u0.z, v0.z); nnr[p] = pack2(u0.w, v0.w);
+        nE[p] = pack2(u1.x, v1.x); rc[p] = pack2(u1.z, v1.z); cc[p] = pack2(u1.w, v1.w);
+        rb[p] = flip ? pack2(-u1.y, -v1.y) : pack2(u1.y, v1.y);      // 2 nA h, with h -> -h on reversed strips
+        steep = steep || sc[3 * k + 2].x != 0.f || sc[3 * k + 5].x != 0.f;
+      }
+      seg_par ^= 1;
+      const int next_seg = b * a.T + s.tile_begin + s.tiles;        // first item of the next (image, scale)
+      if (next_seg < w_end) stage_segment_consts(a, next_seg, sc_base + (size_t)seg_par * 3 * K);
+    }
+    const bool flush = work == w_end - 1 || (work + 1) / a.T != b;   // last item of this image in this CTA's range
+    float *out = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K) * GG_MOMENTS;
+    if (!flush)
+      for (int c = threadIdx.x; c < K * GG_MOMENTS; c += kThreads) out[c] = 0.f;
+
+    const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+    const int strips_per_row = n >> 3;
+    const FastItem cur = fast_item(a, work, warp, spw);
+    const bool use_gmask = WITH_GMASK && s.mask != nullptr;
+    const float hs = flip ? -h : h;                // signed step of this thread's traversal
+    const f32x2 h8 = bc(8.0f * hs), nhs = bc(-hs), hh = bc(h * h);
+    int g = warp * spw + sl;                       // strip index inside the tile
+    int rrel = g / strips_per_row;
+    int cs = g - rrel * strips_per_row;            // strip index inside its row
+    for (int i = 0; i < cur.my_slices; ++i) {
+      const bool valid = g < cur.nstrips;
+      const int col0 = valid ? cs * 8 : 0;
+      const int row = row_begin + (valid ? rrel : 0);
+      const int cstart = flip ? col0 + 7 : col0;
+      const float x0 = grid_coord(cstart, h);
+      float gm[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gm[j] = 0.f;
+      if (use_gmask && valid) {
+        const float4 *mp = reinterpret_cast<const float4 *>(s.mask + ((size_t)b * n + row) * n + col0);
+        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+        const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gm[j] = flip ? mm[7 - j] : mm[j];
+      }
+      const f32x2 y2 = bc(grid_coord(row, h)), x02 = bc(x0);
+      f32x2 dy[2], tr[2], e[2], gg[2], rr[2], M0[2], M1[2], M2[2];   // tr = t at the moments' reference point
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        dy[p] = sub2(y2, muy[p]);
+        tr[p] = fma2(nnr[p], dy[p], sub2(x02, mux[p]));
+        e[p] = mul2(mul2(nE[p], dy[p]), dy[p]);
+        gg[p] = ex2_2(fma2(mul2(nA[p], tr[p]), tr[p], e[p]));
+        rr[p] = ex2_2(fma2(rb[p], tr[p], rc[p]));
+        M0[p] = M1[p] = M2[p] = pack2(0.f, 0.f);
+      }
+      mbar_wait(&full[warp][stage], phase);
+      if (valid) {
+        const float4 *sp = reinterpret_cast<const float4 *>(wring + (size_t)stage * kFastStageBytes + sp_off);
+        if (!steep) {
+          f32x2 Bs[2], Cs[2];
+          strip_sums_recurrence<WITH_GMASK>(sp, dir * KQ, gm, gg, rr, cc, M0, Bs, Cs);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {   // moments about the point one step past the strip: xi_j = -(8 - j) hs
+            tr[p] = add2(tr[p], h8);
+            M1[p] = mul2(Bs[p], nhs);
+            M2[p] = mul2(sub2(add2(Cs[p], Cs[p]), Bs[p]), hh);
+          }
+        } else {
+          f32x2 nsh[2];
+#pragma unroll
+          for (int p = 0; p < 2; ++p) nsh[p] = fma2(nnr[p], dy[p], sub2(bc(0.f), mux[p]));
+          strip_sums_direct<WITH_GMASK>(sp, dir * KQ, gm, cstart, dir, h, x0, nA, e, nsh, M0, M1, M2);
+        }
+      }
+      __syncwarp();                                    // every lane is done with the stage
+      issue_next();
+      // strip-local moments (about the reference point) -> moments of t = tr + xi, then the row weights
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const f32x2 m1 = fma2(tr[p], M0[p], M1[p]);
+        const f32x2 m2 = fma2(tr[p], add2(M1[p], m1), M2[p]);
+        const f32x2 d0 = mul2(dy[p], M0[p]);
+        T[p][0] = add2(T[p][0], m2);
+        T[p][3] = add2(T[p][3], m1);
+        T[p][1] = fma2(dy[p], m1, T[p][1]);
+        T[p][4] = add2(T[p][4], d0);
+        T[p][2] = fma2(dy[p], d0, T[p][2]);
+      }
+      g += kWarps * spw;
+      cs += kWarps * spw;
+      while (cs >= strips_per_row) { cs -= strips_per_row; ++rrel; }
+      if (++stage == kFastStages) { stage = 0; phase ^= 1u; }
+    }
+    if (flush) {
+      // lanes that share kq (stride KQ) -> butterfly; then lanes 0..KQ-1 hold the warp totals [k][moment]
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int j = 0; j < GG_MOMENTS; ++j) {
+          float lo, hi;
+          unpack2(T[p][j], lo, hi);
+          for (int off = KQ; off < 32; off <<= 1) {
+            lo += __shfl_xor_sync(0xffffffffu, lo, off);
+            hi += __shfl_xor_sync(0xffffffffu, hi, off);
+          }
+          if (lane < KQ) {
+            wsum[((size_t)warp * K + 4 * kq + 2 * p) * GG_MOMENTS + j] = lo;
+            wsum[((size_t)warp * K + 4 * kq + 2 * p + 1) * GG_MOMENTS + j] = hi;
+          }
+          T[p][j] = pack2(0.f, 0.f);
+        }
+      __syncthreads();
+      for (int c = threadIdx.x; c < K * GG_MOMENTS; c += kThreads) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) acc += wsum[(size_t)w * K * GG_MOMENTS + c];
+        out[c] = acc;
+      }
+    }
+  }
+}
+
+bool splat_bwd_quad_fast_ok(const SplatArgs &a) {
+  for (int i = 0; i < a.nscales; ++i)
+    if ((a.sc[i].n & 7) != 0) return false;
+  return true;
+}
+
+cudaError_t launch_splat_bwd_quad_fast(const SplatArgs &a, int B, int kq_shift, bool any_mask, cudaStream_t st) {
+  static int sm_count[64] = {};
+  const size_t smem = fast_consts_bytes(a.K) + fast_wsum_bytes(a.K) + (size_t)kWarps * kFastStages * kFastStageBytes;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &sms = sm_count[dev & 63];
+  if (sms == 0) {   // first launch on this device
+    const int max_smem = (int)(fast_consts_bytes(128) + fast_wsum_bytes(128) + (size_t)kWarps * kFastStages * kFastStageBytes);
+    cudaError_t e = cudaFuncSetAttribute(splat_bwd_quad_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         max_smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(splat_bwd_quad_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    int count = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    sms = count;
+  }
+  const size_t nwork = (size_t)B * a.T;
+  if (nwork == 0) return cudaSuccess;
+  if (nwork > 0x7fffffffu) return cudaErrorInvalidValue;
+  // persistent: 2 CTAs per SM (registers and shared memory both allow exactly two)
+  const unsigned grid = (unsigned)(nwork < (size_t)2 * sms ? nwork : (size_t)2 * sms);
+  if (any_mask) launch_pdl(splat_bwd_quad_fast_kernel<true>, dim3(grid), dim3(kThreads), smem, st, a, kq_shift, (int)nwork);
+  else launch_pdl(splat_bwd_quad_fast_kernel<false>, dim3(grid), dim3(kThreads), smem, st, a, kq_shift, (int)nwork);
+  return cudaGetLastError();
 }
 
 // shapes the bulk-copy kernel handles: every warp slice (128 quads) inside one row

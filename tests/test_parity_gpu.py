@@ -813,6 +813,39 @@ def test_randomised_shapes_and_scales_fast_mask_path(gg, cuda_device, restore_mo
     print(f"worst forward {worst_f:.2e}, worst gradient {worst_g:.2e}")
 
 
+@pytest.mark.parametrize("K,sizes,B", [
+    (16, (32, 64, 128, 256), 3), (4, (8, 24), 2), (8, (40, 64), 2), (32, (48,), 2), (64, (72, 16), 1), (128, (32,), 1),
+])
+def test_nhwc_maps_backward_forward_differenced_vs_oracle_and_direct(gg, cuda_device, restore_modes, K, sizes, B):
+    """NHWC maps + silhouette gradients through the forward-differenced bulk-copy kernel (gg_splat_tma.cu; any K whose
+    quads are a power of two, any n that is a multiple of 8, strips of one warp slice in different rows at small n,
+    partial last slices) against the oracle's autograd, and against the direct kernels (gg.set_fast_mask(False))."""
+    inp = rp.synth_inputs(B, K, seed=700 + K, angle=45.0)
+    # one needle narrower than a pixel at the finest scale (the kernel's direct fall-back for its quad) and one blob
+    # far outside the frame
+    inp["sigma"][0, 0] = torch.diag(torch.tensor([3e-4, 0.2, 0.05], dtype=torch.float64))
+    inp["mus"][0, K - 1, 0] = torch.tensor([2.5, -0.3, 0.1])
+    lv = _leaves(inp)
+    ref = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0, 0, -2., sizes=sizes)
+    w = weights_like([r.shape for r in ref], 31)
+    wm = weights_like([(B, sizes[-1], sizes[-1], 1)], 32)[0]
+    (sum((r * q).sum() for r, q in zip(ref, w)) + (ref[-1].sum(-1, keepdim=True) * wm).sum()).backward()
+
+    def run(fast):
+        gg.set_fast_mask(fast)
+        dv = _leaves(inp, cuda_device)
+        out, mask = gg.get_landmarks_with_mask(dv["mus"], dv["sigma"], dv["rotx"], dv["roty"], dv["rotz"], 0, 0, -2.,
+                                               sizes=sizes)
+        (sum((o * q.to(cuda_device)).sum() for o, q in zip(out, w)) + (mask * wm.to(cuda_device)).sum()).backward()
+        return {k: dv[k].grad for k in ("mus", "sigma", "rotx", "roty", "rotz")}
+
+    fast, direct = run(True), run(False)
+    for k in fast:
+        assert_close_norm(fast[k], lv[k].grad, GRAD_RTOL, f"K={K} grad {k} (forward-differenced)")
+        assert_close_norm(direct[k], lv[k].grad, GRAD_RTOL, f"K={K} grad {k} (direct)")
+        assert_close_norm(fast[k], direct[k], GRAD_RTOL, f"K={K} grad {k} fast vs direct")
+
+
 def test_second_device_in_the_same_process(gg, cuda_device):
     """Tensors on cuda:1 while cuda:0 is PyTorch's current device (and the other way round): the library follows the
     tensors' device on every call.  Needs two GPUs."""

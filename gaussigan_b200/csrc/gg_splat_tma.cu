@@ -52,6 +52,33 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                : "memory");
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void *src, unsigned bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 }  // namespace
 
 // One ring PER WARP: a warp streams its own 128-quad (2 KB) slices of the tile, its lane 0 issues the bulk copies and
@@ -229,7 +256,10 @@ __global__ void __launch_bounds__(kThreads, GG_TMA_MINBLOCKS) splat_bwd_quad_tma
 // partial-sum slot per (CTA, image), the slots of its other tiles are zero-filled -- and the per-Gaussian constants
 // are re-staged only where the image or the scale changes (double-buffered, staged one segment ahead).
 constexpr int kFastStageBytes = 4096;
-constexpr int kFastStages = 2;             // ring depth per warp (3 measured the same, 4 halves the resident CTAs)
+#ifndef GG_FAST_STAGES
+#define GG_FAST_STAGES 2
+#endif
+constexpr int kFastStages = GG_FAST_STAGES;             // ring depth per warp (3 measured the same, 4 halves the resident CTAs)
 
 // One strip (8 pixels) of one quad of Gaussians by the recurrence, per lane pair p (lanes = two Gaussians):
 //   A = sum u_j,  Bs = sum (8 - j) u_j,  Cs = sum (8 - j)(9 - j)/2 u_j,   u_j = g_j Gbar_j
@@ -237,14 +267,14 @@ constexpr int kFastStages = 2;             // ring depth per warp (3 measured th
 // registers).  They are the strip's moments about the point one step past its last pixel, on a uniform grid -- the
 // same assumption the recurrence itself makes, and the guard (|nA| <= 512, i.e. sigma >= 4.8 pixels at n = 256)
 // keeps the 1.8e-7 non-uniformity of the reference's float32 grid below 5e-6 of any first moment.
-// sp = the quad of the strip's first pixel in the order of traversal, dstride = +-KQ float4 per step.
+// sp = shared address of the quad of the strip's first pixel in the order of traversal, dstride = +-16 KQ bytes.
 template <bool WITH_GMASK>
-__device__ __forceinline__ void strip_sums_recurrence(const float4 *sp, int dstride, const float (&gm)[8],
+__device__ __forceinline__ void strip_sums_recurrence(uint32_t sp, int dstride, const float (&gm)[8],
                                                       f32x2 (&gg)[2], f32x2 (&rr)[2], const f32x2 (&cc)[2],
                                                       f32x2 (&A)[2], f32x2 (&Bs)[2], f32x2 (&Cs)[2]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 G4 = sp[j * dstride];
+    const float4 G4 = lds128(sp + (uint32_t)(j * dstride));
     f32x2 G[2] = {pack2(G4.x, G4.y), pack2(G4.z, G4.w)};
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -269,13 +299,13 @@ __device__ __forceinline__ void strip_sums_recurrence(const float4 *sp, int dstr
 // very distant Gaussian): S0 = sum u, S1 = sum u xi, S2 = sum u xi^2 about the strip's first pixel, xi_j = x_j - x_0
 // (exact), t_j = x_j - (mu_x + nr dy) formed exactly as the direct kernels do; nsh = -(mu_x + nr dy).
 template <bool WITH_GMASK>
-__device__ __forceinline__ void strip_sums_direct(const float4 *sp, int dstride, const float (&gm)[8], int cstart,
+__device__ __forceinline__ void strip_sums_direct(uint32_t sp, int dstride, const float (&gm)[8], int cstart,
                                                   int dir, float h, float x0, const f32x2 (&nA)[2],
                                                   const f32x2 (&e)[2], const f32x2 (&nsh)[2], f32x2 (&S0)[2],
                                                   f32x2 (&S1)[2], f32x2 (&S2)[2]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 G4 = sp[j * dstride];
+    const float4 G4 = lds128(sp + (uint32_t)(j * dstride));
     f32x2 G[2] = {pack2(G4.x, G4.y), pack2(G4.z, G4.w)};
     const float xj = grid_coord(cstart + dir * j, h);
     const f32x2 xi = bc(xj - x0);
@@ -292,34 +322,30 @@ __device__ __forceinline__ void strip_sums_direct(const float4 *sp, int dstride,
   }
 }
 
-struct FastItem {            // what a warp needs to stream one (image, tile) item
-  const float *gtile;        // the tile's contiguous span of upstream gradients
+// the tile of item (b, tile): its contiguous span of upstream gradients and its size
+struct FastTile {
+  const float *gtile;
+  int row_begin;
   int nstrips;               // 8-pixel strips in the tile
-  int my_slices;             // slices of this warp: warp, warp + 8, ...
 };
 
-__device__ __forceinline__ FastItem fast_item(const SplatArgs &a, int work, int warp, int spw) {
-  const int b = work / a.T, tile = work - b * a.T;
-  const ScaleDesc &s = a.sc[find_scale(a, tile)];
-  const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
-  const int row_end = min(s.n, row_begin + s.rows_per_tile);
-  FastItem it;
-  it.gtile = s.maps + ((size_t)b * s.n + row_begin) * s.n * a.K;
-  it.nstrips = (row_end - row_begin) * (s.n >> 3);
-  const int nslices = (it.nstrips + spw - 1) / spw;
-  it.my_slices = nslices > warp ? (nslices - warp + kWarps - 1) / kWarps : 0;
-  return it;
+__device__ __forceinline__ FastTile fast_tile(const SplatArgs &a, const ScaleDesc &s, int b, int tile) {
+  FastTile t;
+  t.row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+  const int row_end = min(s.n, t.row_begin + s.rows_per_tile);
+  t.gtile = s.maps + ((size_t)b * s.n + t.row_begin) * s.n * a.K;
+  t.nstrips = (row_end - t.row_begin) * (s.n >> 3);
+  return t;
 }
 
 // constants of one (image, scale) segment; the guard is evaluated over the whole image
-__device__ __forceinline__ void stage_segment_consts(const SplatArgs &a, int work, float4 *sc) {
-  const int b = work / a.T, tile = work - b * a.T;
-  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+__device__ __forceinline__ void stage_segment_consts(const SplatArgs &a, const ScaleDesc &s, int b, float *sc) {
   const float lo = grid_coord(0, s.step), hi = grid_coord(s.n - 1, s.step);
-  stage_fast_consts(a.params + (size_t)b * a.K * GG_PARAM_STRIDE, a.K, s.step, lo, hi, lo, hi, sc);
+  stage_fast_consts_paired(a.params + (size_t)b * a.K * GG_PARAM_STRIDE, a.K, s.step, lo, hi, lo, hi, sc);
 }
 
-// dynamic shared memory: [2][K][3] float4 constants | [kWarps][K][5] float warp sums | [kWarps][kFastStages] stages
+// dynamic shared memory: [2][9 K] float constants (pair-interleaved, gg_fast.cuh) | [kWarps][K][5] float warp sums |
+// [kWarps][kFastStages] stages
 __host__ __device__ inline size_t fast_consts_bytes(int K) { return (((size_t)2 * K * 48) + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t fast_wsum_bytes(int K) {
   return (((size_t)kWarps * K * GG_MOMENTS * 4) + 127) & ~(size_t)127;
@@ -337,14 +363,18 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
   const int kq = lane & (KQ - 1);            // this thread's quad of Gaussians (fixed for the whole kernel)
   const int sl = lane >> kq_shift;           // its strip inside a warp slice
   const int spw = 32 >> kq_shift;            // strips per warp slice
-  const int chunk_bytes = 128 << kq_shift;   // one strip: 8 pixels x K floats
+  const int chunk_shift = 7 + kq_shift;      // one strip: 8 pixels x K floats = 128 KQ bytes
   const bool flip = KQ <= 4 && (sl & 1);     // odd strips run from pixel 7 down to pixel 0
   const int dir = flip ? -1 : 1;
-  float4 *sc_base = reinterpret_cast<float4 *>(dyn);
+  float *sc_base = reinterpret_cast<float *>(dyn);     // two buffers of 12 K floats (9 K used)
   float *wsum = reinterpret_cast<float *>(dyn + fast_consts_bytes(K));
-  unsigned char *wring = dyn + fast_consts_bytes(K) + fast_wsum_bytes(K) + (size_t)warp * kFastStages * kFastStageBytes;
-  // this thread's first quad inside a stage, in its order of traversal
-  const unsigned sp_off = (unsigned)((((sl * 8 + (flip ? 7 : 0)) << kq_shift) + kq) * 16);
+  // 32-bit shared addresses of this warp's ring and barriers, and of this thread's first quad inside a stage (in
+  // its order of traversal); pinned so that they are not re-derived inside the loop
+  const uint32_t ring_u32 = pin_u32(smem_u32(dyn + fast_consts_bytes(K) + fast_wsum_bytes(K)) +
+                                    (uint32_t)(warp * kFastStages * kFastStageBytes));
+  const uint32_t bar_u32 = pin_u32(smem_u32(&full[warp][0]));
+  const uint32_t sp_u32 = pin_u32(ring_u32 + (uint32_t)((((sl * 8 + (flip ? 7 : 0)) << kq_shift) + kq) * 16));
+  const int dstride = dir * (16 << kq_shift);
   const int w_begin = (int)((long long)blockIdx.x * nwork / gridDim.x);
   const int w_end = (int)((long long)(blockIdx.x + 1) * nwork / gridDim.x);
 
@@ -356,31 +386,39 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
   pdl_enter();   // global memory is first touched below
   __syncwarp();
 
-  // ---- issue cursor: runs kFastStages slices ahead of the consume cursor, across item boundaries
-  int iss_work = w_begin, iss_idx = 0, iss_stage = 0;
-  FastItem iss = {nullptr, 0, 0};
-  if (iss_work < w_end) iss = fast_item(a, iss_work, warp, spw);
+  // ---- issue cursor: runs kFastStages slices ahead of the consume cursor, across item boundaries.  Byte offsets
+  // inside the item's tile: this warp's slices start at warp * 4 KB and are 8 * 4 KB apart.
+  int iss_b = w_begin / a.T, iss_tile = w_begin - iss_b * a.T, iss_left = w_end - w_begin;
+  int iss_off = warp * kFastStageBytes, iss_total = 0, iss_stage = 0;
+  const char *iss_src = nullptr;
+  auto iss_open = [&]() {   // the tile of item (iss_b, iss_tile)
+    const FastTile t = fast_tile(a, a.sc[find_scale(a, iss_tile)], iss_b, iss_tile);
+    iss_src = reinterpret_cast<const char *>(t.gtile);
+    iss_total = t.nstrips << chunk_shift;
+    iss_off = warp * kFastStageBytes;
+  };
+  if (iss_left > 0) iss_open();
   auto issue_next = [&]() {
-    while (iss_work < w_end && iss_idx >= iss.my_slices) {
-      ++iss_work;
-      iss_idx = 0;
-      if (iss_work < w_end) iss = fast_item(a, iss_work, warp, spw);
+    while (iss_left > 0 && iss_off >= iss_total) {
+      --iss_left;
+      if (++iss_tile == a.T) { iss_tile = 0; ++iss_b; }
+      if (iss_left > 0) iss_open();
     }
-    if (iss_work >= w_end) return;
+    if (iss_left <= 0) return;
     if (lane == 0) {
-      const int first = (warp + iss_idx * kWarps) * spw;
-      const unsigned bytes = (unsigned)(min(spw, iss.nstrips - first) * chunk_bytes);
-      mbar_expect_tx(&full[warp][iss_stage], bytes);
-      bulk_g2s(wring + (size_t)iss_stage * kFastStageBytes, iss.gtile + (size_t)first * 8 * K, bytes,
-               &full[warp][iss_stage]);
+      const unsigned bytes = (unsigned)min(kFastStageBytes, iss_total - iss_off);
+      const uint32_t bar = bar_u32 + (uint32_t)iss_stage * 8u;
+      mbar_expect_tx_u32(bar, bytes);
+      bulk_g2s_u32(ring_u32 + (uint32_t)iss_stage * kFastStageBytes, iss_src + iss_off, bytes, bar);
     }
-    ++iss_idx;
+    iss_off += kWarps * kFastStageBytes;
     iss_stage = iss_stage + 1 == kFastStages ? 0 : iss_stage + 1;
   };
 #pragma unroll
   for (int i = 0; i < kFastStages; ++i) issue_next();
 
-  if (w_begin < w_end) stage_segment_consts(a, w_begin, sc_base);
+  int b = w_begin / a.T, tile = w_begin - b * a.T;
+  if (w_begin < w_end) stage_segment_consts(a, a.sc[find_scale(a, tile)], b, sc_base);
 
   f32x2 mux[2], muy[2], nA[2], nnr[2], nE[2], rb[2], rc[2], cc[2];   // this thread's four Gaussians, two lane pairs
   bool steep = false;
@@ -394,7 +432,6 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
   int seg_par = 0, prev_b = -1, prev_si = -1;
 
   for (int work = w_begin; work < w_end; ++work) {
-    const int b = work / a.T, tile = work - b * a.T;
     const int si = find_scale(a, tile);
     const ScaleDesc &s = a.sc[si];
     const int n = s.n;
@@ -402,39 +439,44 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
     if (b != prev_b || si != prev_si) {   // new (image, scale) segment: its constants were staged one segment ago
       prev_b = b; prev_si = si;
       __syncthreads();
-      const float4 *sc = sc_base + (size_t)seg_par * 3 * K;
+      const float *sc = sc_base + (size_t)seg_par * 12 * K;
       steep = false;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
-        const int k = 4 * kq + 2 * p;
-        const float4 u0 = sc[3 * k], u1 = sc[3 * k + 1], v0 = sc[3 * k + 3], v1 = sc[3 * k + 4];
-        mux[p] = pack2(u0.x, v0.x); muy[p] = pack2(u0.y, v0.y); nA[p] = pack2(u0.z, v0.z); nnr[p] = pack2(u0.w, v0.w);
-        nE[p] = pack2(u1.x, v1.x); rc[p] = pack2(u1.z, v1.z); cc[p] = pack2(u1.w, v1.w);
-        rb[p] = flip ? pack2(-u1.y, -v1.y) : pack2(u1.y, v1.y);      // 2 nA h, with h -> -h on reversed strips
-        steep = steep || sc[3 * k + 2].x != 0.f || sc[3 * k + 5].x != 0.f;
+        // lane pair p = Gaussians 4 kq + 2 p, + 1: four LDS.128 whose 64-bit halves are the packed constants
+        const float4 *q4 = reinterpret_cast<const float4 *>(sc + (2 * kq + p) * 16);
+        const float4 w0 = q4[0], w1 = q4[1], w2 = q4[2], w3 = q4[3];
+        mux[p] = pack2(w0.x, w0.y); muy[p] = pack2(w0.z, w0.w); nA[p] = pack2(w1.x, w1.y); nnr[p] = pack2(w1.z, w1.w);
+        nE[p] = pack2(w2.x, w2.y); rc[p] = pack2(w3.x, w3.y); cc[p] = pack2(w3.z, w3.w);
+        rb[p] = mul2(pack2(w2.z, w2.w), bc(flip ? -1.f : 1.f));     // 2 nA h, with h -> -h on reversed strips
+        steep = steep || sc[8 * K + 4 * kq + 2 * p] != 0.f || sc[8 * K + 4 * kq + 2 * p + 1] != 0.f;
       }
       seg_par ^= 1;
-      const int next_seg = b * a.T + s.tile_begin + s.tiles;        // first item of the next (image, scale)
-      if (next_seg < w_end) stage_segment_consts(a, next_seg, sc_base + (size_t)seg_par * 3 * K);
+      // the next (image, scale) segment of this CTA's range starts right after this scale's tiles
+      int nb = b, ntile = s.tile_begin + s.tiles;
+      if (ntile == a.T) { ntile = 0; ++nb; }
+      if (nb * a.T + ntile < w_end)
+        stage_segment_consts(a, a.sc[find_scale(a, ntile)], nb, sc_base + (size_t)seg_par * 12 * K);
     }
-    const bool flush = work == w_end - 1 || (work + 1) / a.T != b;   // last item of this image in this CTA's range
+    const bool flush = work == w_end - 1 || tile == a.T - 1;   // last item of this image in this CTA's range
     float *out = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K) * GG_MOMENTS;
     if (!flush)
       for (int c = threadIdx.x; c < K * GG_MOMENTS; c += kThreads) out[c] = 0.f;
 
-    const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+    const FastTile cur = fast_tile(a, s, b, tile);
     const int strips_per_row = n >> 3;
-    const FastItem cur = fast_item(a, work, warp, spw);
     const bool use_gmask = WITH_GMASK && s.mask != nullptr;
     const float hs = flip ? -h : h;                // signed step of this thread's traversal
-    const f32x2 h8 = bc(8.0f * hs), nhs = bc(-hs), hh = bc(h * h);
+    const f32x2 h8 = pin2(bc(8.0f * hs)), nhs = pin2(bc(-hs)), hh = pin2(bc(h * h));
+    const int nslices = (cur.nstrips + spw - 1) >> (5 - kq_shift);
+    const int my_slices = nslices > warp ? (nslices - warp + kWarps - 1) / kWarps : 0;   // slices warp, warp+8, ...
     int g = warp * spw + sl;                       // strip index inside the tile
-    int rrel = g / strips_per_row;
-    int cs = g - rrel * strips_per_row;            // strip index inside its row
-    for (int i = 0; i < cur.my_slices; ++i) {
+    int rrel = 0, cs = g;                          // its row inside the tile and its position inside the row
+    while (cs >= strips_per_row) { cs -= strips_per_row; ++rrel; }
+    for (int i = 0; i < my_slices; ++i) {
       const bool valid = g < cur.nstrips;
       const int col0 = valid ? cs * 8 : 0;
-      const int row = row_begin + (valid ? rrel : 0);
+      const int row = cur.row_begin + (valid ? rrel : 0);
       const int cstart = flip ? col0 + 7 : col0;
       const float x0 = grid_coord(cstart, h);
       float gm[8];
@@ -456,26 +498,26 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
         e[p] = mul2(mul2(nE[p], dy[p]), dy[p]);
         gg[p] = ex2_2(fma2(mul2(nA[p], tr[p]), tr[p], e[p]));
         rr[p] = ex2_2(fma2(rb[p], tr[p], rc[p]));
-        M0[p] = M1[p] = M2[p] = pack2(0.f, 0.f);
       }
-      mbar_wait(&full[warp][stage], phase);
-      if (valid) {
-        const float4 *sp = reinterpret_cast<const float4 *>(wring + (size_t)stage * kFastStageBytes + sp_off);
-        if (!steep) {
-          f32x2 Bs[2], Cs[2];
-          strip_sums_recurrence<WITH_GMASK>(sp, dir * KQ, gm, gg, rr, cc, M0, Bs, Cs);
+      mbar_wait_u32(bar_u32 + (uint32_t)stage * 8u, phase);
+      const uint32_t sp = sp_u32 + (uint32_t)stage * kFastStageBytes;
+      if (!valid) {
 #pragma unroll
-          for (int p = 0; p < 2; ++p) {   // moments about the point one step past the strip: xi_j = -(8 - j) hs
-            tr[p] = add2(tr[p], h8);
-            M1[p] = mul2(Bs[p], nhs);
-            M2[p] = mul2(sub2(add2(Cs[p], Cs[p]), Bs[p]), hh);
-          }
-        } else {
-          f32x2 nsh[2];
+        for (int p = 0; p < 2; ++p) M0[p] = M1[p] = M2[p] = pack2(0.f, 0.f);
+      } else if (!steep) {
+        f32x2 Bs[2], Cs[2];
+        strip_sums_recurrence<WITH_GMASK>(sp, dstride, gm, gg, rr, cc, M0, Bs, Cs);
 #pragma unroll
-          for (int p = 0; p < 2; ++p) nsh[p] = fma2(nnr[p], dy[p], sub2(bc(0.f), mux[p]));
-          strip_sums_direct<WITH_GMASK>(sp, dir * KQ, gm, cstart, dir, h, x0, nA, e, nsh, M0, M1, M2);
+        for (int p = 0; p < 2; ++p) {   // moments about the point one step past the strip: xi_j = -(8 - j) hs
+          tr[p] = add2(tr[p], h8);
+          M1[p] = mul2(Bs[p], nhs);
+          M2[p] = mul2(sub2(add2(Cs[p], Cs[p]), Bs[p]), hh);
         }
+      } else {
+        f32x2 nsh[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) nsh[p] = fma2(nnr[p], dy[p], sub2(bc(0.f), mux[p]));
+        strip_sums_direct<WITH_GMASK>(sp, dstride, gm, cstart, dir, h, x0, nA, e, nsh, M0, M1, M2);
       }
       __syncwarp();                                    // every lane is done with the stage
       issue_next();
@@ -522,6 +564,7 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
         out[c] = acc;
       }
     }
+    if (++tile == a.T) { tile = 0; ++b; }
   }
 }
 

@@ -1,4 +1,4 @@
-"""CUDA-event timing of the NHWC maps backward (gg_splat_bwd with upstream gradients of the K-channel maps),
+"""CUDA-event timing of the NHWC maps backward and forward (gg_splat_bwd with upstream gradients of the K-channel maps),
 single scale and pyramid (development tool; not a bench line)."""
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -37,4 +37,13 @@ e0.record()
 for i in range(a.reps): run(i)
 e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / a.reps * 1e3
-print(f"B={B} K={K} sizes={sizes} T={T}: {us:.1f} us = {byts/us*1e6/1e9:.0f} GB/s ({byts/1e6:.0f} MB per launch)")
+print(f"B={B} K={K} sizes={sizes} T={T}: bwd {us:.1f} us = {byts/us*1e6/1e9:.0f} GB/s ({byts/1e6:.0f} MB per launch)")
+# forward into the same buffers
+def runf(i): check(lib.gg_splat_fwd(params.data_ptr(), B, K, ns, sz, gps[i % a.sets], nul, LAYOUT_NHWC, 0, st()), 'f')
+for i in range(3): runf(i)
+torch.cuda.synchronize()
+e0.record()
+for i in range(a.reps): runf(i)
+e1.record(); torch.cuda.synchronize()
+us = e0.elapsed_time(e1) / a.reps * 1e3
+print(f"B={B} K={K} sizes={sizes}: fwd {us:.1f} us = {byts/us*1e6/1e9:.0f} GB/s")

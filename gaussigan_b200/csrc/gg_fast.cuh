@@ -71,18 +71,20 @@ __device__ __forceinline__ void stage_fast_consts(const float *__restrict__ gpar
 
 // The same constants interleaved for kernels whose FP32x2 lanes are two consecutive GAUSSIANS (gg_splat_tma.cu):
 // word w of Gaussian k goes to float index (k / 2) * 16 + 2 w + (k & 1) (w = 0..3: c0, 4..7: c1), so a lane pair is
-// loaded as aligned 64-bit halves of four LDS.128; the steep flags follow at float index 8 kn + k.
+// loaded as aligned 64-bit halves of four LDS.128; the steep flags follow at float index 8 Kp + k, Kp = kn rounded
+// up to even.  For odd kn the missing partner of the last Gaussian gets all-zero constants (g = 1, finite).
 __device__ __forceinline__ void stage_fast_consts_paired(const float *__restrict__ gparams, int kn, float h, float x_lo,
                                                          float x_hi, float y_lo, float y_hi, float *sc) {
   const float4 *gp = reinterpret_cast<const float4 *>(gparams);
-  for (int k = threadIdx.x; k < kn; k += blockDim.x) {
-    float4 c0, c1;
-    bool steep;
-    fast_consts_one(gp, k, h, x_lo, x_hi, y_lo, y_hi, c0, c1, steep);
+  const int Kp = (kn + 1) & ~1;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+    bool steep = false;
+    if (k < kn) fast_consts_one(gp, k, h, x_lo, x_hi, y_lo, y_hi, c0, c1, steep);
     float *d = sc + (k >> 1) * 16 + (k & 1);
     d[0] = c0.x; d[2] = c0.y; d[4] = c0.z; d[6] = c0.w;
     d[8] = c1.x; d[10] = c1.y; d[12] = c1.z; d[14] = c1.w;
-    sc[8 * kn + k] = steep ? 1.f : 0.f;
+    sc[8 * Kp + k] = steep ? 1.f : 0.f;
   }
 }
 

@@ -412,6 +412,107 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quad_kernel(const __grid_c
   }
 }
 
+// ====================================================================== forward, quads, any K % 4 == 0
+// The quad kernel without the power-of-two restriction (the reference's K = 12): the first (256 / KQ) KQ threads of
+// the CTA are used, so that a thread keeps its quad of Gaussians (constants in registers) from pass to pass and
+// consecutive threads still write consecutive 16-byte chunks.  No fused silhouette: the lanes of a pixel do not form
+// an aligned group of a warp; the launcher gives the silhouette to the mask kernel.
+__global__ void __launch_bounds__(kThreads) splat_fwd_quadg_kernel(const __grid_constant__ SplatArgs a, int KQ) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
+  const int b = blockIdx.x / a.T;
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+  const int cpp = kThreads / KQ;                    // pixels per pass
+  const int c0 = threadIdx.x / KQ, kq = threadIdx.x - c0 * KQ;
+  if (c0 >= cpp) return;
+
+  float mux[4], muy[4], nA[4], nr[4], nE[4];
+  {
+    const float4 *gp = reinterpret_cast<const float4 *>(a.params + ((size_t)b * K + 4 * kq) * GG_PARAM_STRIDE);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 lo = __ldg(gp + 2 * i), hi = __ldg(gp + 2 * i + 1);
+      mux[i] = lo.x; muy[i] = lo.y; nA[i] = lo.z; nr[i] = lo.w; nE[i] = hi.x;
+    }
+  }
+  const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+  const int row_end = min(n, row_begin + s.rows_per_tile);
+  for (int row = row_begin; row < row_end; ++row) {
+    const float y = grid_coord(row, s.step);
+    float sh[4], e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float dy = y - muy[i];
+      sh[i] = fmaf(nr[i], dy, mux[i]);
+      e[i] = (nE[i] * dy) * dy;
+    }
+    float *mrow = s.maps + ((size_t)b * n + row) * n * K + 4 * kq;
+    for (int col = c0; col < n; col += cpp) {
+      const float x = grid_coord(col, s.step);
+      float g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float t = x - sh[i];
+        g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+      }
+      st_f4(mrow + (size_t)col * K, g[0], g[1], g[2], g[3]);
+    }
+  }
+}
+
+// ================================================================================= forward, flat
+// NHWC maps for ANY K with n K % 4 == 0 (the reference's own K = 6 and 12 among them).  A row of the output is n K
+// consecutive floats; thread = 4 of them = one 128-bit store, whichever (pixel, Gaussian) pairs they belong to.
+// The row-dependent part of every Gaussian (sh = mu_x + nr dy, e = nE dy^2) is staged once per tile in shared
+// memory, so an element costs one LDS.128, four FP32 instructions and one exponential, as in the quad kernel --
+// same arithmetic, bit-identical values.
+__global__ void __launch_bounds__(kThreads) splat_fwd_flat_kernel(const __grid_constant__ SplatArgs a, float inv_k) {
+  extern __shared__ float4 rowc[];   // [rows of the tile][K]: sh, e, nA, -
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
+  const int b = blockIdx.x / a.T;
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+  const float h = s.step;
+  const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+  const int rows = min(n, row_begin + s.rows_per_tile) - row_begin;
+  const float4 *gp = reinterpret_cast<const float4 *>(a.params + (size_t)b * K * GG_PARAM_STRIDE);
+  for (int idx = threadIdx.x; idx < rows * K; idx += kThreads) {
+    const int r = idx / K, k = idx - r * K;
+    const float4 lo = __ldg(gp + 2 * k);
+    const float nE = __ldg(reinterpret_cast<const float *>(gp + 2 * k + 1));
+    const float dy = grid_coord(row_begin + r, h) - lo.y;
+    rowc[idx] = make_float4(fmaf(lo.w, dy, lo.x), (nE * dy) * dy, lo.z, 0.f);
+  }
+  __syncthreads();
+  const int vpr = (n * K) >> 2;                       // 128-bit vectors per row
+  const float inv_vpr = 1.0f / (float)vpr;
+  float *mtile = s.maps + ((size_t)b * n + row_begin) * n * K;
+  for (int idx = threadIdx.x; idx < rows * vpr; idx += kThreads) {
+    // r = idx / vpr and p = f / K by float reciprocal (exact for operands < 2^22, which the launcher checks), with
+    // a correction step for the last-bit cases
+    int r = __float2int_rd(((float)idx + 0.5f) * inv_vpr);
+    int q = idx - r * vpr;
+    if (q < 0) { q += vpr; --r; } else if (q >= vpr) { q -= vpr; ++r; }
+    const int f = 4 * q;
+    int p = __float2int_rd(((float)f + 0.5f) * inv_k);
+    int k = f - p * K;
+    if (k < 0) { k += K; --p; } else if (k >= K) { k -= K; ++p; }
+    const float4 *rc = rowc + r * K;
+    float x = grid_coord(p, h);
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float4 c = rc[k];
+      const float t = x - c.x;
+      g[e] = ex2_approx(fmaf(c.z * t, t, c.y));
+      if (++k == K) { k = 0; ++p; x = grid_coord(p, h); }
+    }
+    st_f4(mtile + (size_t)r * n * K + f, g[0], g[1], g[2], g[3]);
+  }
+}
+
 // =============================================================================== backward, quads
 template <bool WITH_GMASK>
 __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_kernel(const __grid_constant__ SplatArgs a,
@@ -477,7 +578,9 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_kernel(const __gri
 #pragma unroll
       for (int u = 0; u < kUQ; ++u) {
         const int qq = q0 + u * kThreads;
-        const float x = grid_coord(qq >> kq_shift, s.step);
+        // column clamped for the quads past the row's end (their G is 0, but a conic that is not positive definite
+        // -- a blob at the camera plane -- grows away from its centre and inf * 0 would poison the sums)
+        const float x = grid_coord(min(qq >> kq_shift, n - 1), s.step);
         const f32x2 x2 = pack2(x, x);
         const f32x2 gm2 = pack2(gmv[u], gmv[u]);
         const f32x2 Ga = add2(pack2(G[u].x, G[u].y), gm2), Gb = add2(pack2(G[u].z, G[u].w), gm2);
@@ -581,8 +684,8 @@ void make_strip_desc(ScaleDesc &d, int n, int rpt) { strip_geometry(d, n, rpt); 
 int fast_cta(bool backward, int rpt);
 cudaError_t launch_splat_bwd_quad_tma(const SplatArgs &a, int B, int kq_shift, bool any_mask, cudaStream_t st);
 bool splat_bwd_quad_tma_ok(const SplatArgs &a, int kq_shift);
-cudaError_t launch_splat_bwd_quad_fast(const SplatArgs &a, int B, int kq_shift, bool any_mask, cudaStream_t st);
-bool splat_bwd_quad_fast_ok(const SplatArgs &a);
+cudaError_t launch_splat_bwd_nhwc_fast(const SplatArgs &a, int B, bool any_mask, cudaStream_t st);
+bool splat_bwd_nhwc_fast_ok(int K, int nscales, const int *sizes);
 cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st);
 cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st);
 
@@ -614,11 +717,32 @@ int quad_passes(bool backward) {
   return backward ? b : f;
 }
 
+// forward-differenced NHWC maps backward (gg_splat_tma.cu): same switch as the silhouette kernels, GG_FAST_MAPS_BWD=0
+// keeps the direct kernels
+static bool fast_maps_bwd() {
+  static const bool env_on = env_int("GG_FAST_MAPS_BWD", 1) != 0 && env_int("GG_TMA_BWD", 1) != 0;
+  return env_on && fast_mask();
+}
+
+// flat forward kernel: 128-bit stores need whole vectors per row, the index arithmetic operands below 2^22, and the
+// per-tile constants have to fit the default dynamic shared memory
+static bool flat_fwd_ok(int K, int nscales, const int *sizes, const bool *has_maps) {
+  for (int i = 0; i < nscales; ++i) {
+    if (!has_maps[i]) continue;
+    const long long nk = (long long)sizes[i] * K;
+    if ((nk & 3) != 0 || nk >= (1 << 22)) return false;
+  }
+  return (size_t)16 * K * sizeof(float4) <= 48 * 1024;
+}
+
 // A launch plan: which scales go to which kernel family, with tile numbering.
+enum MapsKind { MAPS_STRIP = 0, MAPS_QUAD, MAPS_FLAT };
 struct Plan {
-  SplatArgs strip_mask;    // scales with only a mask (or gmask)
-  SplatArgs maps;          // scales with maps (quad or strip kernel), mask fused
-  bool maps_quad;
+  SplatArgs strip_mask;    // scales with only a mask (or gmask); forward MAPS_FLAT: also the masks of map scales
+  SplatArgs maps;          // scales with maps, mask fused (except forward MAPS_FLAT)
+  int maps_kind;           // MAPS_QUAD: NHWC, K = 4 * 2^i (quad kernels); MAPS_FLAT: NHWC, any other K that the
+                           // flat forward / forward-differenced backward handle; MAPS_STRIP: everything else
+  bool maps_fast_bwd;      // backward of the maps through splat_bwd_nhwc_fast_kernel
   int kq_shift;
   bool maps_any_mask;
   int tiles_mask, tiles_maps;
@@ -628,23 +752,37 @@ static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool
                       int layout, bool backward) {
   pl = Plan();
   pl.kq_shift = 0;
-  pl.maps_quad = (layout == GG_LAYOUT_NHWC) && quad_ok(K, &pl.kq_shift);
+  int map_sizes[GG_MAX_SCALES], nmaps = 0;
+  for (int i = 0; i < nscales; ++i)
+    if (has_maps[i]) map_sizes[nmaps++] = sizes[i];
+  pl.maps_kind = MAPS_STRIP;
+  if (layout == GG_LAYOUT_NHWC && nmaps > 0) {
+    pl.maps_fast_bwd = backward && fast_maps_bwd() && splat_bwd_nhwc_fast_ok(K, nmaps, map_sizes);
+    if (quad_ok(K, &pl.kq_shift)) pl.maps_kind = MAPS_QUAD;
+    else if (backward ? pl.maps_fast_bwd : flat_fwd_ok(K, nscales, sizes, has_maps)) pl.maps_kind = MAPS_FLAT;
+  }
   int rpt = backward ? bwd_rpt() : fwd_rpt();
   int tb_mask = 0, tb_maps = 0;
+  auto add_mask_scale = [&](int n) {
+    ScaleDesc &d = pl.strip_mask.sc[pl.strip_mask.nscales++];
+    if (fast_mask()) strip_geometry(d, n, rpt >= 4 ? 4 : 2, true, fast_cta(backward, rpt));   // row pairs
+    else strip_geometry(d, n, rpt);
+    d.tile_begin = tb_mask;
+    tb_mask += d.tiles;
+  };
   for (int i = 0; i < nscales; ++i) {
     if (has_maps[i]) {
       ScaleDesc &d = pl.maps.sc[pl.maps.nscales++];
-      if (pl.maps_quad) quad_geometry(d, sizes[i], K >> 2, quad_passes(backward));
+      if (pl.maps_kind != MAPS_STRIP) quad_geometry(d, sizes[i], (K + 3) >> 2, quad_passes(backward));
       else strip_geometry(d, sizes[i], rpt);
       d.tile_begin = tb_maps;
       tb_maps += d.tiles;
-      if (has_mask[i]) pl.maps_any_mask = true;
+      if (has_mask[i]) {
+        if (pl.maps_kind == MAPS_FLAT && !backward) add_mask_scale(sizes[i]);   // silhouette by its own kernel
+        else pl.maps_any_mask = true;
+      }
     } else if (has_mask[i]) {
-      ScaleDesc &d = pl.strip_mask.sc[pl.strip_mask.nscales++];
-      if (fast_mask()) strip_geometry(d, sizes[i], rpt >= 4 ? 4 : 2, true, fast_cta(backward, rpt));   // row pairs
-      else strip_geometry(d, sizes[i], rpt);
-      d.tile_begin = tb_mask;
-      tb_mask += d.tiles;
+      add_mask_scale(sizes[i]);
     }
   }
   pl.tiles_mask = tb_mask;
@@ -692,8 +830,9 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
   make_plan(pl, K, nscales, sizes, hm, hk, layout, false);
   int im = 0, ik = 0;
   for (int i = 0; i < nscales; ++i) {
-    if (hm[i]) { pl.maps.sc[im].maps = maps[i]; pl.maps.sc[im].mask = hk[i] ? masks[i] : nullptr; ++im; }
-    else if (hk[i]) { pl.strip_mask.sc[ik].maps = nullptr; pl.strip_mask.sc[ik].mask = masks[i]; ++ik; }
+    const bool own_mask_kernel = hm[i] && hk[i] && pl.maps_kind == MAPS_FLAT;
+    if (hm[i]) { pl.maps.sc[im].maps = maps[i]; pl.maps.sc[im].mask = hk[i] && !own_mask_kernel ? masks[i] : nullptr; ++im; }
+    if (hk[i] && (!hm[i] || own_mask_kernel)) { pl.strip_mask.sc[ik].maps = nullptr; pl.strip_mask.sc[ik].mask = masks[i]; ++ik; }
   }
   cudaError_t err = cudaSuccess;
   const int rpt = fwd_rpt();
@@ -708,10 +847,19 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
   if (pl.maps.nscales) {
     SplatArgs &a = pl.maps;
     a.params = params; a.B = B; a.K = K; a.T = pl.tiles_maps; a.layout = layout;
-    if (pl.maps_quad) {
+    if (pl.maps_kind == MAPS_QUAD) {
       dim3 grid((unsigned)((size_t)B * a.T));
       if (pl.maps_any_mask) launch_pdl(splat_fwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
       else launch_pdl(splat_fwd_quad_kernel<false>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
+      err = cudaGetLastError();
+    } else if (pl.maps_kind == MAPS_FLAT && (K & 3) == 0 && (K >> 2) <= kThreads) {
+      launch_pdl(splat_fwd_quadg_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 2);
+      err = cudaGetLastError();
+    } else if (pl.maps_kind == MAPS_FLAT) {
+      int max_rows = 1;
+      for (int i = 0; i < a.nscales; ++i) max_rows = a.sc[i].rows_per_tile > max_rows ? a.sc[i].rows_per_tile : max_rows;
+      launch_pdl(splat_fwd_flat_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads),
+                 (size_t)max_rows * K * sizeof(float4), st, a, 1.0f / (float)K);
       err = cudaGetLastError();
     } else {
       int mode = layout == GG_LAYOUT_NCHW ? 1 : 2;
@@ -759,16 +907,14 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
     SplatArgs &a = pl.maps;
     a.params = params; a.partials = partials; a.B = B; a.K = K; a.T = pl.tiles_maps; a.slots = T;
     a.tile_offset = pl.tiles_mask; a.layout = layout;
-    if (pl.maps_quad) {
+    if (pl.maps_fast_bwd) {
+      err = launch_splat_bwd_nhwc_fast(a, B, pl.maps_any_mask, st);
+    } else if (pl.maps_kind == MAPS_QUAD) {
       dim3 grid((unsigned)((size_t)B * a.T));
-      // the quad kernel adds gmask to every channel only when a scale carries one; scales without a
+      // the quad kernels add gmask to every channel only when a scale carries one; scales without a
       // gmask are handled by giving the kernel a per-scale NULL check
       static const bool use_tma = env_int("GG_TMA_BWD", 1) != 0;
-      // forward-differenced strips (same switch as the silhouette kernels); direct form otherwise
-      static const bool use_fast = env_int("GG_FAST_MAPS_BWD", 1) != 0;
-      if (use_tma && use_fast && fast_mask() && splat_bwd_quad_fast_ok(a)) {
-        err = launch_splat_bwd_quad_fast(a, B, pl.kq_shift, pl.maps_any_mask, st);
-      } else if (use_tma && splat_bwd_quad_tma_ok(a, pl.kq_shift)) {
+      if (use_tma && splat_bwd_quad_tma_ok(a, pl.kq_shift)) {
         err = launch_splat_bwd_quad_tma(a, B, pl.kq_shift, pl.maps_any_mask, st);
       } else {
         if (pl.maps_any_mask) launch_pdl(splat_bwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);

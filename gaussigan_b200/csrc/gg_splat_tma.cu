@@ -237,19 +237,20 @@ __global__ void __launch_bounds__(kThreads, GG_TMA_MINBLOCKS) splat_bwd_quad_tma
 }
 
 // =============================================================== forward-differenced NHWC maps backward
-// Same contract again, a quarter of the exponentials and half the issue slots: thread = (strip of 8 consecutive
-// pixels of a row, quad of 4 consecutive Gaussians).  Along the strip each Gaussian follows the recurrence of
-// gg_splat_fast.cu (g_{j+1} = g_j r_j, r_{j+1} = r_j c: two exponentials per strip instead of eight); the two lanes
-// of every FP32x2 register are two GAUSSIANS of the quad, which is how the 128-bit gradient quads arrive, so nothing
-// is repacked.
+// Same contract again for ANY K, a quarter of the exponentials and half the issue slots: thread = (strip of 8
+// consecutive pixels of a row, unit of consecutive Gaussians) -- a unit is a quad (K % 4 == 0: one LDS.128 per
+// pixel, NP = 2 lane pairs) or a pair (any other K, the reference's own K = 6 among them: NP = 1; an odd K leaves
+// the last pair half empty).  Along the strip each Gaussian follows the recurrence of gg_splat_fast.cu
+// (g_{j+1} = g_j r_j, r_{j+1} = r_j c: two exponentials per strip instead of eight); the two lanes of every FP32x2
+// register are two GAUSSIANS of the unit, which is how the gradient arrives, so nothing is repacked.
 //
-// A warp slice is 32 >> kq_shift strips = 4 KB of contiguous upstream gradient, one bulk copy; strips of a slice may
-// lie in different rows (n % 8 == 0 keeps a strip inside one row), so any n that is a multiple of 8 works, including
-// the 32 x 32 scale of the pyramid.  Bank conflicts: the 8 lanes of an LDS.128 phase are 8/KQ strips x KQ quads
-// reading the same pixel index j, and strips are 128 KQ bytes apart -- the same banks.  For KQ <= 4 odd strips
-// therefore run the recurrence BACKWARDS (from pixel 7, step -h: only the sign of one constant changes): at step i
-// even strips read pixel i, odd strips pixel 7 - i, which differ in parity, i.e. in the 64-byte half of the bank
-// window (conflict-free at K = 16; KQ >= 8 is conflict-free as it is).
+// A warp slice is 32 / KU strips (KU = units per pixel) of contiguous upstream gradient, at most 4 KB, one bulk
+// copy; strips of a slice may lie in different rows (n % 8 == 0 keeps a strip inside one row), so any n that is a
+// multiple of 8 works, including the 32 x 32 scale of the pyramid.  Bank conflicts: the 8 lanes of an LDS.128 phase
+// are 8/KQ strips x KQ quads reading the same pixel index j, and strips are 128 KQ bytes apart -- the same banks.
+// For power-of-two KQ <= 4 odd strips therefore run the recurrence BACKWARDS (from pixel 7, step -h: only the sign
+// of one constant changes): at step i even strips read pixel i, odd strips pixel 7 - i, which differ in parity,
+// i.e. in the 64-byte half of the bank window (conflict-free at K = 16; KQ >= 8 is conflict-free as it is).
 //
 // The kernel is PERSISTENT: every CTA (2 per SM) takes a contiguous range of the launch's (image, tile) items; a
 // warp's ring keeps running across items, the accumulators across the tiles of an image -- one reduction and one
@@ -259,25 +260,53 @@ constexpr int kFastStageBytes = 4096;
 #ifndef GG_FAST_STAGES
 #define GG_FAST_STAGES 2
 #endif
-constexpr int kFastStages = GG_FAST_STAGES;             // ring depth per warp (3 measured the same, 4 halves the resident CTAs)
+constexpr int kFastStages = GG_FAST_STAGES;     // ring depth per warp (3 measured slower: fewer bytes per barrier wait)
 
-// One strip (8 pixels) of one quad of Gaussians by the recurrence, per lane pair p (lanes = two Gaussians):
+__device__ __forceinline__ f32x2 lds64(uint32_t addr) {
+  f32x2 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// the unit of one pixel: NP lane pairs.  `kodd` (odd K, NP = 1): pixels are not 8-byte aligned and the partner of
+// the last Gaussian does not exist -- two 32-bit loads, the missing lane multiplied away by vm = (1, 0).
+template <int NP>
+__device__ __forceinline__ void load_unit(uint32_t addr, bool kodd, f32x2 vm, f32x2 (&G)[NP]) {
+  if (NP == 2) {
+    const float4 v = lds128(addr);
+    G[0] = pack2(v.x, v.y);
+    G[NP - 1] = pack2(v.z, v.w);
+  } else if (!kodd) {
+    G[0] = lds64(addr);
+  } else {
+    const float lo = lds32(addr), hi = lds32(addr + 4);
+    G[0] = mul2(pack2(lo, hi), vm);
+  }
+}
+
+// One strip (8 pixels) of one unit of Gaussians by the recurrence, per lane pair p (lanes = two Gaussians):
 //   A = sum u_j,  Bs = sum (8 - j) u_j,  Cs = sum (8 - j)(9 - j)/2 u_j,   u_j = g_j Gbar_j
 // as running sums (A += u; Bs += A; Cs += Bs: three two-operand adds per pixel, no per-pixel coordinates in
 // registers).  They are the strip's moments about the point one step past its last pixel, on a uniform grid -- the
 // same assumption the recurrence itself makes, and the guard (|nA| <= 512, i.e. sigma >= 4.8 pixels at n = 256)
 // keeps the 1.8e-7 non-uniformity of the reference's float32 grid below 5e-6 of any first moment.
-// sp = shared address of the quad of the strip's first pixel in the order of traversal, dstride = +-16 KQ bytes.
-template <bool WITH_GMASK>
-__device__ __forceinline__ void strip_sums_recurrence(uint32_t sp, int dstride, const float (&gm)[8],
-                                                      f32x2 (&gg)[2], f32x2 (&rr)[2], const f32x2 (&cc)[2],
-                                                      f32x2 (&A)[2], f32x2 (&Bs)[2], f32x2 (&Cs)[2]) {
+// sp = shared address of the unit of the strip's first pixel in the order of traversal, dstride = +-4 K bytes.
+template <int NP, bool WITH_GMASK>
+__device__ __forceinline__ void strip_sums_recurrence(uint32_t sp, int dstride, bool kodd, f32x2 vm,
+                                                      const float (&gm)[8], f32x2 (&gg)[NP], f32x2 (&rr)[NP],
+                                                      const f32x2 (&cc)[NP], f32x2 (&A)[NP], f32x2 (&Bs)[NP],
+                                                      f32x2 (&Cs)[NP]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 G4 = lds128(sp + (uint32_t)(j * dstride));
-    f32x2 G[2] = {pack2(G4.x, G4.y), pack2(G4.z, G4.w)};
+    f32x2 G[NP];
+    load_unit<NP>(sp + (uint32_t)(j * dstride), kodd, vm, G);
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < NP; ++p) {
       if (WITH_GMASK) G[p] = add2(G[p], bc(gm[j]));
       const f32x2 u = mul2(gg[p], G[p]);
       if (j == 0) {
@@ -295,22 +324,22 @@ __device__ __forceinline__ void strip_sums_recurrence(uint32_t sp, int dstride, 
   }
 }
 
-// The same strip with one exponential per pixel on the reference's own float32 grid (quads that contain a narrow or
+// The same strip with one exponential per pixel on the reference's own float32 grid (units that contain a narrow or
 // very distant Gaussian): S0 = sum u, S1 = sum u xi, S2 = sum u xi^2 about the strip's first pixel, xi_j = x_j - x_0
 // (exact), t_j = x_j - (mu_x + nr dy) formed exactly as the direct kernels do; nsh = -(mu_x + nr dy).
-template <bool WITH_GMASK>
-__device__ __forceinline__ void strip_sums_direct(uint32_t sp, int dstride, const float (&gm)[8], int cstart,
-                                                  int dir, float h, float x0, const f32x2 (&nA)[2],
-                                                  const f32x2 (&e)[2], const f32x2 (&nsh)[2], f32x2 (&S0)[2],
-                                                  f32x2 (&S1)[2], f32x2 (&S2)[2]) {
+template <int NP, bool WITH_GMASK>
+__device__ __forceinline__ void strip_sums_direct(uint32_t sp, int dstride, bool kodd, f32x2 vm, const float (&gm)[8],
+                                                  int cstart, int dir, float h, float x0, const f32x2 (&nA)[NP],
+                                                  const f32x2 (&e)[NP], const f32x2 (&nsh)[NP], f32x2 (&S0)[NP],
+                                                  f32x2 (&S1)[NP], f32x2 (&S2)[NP]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 G4 = lds128(sp + (uint32_t)(j * dstride));
-    f32x2 G[2] = {pack2(G4.x, G4.y), pack2(G4.z, G4.w)};
+    f32x2 G[NP];
+    load_unit<NP>(sp + (uint32_t)(j * dstride), kodd, vm, G);
     const float xj = grid_coord(cstart + dir * j, h);
     const f32x2 xi = bc(xj - x0);
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < NP; ++p) {
       if (WITH_GMASK) G[p] = add2(G[p], bc(gm[j]));
       const f32x2 t = add2(bc(xj), nsh[p]);
       const f32x2 u = mul2(ex2_2(fma2(nA[p], mul2(t, t), e[p])), G[p]);
@@ -344,37 +373,44 @@ __device__ __forceinline__ void stage_segment_consts(const SplatArgs &a, const S
   stage_fast_consts_paired(a.params + (size_t)b * a.K * GG_PARAM_STRIDE, a.K, s.step, lo, hi, lo, hi, sc);
 }
 
-// dynamic shared memory: [2][9 K] float constants (pair-interleaved, gg_fast.cuh) | [kWarps][K][5] float warp sums |
-// [kWarps][kFastStages] stages
-__host__ __device__ inline size_t fast_consts_bytes(int K) { return (((size_t)2 * K * 48) + 127) & ~(size_t)127; }
+// dynamic shared memory: [2][12 Kp] float constants (pair-interleaved, gg_fast.cuh; Kp = K rounded up to even) |
+// [kWarps][K][5] float warp sums | [kWarps][kFastStages] stages
+__host__ __device__ inline size_t fast_consts_floats(int K) { return (size_t)12 * ((K + 1) & ~1); }
+__host__ __device__ inline size_t fast_consts_bytes(int K) { return ((2 * fast_consts_floats(K) * 4) + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t fast_wsum_bytes(int K) {
   return (((size_t)kWarps * K * GG_MOMENTS * 4) + 127) & ~(size_t)127;
 }
 
-template <bool WITH_GMASK>
-__global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const __grid_constant__ SplatArgs a,
-                                                                          int kq_shift, int nwork) {
+// NP = lane pairs per thread (2: a quad of Gaussians, K % 4 == 0; 1: a pair); KU = units per pixel (<= 32)
+template <int NP, bool WITH_GMASK>
+__global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const __grid_constant__ SplatArgs a, int KU,
+                                                                          int nwork) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ __align__(8) uint64_t full[kWarps][kFastStages];
 
   const int K = a.K;
-  const int KQ = 1 << kq_shift;
+  const int Kp = (K + 1) & ~1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kq = lane & (KQ - 1);            // this thread's quad of Gaussians (fixed for the whole kernel)
-  const int sl = lane >> kq_shift;           // its strip inside a warp slice
-  const int spw = 32 >> kq_shift;            // strips per warp slice
-  const int chunk_shift = 7 + kq_shift;      // one strip: 8 pixels x K floats = 128 KQ bytes
-  const bool flip = KQ <= 4 && (sl & 1);     // odd strips run from pixel 7 down to pixel 0
+  const int sl = lane / KU;                  // this thread's strip inside a warp slice ...
+  const int ku = lane - sl * KU;             // ... and its unit of Gaussians (fixed for the whole kernel)
+  const int kbase = 2 * NP * ku;             // first Gaussian of the unit
+  const int spw = 32 / KU;                   // strips per warp slice; lanes beyond spw * KU idle
+  const bool lane_ok = sl < spw;
+  const bool pow2 = (KU & (KU - 1)) == 0;
+  const int slice_bytes = spw * 32 * K;      // a strip is 8 pixels x K floats
+  const bool flip = NP == 2 && pow2 && KU <= 4 && (sl & 1);     // odd strips run from pixel 7 down to pixel 0
   const int dir = flip ? -1 : 1;
-  float *sc_base = reinterpret_cast<float *>(dyn);     // two buffers of 12 K floats (9 K used)
+  const bool kodd = (K & 1) != 0;
+  const f32x2 vm = pack2(1.0f, kbase + 1 < K ? 1.0f : 0.0f);
+  float *sc_base = reinterpret_cast<float *>(dyn);
   float *wsum = reinterpret_cast<float *>(dyn + fast_consts_bytes(K));
-  // 32-bit shared addresses of this warp's ring and barriers, and of this thread's first quad inside a stage (in
+  // 32-bit shared addresses of this warp's ring and barriers, and of this thread's first unit inside a stage (in
   // its order of traversal); pinned so that they are not re-derived inside the loop
   const uint32_t ring_u32 = pin_u32(smem_u32(dyn + fast_consts_bytes(K) + fast_wsum_bytes(K)) +
                                     (uint32_t)(warp * kFastStages * kFastStageBytes));
   const uint32_t bar_u32 = pin_u32(smem_u32(&full[warp][0]));
-  const uint32_t sp_u32 = pin_u32(ring_u32 + (uint32_t)((((sl * 8 + (flip ? 7 : 0)) << kq_shift) + kq) * 16));
-  const int dstride = dir * (16 << kq_shift);
+  const uint32_t sp_u32 = pin_u32(ring_u32 + (uint32_t)(((sl * 8 + (flip ? 7 : 0)) * K + kbase) * 4));
+  const int dstride = dir * 4 * K;
   const int w_begin = (int)((long long)blockIdx.x * nwork / gridDim.x);
   const int w_end = (int)((long long)(blockIdx.x + 1) * nwork / gridDim.x);
 
@@ -387,15 +423,15 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
   __syncwarp();
 
   // ---- issue cursor: runs kFastStages slices ahead of the consume cursor, across item boundaries.  Byte offsets
-  // inside the item's tile: this warp's slices start at warp * 4 KB and are 8 * 4 KB apart.
+  // inside the item's tile: this warp's slices start at warp * slice_bytes and are 8 slices apart.
   int iss_b = w_begin / a.T, iss_tile = w_begin - iss_b * a.T, iss_left = w_end - w_begin;
-  int iss_off = warp * kFastStageBytes, iss_total = 0, iss_stage = 0;
+  int iss_off = 0, iss_total = 0, iss_stage = 0;
   const char *iss_src = nullptr;
   auto iss_open = [&]() {   // the tile of item (iss_b, iss_tile)
     const FastTile t = fast_tile(a, a.sc[find_scale(a, iss_tile)], iss_b, iss_tile);
     iss_src = reinterpret_cast<const char *>(t.gtile);
-    iss_total = t.nstrips << chunk_shift;
-    iss_off = warp * kFastStageBytes;
+    iss_total = t.nstrips * 32 * K;
+    iss_off = warp * slice_bytes;
   };
   if (iss_left > 0) iss_open();
   auto issue_next = [&]() {
@@ -406,12 +442,12 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
     }
     if (iss_left <= 0) return;
     if (lane == 0) {
-      const unsigned bytes = (unsigned)min(kFastStageBytes, iss_total - iss_off);
+      const unsigned bytes = (unsigned)min(slice_bytes, iss_total - iss_off);
       const uint32_t bar = bar_u32 + (uint32_t)iss_stage * 8u;
       mbar_expect_tx_u32(bar, bytes);
       bulk_g2s_u32(ring_u32 + (uint32_t)iss_stage * kFastStageBytes, iss_src + iss_off, bytes, bar);
     }
-    iss_off += kWarps * kFastStageBytes;
+    iss_off += kWarps * slice_bytes;
     iss_stage = iss_stage + 1 == kFastStages ? 0 : iss_stage + 1;
   };
 #pragma unroll
@@ -420,11 +456,11 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
   int b = w_begin / a.T, tile = w_begin - b * a.T;
   if (w_begin < w_end) stage_segment_consts(a, a.sc[find_scale(a, tile)], b, sc_base);
 
-  f32x2 mux[2], muy[2], nA[2], nnr[2], nE[2], rb[2], rc[2], cc[2];   // this thread's four Gaussians, two lane pairs
+  f32x2 mux[NP], muy[NP], nA[NP], nnr[NP], nE[NP], rb[NP], rc[NP], cc[NP];   // this thread's Gaussians, lane pairs
   bool steep = false;
-  f32x2 T[2][GG_MOMENTS];
+  f32x2 T[NP][GG_MOMENTS];
 #pragma unroll
-  for (int p = 0; p < 2; ++p)
+  for (int p = 0; p < NP; ++p)
 #pragma unroll
     for (int j = 0; j < GG_MOMENTS; ++j) T[p][j] = pack2(0.f, 0.f);
   int stage = 0;             // ring position and barrier phase of the consume cursor
@@ -439,24 +475,30 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
     if (b != prev_b || si != prev_si) {   // new (image, scale) segment: its constants were staged one segment ago
       prev_b = b; prev_si = si;
       __syncthreads();
-      const float *sc = sc_base + (size_t)seg_par * 12 * K;
+      const float *sc = sc_base + (size_t)seg_par * fast_consts_floats(K);
       steep = false;
+      if (lane_ok) {
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        // lane pair p = Gaussians 4 kq + 2 p, + 1: four LDS.128 whose 64-bit halves are the packed constants
-        const float4 *q4 = reinterpret_cast<const float4 *>(sc + (2 * kq + p) * 16);
-        const float4 w0 = q4[0], w1 = q4[1], w2 = q4[2], w3 = q4[3];
-        mux[p] = pack2(w0.x, w0.y); muy[p] = pack2(w0.z, w0.w); nA[p] = pack2(w1.x, w1.y); nnr[p] = pack2(w1.z, w1.w);
-        nE[p] = pack2(w2.x, w2.y); rc[p] = pack2(w3.x, w3.y); cc[p] = pack2(w3.z, w3.w);
-        rb[p] = mul2(pack2(w2.z, w2.w), bc(flip ? -1.f : 1.f));     // 2 nA h, with h -> -h on reversed strips
-        steep = steep || sc[8 * K + 4 * kq + 2 * p] != 0.f || sc[8 * K + 4 * kq + 2 * p + 1] != 0.f;
+        for (int p = 0; p < NP; ++p) {
+          // lane pair p = Gaussians kbase + 2 p, + 1: four LDS.128 whose 64-bit halves are the packed constants
+          const float4 *q4 = reinterpret_cast<const float4 *>(sc + (NP * ku + p) * 16);
+          const float4 w0 = q4[0], w1 = q4[1], w2 = q4[2], w3 = q4[3];
+          mux[p] = pack2(w0.x, w0.y); muy[p] = pack2(w0.z, w0.w); nA[p] = pack2(w1.x, w1.y); nnr[p] = pack2(w1.z, w1.w);
+          nE[p] = pack2(w2.x, w2.y); rc[p] = pack2(w3.x, w3.y); cc[p] = pack2(w3.z, w3.w);
+          rb[p] = mul2(pack2(w2.z, w2.w), bc(flip ? -1.f : 1.f));     // 2 nA h, with h -> -h on reversed strips
+          steep = steep || sc[8 * Kp + kbase + 2 * p] != 0.f || sc[8 * Kp + kbase + 2 * p + 1] != 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+          mux[p] = muy[p] = nA[p] = nnr[p] = nE[p] = rc[p] = cc[p] = rb[p] = pack2(0.f, 0.f);
       }
       seg_par ^= 1;
       // the next (image, scale) segment of this CTA's range starts right after this scale's tiles
       int nb = b, ntile = s.tile_begin + s.tiles;
       if (ntile == a.T) { ntile = 0; ++nb; }
       if (nb * a.T + ntile < w_end)
-        stage_segment_consts(a, a.sc[find_scale(a, ntile)], nb, sc_base + (size_t)seg_par * 12 * K);
+        stage_segment_consts(a, a.sc[find_scale(a, ntile)], nb, sc_base + (size_t)seg_par * fast_consts_floats(K));
     }
     const bool flush = work == w_end - 1 || tile == a.T - 1;   // last item of this image in this CTA's range
     float *out = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K) * GG_MOMENTS;
@@ -468,13 +510,13 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
     const bool use_gmask = WITH_GMASK && s.mask != nullptr;
     const float hs = flip ? -h : h;                // signed step of this thread's traversal
     const f32x2 h8 = pin2(bc(8.0f * hs)), nhs = pin2(bc(-hs)), hh = pin2(bc(h * h));
-    const int nslices = (cur.nstrips + spw - 1) >> (5 - kq_shift);
+    const int nslices = (cur.nstrips + spw - 1) / spw;
     const int my_slices = nslices > warp ? (nslices - warp + kWarps - 1) / kWarps : 0;   // slices warp, warp+8, ...
     int g = warp * spw + sl;                       // strip index inside the tile
     int rrel = 0, cs = g;                          // its row inside the tile and its position inside the row
     while (cs >= strips_per_row) { cs -= strips_per_row; ++rrel; }
     for (int i = 0; i < my_slices; ++i) {
-      const bool valid = g < cur.nstrips;
+      const bool valid = lane_ok && g < cur.nstrips;
       const int col0 = valid ? cs * 8 : 0;
       const int row = cur.row_begin + (valid ? rrel : 0);
       const int cstart = flip ? col0 + 7 : col0;
@@ -490,9 +532,9 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
         for (int j = 0; j < 8; ++j) gm[j] = flip ? mm[7 - j] : mm[j];
       }
       const f32x2 y2 = bc(grid_coord(row, h)), x02 = bc(x0);
-      f32x2 dy[2], tr[2], e[2], gg[2], rr[2], M0[2], M1[2], M2[2];   // tr = t at the moments' reference point
+      f32x2 dy[NP], tr[NP], e[NP], gg[NP], rr[NP], M0[NP], M1[NP], M2[NP];   // tr = t at the moments' reference point
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
+      for (int p = 0; p < NP; ++p) {
         dy[p] = sub2(y2, muy[p]);
         tr[p] = fma2(nnr[p], dy[p], sub2(x02, mux[p]));
         e[p] = mul2(mul2(nE[p], dy[p]), dy[p]);
@@ -503,27 +545,27 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
       const uint32_t sp = sp_u32 + (uint32_t)stage * kFastStageBytes;
       if (!valid) {
 #pragma unroll
-        for (int p = 0; p < 2; ++p) M0[p] = M1[p] = M2[p] = pack2(0.f, 0.f);
+        for (int p = 0; p < NP; ++p) M0[p] = M1[p] = M2[p] = pack2(0.f, 0.f);
       } else if (!steep) {
-        f32x2 Bs[2], Cs[2];
-        strip_sums_recurrence<WITH_GMASK>(sp, dstride, gm, gg, rr, cc, M0, Bs, Cs);
+        f32x2 Bs[NP], Cs[NP];
+        strip_sums_recurrence<NP, WITH_GMASK>(sp, dstride, kodd, vm, gm, gg, rr, cc, M0, Bs, Cs);
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {   // moments about the point one step past the strip: xi_j = -(8 - j) hs
+        for (int p = 0; p < NP; ++p) {   // moments about the point one step past the strip: xi_j = -(8 - j) hs
           tr[p] = add2(tr[p], h8);
           M1[p] = mul2(Bs[p], nhs);
           M2[p] = mul2(sub2(add2(Cs[p], Cs[p]), Bs[p]), hh);
         }
       } else {
-        f32x2 nsh[2];
+        f32x2 nsh[NP];
 #pragma unroll
-        for (int p = 0; p < 2; ++p) nsh[p] = fma2(nnr[p], dy[p], sub2(bc(0.f), mux[p]));
-        strip_sums_direct<WITH_GMASK>(sp, dstride, gm, cstart, dir, h, x0, nA, e, nsh, M0, M1, M2);
+        for (int p = 0; p < NP; ++p) nsh[p] = fma2(nnr[p], dy[p], sub2(bc(0.f), mux[p]));
+        strip_sums_direct<NP, WITH_GMASK>(sp, dstride, kodd, vm, gm, cstart, dir, h, x0, nA, e, nsh, M0, M1, M2);
       }
       __syncwarp();                                    // every lane is done with the stage
       issue_next();
       // strip-local moments (about the reference point) -> moments of t = tr + xi, then the row weights
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
+      for (int p = 0; p < NP; ++p) {
         const f32x2 m1 = fma2(tr[p], M0[p], M1[p]);
         const f32x2 m2 = fma2(tr[p], add2(M1[p], m1), M2[p]);
         const f32x2 d0 = mul2(dy[p], M0[p]);
@@ -539,20 +581,30 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
       if (++stage == kFastStages) { stage = 0; phase ^= 1u; }
     }
     if (flush) {
-      // lanes that share kq (stride KQ) -> butterfly; then lanes 0..KQ-1 hold the warp totals [k][moment]
+      // lanes that share a unit (stride KU) are summed in a fixed order: butterfly when KU is a power of two, else
+      // lane ku adds the lanes ku + KU, ku + 2 KU, ... one by one; lanes 0..KU-1 then hold the warp totals
 #pragma unroll
-      for (int p = 0; p < 2; ++p)
+      for (int p = 0; p < NP; ++p)
 #pragma unroll
         for (int j = 0; j < GG_MOMENTS; ++j) {
           float lo, hi;
           unpack2(T[p][j], lo, hi);
-          for (int off = KQ; off < 32; off <<= 1) {
-            lo += __shfl_xor_sync(0xffffffffu, lo, off);
-            hi += __shfl_xor_sync(0xffffffffu, hi, off);
+          if (pow2) {
+            for (int off = KU; off < 32; off <<= 1) {
+              lo += __shfl_xor_sync(0xffffffffu, lo, off);
+              hi += __shfl_xor_sync(0xffffffffu, hi, off);
+            }
+          } else {
+            const float lo0 = lo, hi0 = hi;
+            for (int t = 1; t < spw; ++t) {
+              lo += __shfl_sync(0xffffffffu, lo0, (lane + t * KU) & 31);
+              hi += __shfl_sync(0xffffffffu, hi0, (lane + t * KU) & 31);
+            }
           }
-          if (lane < KQ) {
-            wsum[((size_t)warp * K + 4 * kq + 2 * p) * GG_MOMENTS + j] = lo;
-            wsum[((size_t)warp * K + 4 * kq + 2 * p + 1) * GG_MOMENTS + j] = hi;
+          if (lane < KU) {
+            const int k = kbase + 2 * p;
+            if (k < K) wsum[((size_t)warp * K + k) * GG_MOMENTS + j] = lo;
+            if (k + 1 < K) wsum[((size_t)warp * K + k + 1) * GG_MOMENTS + j] = hi;
           }
           T[p][j] = pack2(0.f, 0.f);
         }
@@ -568,13 +620,21 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_fast_kernel(const 
   }
 }
 
-bool splat_bwd_quad_fast_ok(const SplatArgs &a) {
-  for (int i = 0; i < a.nscales; ++i)
-    if ((a.sc[i].n & 7) != 0) return false;
+// units per pixel of the kernel above (0: shape not handled)
+int splat_bwd_nhwc_fast_units(int K) {
+  if (K >= 4 && (K & 3) == 0 && (K >> 2) <= 32) return K >> 2;     // quads
+  if (K >= 1 && (K + 1) / 2 <= 32) return (K + 1) / 2;             // pairs
+  return 0;
+}
+
+bool splat_bwd_nhwc_fast_ok(int K, int nscales, const int *sizes) {
+  if (splat_bwd_nhwc_fast_units(K) == 0) return false;
+  for (int i = 0; i < nscales; ++i)
+    if ((sizes[i] & 7) != 0) return false;
   return true;
 }
 
-cudaError_t launch_splat_bwd_quad_fast(const SplatArgs &a, int B, int kq_shift, bool any_mask, cudaStream_t st) {
+cudaError_t launch_splat_bwd_nhwc_fast(const SplatArgs &a, int B, bool any_mask, cudaStream_t st) {
   static int sm_count[64] = {};
   const size_t smem = fast_consts_bytes(a.K) + fast_wsum_bytes(a.K) + (size_t)kWarps * kFastStages * kFastStageBytes;
   int dev = 0;
@@ -582,10 +642,12 @@ cudaError_t launch_splat_bwd_quad_fast(const SplatArgs &a, int B, int kq_shift, 
   int &sms = sm_count[dev & 63];
   if (sms == 0) {   // first launch on this device
     const int max_smem = (int)(fast_consts_bytes(128) + fast_wsum_bytes(128) + (size_t)kWarps * kFastStages * kFastStageBytes);
-    cudaError_t e = cudaFuncSetAttribute(splat_bwd_quad_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         max_smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(splat_bwd_quad_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaError_t e = cudaSuccess;
+#define GG_SET_SMEM(NP, GM)                                                                                           \
+  if (e == cudaSuccess)                                                                                               \
+    e = cudaFuncSetAttribute(splat_bwd_nhwc_fast_kernel<NP, GM>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
+    GG_SET_SMEM(1, false); GG_SET_SMEM(1, true); GG_SET_SMEM(2, false); GG_SET_SMEM(2, true);
+#undef GG_SET_SMEM
     int count = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
@@ -594,10 +656,18 @@ cudaError_t launch_splat_bwd_quad_fast(const SplatArgs &a, int B, int kq_shift, 
   const size_t nwork = (size_t)B * a.T;
   if (nwork == 0) return cudaSuccess;
   if (nwork > 0x7fffffffu) return cudaErrorInvalidValue;
+  const int KU = splat_bwd_nhwc_fast_units(a.K);
+  if (KU == 0) return cudaErrorInvalidValue;
+  const bool quads = (a.K & 3) == 0;
   // persistent: 2 CTAs per SM (registers and shared memory both allow exactly two)
   const unsigned grid = (unsigned)(nwork < (size_t)2 * sms ? nwork : (size_t)2 * sms);
-  if (any_mask) launch_pdl(splat_bwd_quad_fast_kernel<true>, dim3(grid), dim3(kThreads), smem, st, a, kq_shift, (int)nwork);
-  else launch_pdl(splat_bwd_quad_fast_kernel<false>, dim3(grid), dim3(kThreads), smem, st, a, kq_shift, (int)nwork);
+  if (quads) {
+    if (any_mask) launch_pdl(splat_bwd_nhwc_fast_kernel<2, true>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork);
+    else launch_pdl(splat_bwd_nhwc_fast_kernel<2, false>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork);
+  } else {
+    if (any_mask) launch_pdl(splat_bwd_nhwc_fast_kernel<1, true>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork);
+    else launch_pdl(splat_bwd_nhwc_fast_kernel<1, false>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork);
+  }
   return cudaGetLastError();
 }
 

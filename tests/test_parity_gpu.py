@@ -815,16 +815,20 @@ def test_randomised_shapes_and_scales_fast_mask_path(gg, cuda_device, restore_mo
 
 @pytest.mark.parametrize("K,sizes,B", [
     (16, (32, 64, 128, 256), 3), (4, (8, 24), 2), (8, (40, 64), 2), (32, (48,), 2), (64, (72, 16), 1), (128, (32,), 1),
+    (6, (32, 64, 128, 256), 2), (12, (32, 64, 128), 2), (5, (40, 64), 2), (7, (24,), 3), (1, (16,), 2), (2, (64,), 2),
+    (20, (56,), 2), (63, (16,), 1),
 ])
 def test_nhwc_maps_backward_forward_differenced_vs_oracle_and_direct(gg, cuda_device, restore_modes, K, sizes, B):
-    """NHWC maps + silhouette gradients through the forward-differenced bulk-copy kernel (gg_splat_tma.cu; any K whose
-    quads are a power of two, any n that is a multiple of 8, strips of one warp slice in different rows at small n,
-    partial last slices) against the oracle's autograd, and against the direct kernels (gg.set_fast_mask(False))."""
+    """NHWC maps + silhouette gradients through the forward-differenced bulk-copy kernel (gg_splat_tma.cu: quads of
+    Gaussians for K % 4 == 0, pairs for every other K including odd ones and the reference's own 6 and 12; any n that
+    is a multiple of 8, strips of one warp slice in different rows at small n, partial last slices) against the
+    oracle's autograd, and against the direct kernels (gg.set_fast_mask(False)).  The forward of the non-power-of-two
+    K goes through the flat 128-bit-store kernel."""
     inp = rp.synth_inputs(B, K, seed=700 + K, angle=45.0)
-    # one needle narrower than a pixel at the finest scale (the kernel's direct fall-back for its quad) and one blob
-    # far outside the frame
+    # one needle narrower than a pixel at the finest scale (the kernel's direct fall-back for its unit) and one blob
+    # far outside the frame (above it: the yaw leaves y alone, so it stays in front of the camera)
     inp["sigma"][0, 0] = torch.diag(torch.tensor([3e-4, 0.2, 0.05], dtype=torch.float64))
-    inp["mus"][0, K - 1, 0] = torch.tensor([2.5, -0.3, 0.1])
+    inp["mus"][B - 1, K - 1, 0] = torch.tensor([0.1, 2.5, 0.1])
     lv = _leaves(inp)
     ref = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0, 0, -2., sizes=sizes)
     w = weights_like([r.shape for r in ref], 31)
@@ -836,6 +840,9 @@ def test_nhwc_maps_backward_forward_differenced_vs_oracle_and_direct(gg, cuda_de
         dv = _leaves(inp, cuda_device)
         out, mask = gg.get_landmarks_with_mask(dv["mus"], dv["sigma"], dv["rotx"], dv["roty"], dv["rotz"], 0, 0, -2.,
                                                sizes=sizes)
+        for o, r in zip(out, ref):
+            assert_close_norm(o, r, FWD_RTOL, f"K={K} maps n={r.shape[1]}")
+        assert_close_norm(mask, ref[-1].detach().sum(-1, keepdim=True), FWD_RTOL, f"K={K} silhouette")
         (sum((o * q.to(cuda_device)).sum() for o, q in zip(out, w)) + (mask * wm.to(cuda_device)).sum()).backward()
         return {k: dv[k].grad for k in ("mus", "sigma", "rotx", "roty", "rotz")}
 

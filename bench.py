@@ -393,6 +393,37 @@ def run_gpu(args):
     except Exception as exc:                      # pragma: no cover
         fused = {"value": None, "error": repr(exc)}
 
+    # ---- maps mode (HBM-bound): the K-channel NHWC maps [B,n,n,K] the generator consumes, written by the
+    # forward and read back as upstream gradients by the backward; kernels alone, two rotating buffers (> L2)
+    maps_mode = None
+    try:
+        from gaussigan_b200._lib import int_array
+        mbufs = [torch.randn((B, n, n, K), device=dev) for _ in range(2)]
+        mptrs = [ptr_array([m.data_ptr()]) for m in mbufs]
+        msz, mnull = int_array((n,)), ptr_array([None])
+        mT = check(lib.gg_splat_bwd_tiles(K, 1, msz, int_array((1,)), int_array((0,)), LAYOUT_NHWC), "tiles")
+        mpart = torch.empty((B, mT, K, 5), device=dev)
+        p0 = sets[0][0].params
+
+        def maps_bwd(i):
+            check(lib.gg_splat_bwd(p0.data_ptr(), B, K, 1, msz, mptrs[i % 2], mnull, LAYOUT_NHWC, mpart.data_ptr(), mT,
+                                   dev.index, st), "gg_splat_bwd(maps)")
+
+        def maps_fwd(i):
+            check(lib.gg_splat_fwd(p0.data_ptr(), B, K, 1, msz, mptrs[i % 2], mnull, LAYOUT_NHWC, dev.index, st),
+                  "gg_splat_fwd(maps)")
+
+        us_mb, us_mf = kernel_us(maps_bwd, 20), kernel_us(maps_fwd, 20)
+        mbytes = B * n * n * K * 4
+        maps_mode = {"workload": f"NHWC maps [{B},{n},{n},{K}] float32, {mbytes / 1e6:.0f} MB per launch, kernels alone",
+                     "bwd_us": us_mb, "bwd_gbs": mbytes / us_mb / 1e3, "bwd_frac_of_hbm": mbytes / us_mb / 1e3 / peaks["hbm_gbs"],
+                     "fwd_us": us_mf, "fwd_gbs": mbytes / us_mf / 1e3, "fwd_frac_of_hbm": mbytes / us_mf / 1e3 / peaks["hbm_gbs"],
+                     "hbm_peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"],
+                     "note": "the forward only writes: its rate can exceed the measured copy (read+write) bandwidth"}
+        del mbufs, mpart
+    except Exception as exc:                      # pragma: no cover
+        maps_mode = {"error": repr(exc)}
+
     # ---- training-time exchange: the shared (canonical-Gaussian) gradients summed over batch and ranks after every step.
     # (a) gaussigan_b200.dist.P2PSharedGradReducer: one single-CTA kernel over NVLink peer memory, captured in the same
     #     graph as the steps; (b) the same with a local torch sum + one NCCL all_reduce per step (eager).
@@ -548,7 +579,7 @@ def run_gpu(args):
                        "l2": f"{R} rotating input/output sets = {rot_bytes / 1e6:.0f} MB > 126 MB L2",
                        "step": "project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd; 32 steps per CUDA-graph replay, kernels chained by programmatic dependent launch"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "e2e_binary_targets": e2e_bits,
-            "fused_loss": fused, "two_chains": two_chains,
+            "fused_loss": fused, "two_chains": two_chains, "maps_mode": maps_mode,
             "allreduce": allreduce,
             "gpu_launches": args.steps * SilhouetteStep.LAUNCHES_PER_STEP,
         }

@@ -489,27 +489,47 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_flat_kernel(const __grid_c
   const int vpr = (n * K) >> 2;                       // 128-bit vectors per row
   const float inv_vpr = 1.0f / (float)vpr;
   float *mtile = s.maps + ((size_t)b * n + row_begin) * n * K;
-  for (int idx = threadIdx.x; idx < rows * vpr; idx += kThreads) {
-    // r = idx / vpr and p = f / K by float reciprocal (exact for operands < 2^22, which the launcher checks), with
-    // a correction step for the last-bit cases
-    int r = __float2int_rd(((float)idx + 0.5f) * inv_vpr);
-    int q = idx - r * vpr;
-    if (q < 0) { q += vpr; --r; } else if (q >= vpr) { q -= vpr; ++r; }
+  // Index arithmetic is kept off the conversion/transcendental pipe (the exponentials need it): (row, vector) and
+  // (pixel, Gaussian) advance incrementally, the pixel index is carried as a float as well (exact), and the float
+  // reciprocal divisions (exact for operands < 2^22, which the launcher checks, up to a correction step) only run
+  // at the start and when a thread moves to another row.
+  const int dp = (4 * kThreads) / K, dk = 4 * kThreads - dp * K;     // pixel / Gaussian step of one pass
+  const float dpf = (float)dp;
+  int r = __float2int_rd(((float)threadIdx.x + 0.5f) * inv_vpr);
+  int q = (int)threadIdx.x - r * vpr;
+  if (q < 0) { q += vpr; --r; } else if (q >= vpr) { q -= vpr; ++r; }
+  int pix = 0, k = 0;
+  float pixf = 0.f;
+  auto locate = [&]() {   // (pixel, Gaussian) of the first float of vector q
     const int f = 4 * q;
-    int p = __float2int_rd(((float)f + 0.5f) * inv_k);
-    int k = f - p * K;
-    if (k < 0) { k += K; --p; } else if (k >= K) { k -= K; ++p; }
+    pix = __float2int_rd(((float)f + 0.5f) * inv_k);
+    k = f - pix * K;
+    if (k < 0) { k += K; --pix; } else if (k >= K) { k -= K; ++pix; }
+    pixf = (float)pix;
+  };
+  locate();
+  while (r < rows) {
     const float4 *rc = rowc + r * K;
-    float x = grid_coord(p, h);
+    int kk = k;
+    float xf = pixf;
+    float x = __fadd_rn(-1.0f, __fmul_rn(h, xf));     // grid_coord of the pixel
     float g[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float4 c = rc[k];
+      const float4 c = rc[kk];
       const float t = x - c.x;
       g[e] = ex2_approx(fmaf(c.z * t, t, c.y));
-      if (++k == K) { k = 0; ++p; x = grid_coord(p, h); }
+      if (++kk == K) { kk = 0; xf += 1.0f; x = __fadd_rn(-1.0f, __fmul_rn(h, xf)); }
     }
-    st_f4(mtile + (size_t)r * n * K + f, g[0], g[1], g[2], g[3]);
+    st_f4(mtile + (size_t)r * n * K + 4 * q, g[0], g[1], g[2], g[3]);
+    q += kThreads;
+    if (q < vpr) {
+      pix += dp; pixf += dpf; k += dk;
+      if (k >= K) { k -= K; ++pix; pixf += 1.0f; }
+    } else {
+      do { q -= vpr; ++r; } while (q >= vpr);
+      locate();
+    }
   }
 }
 

@@ -461,6 +461,53 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quadg_kernel(const __grid_
   }
 }
 
+// ========================================================================== forward, pairs, even K
+// The same for K = 2 KP that is not a multiple of 4 (the reference's K = 6): thread = (pixel, 2 Gaussians), one
+// 64-bit store, consecutive threads -> consecutive 8-byte chunks.
+__global__ void __launch_bounds__(kThreads) splat_fwd_pair_kernel(const __grid_constant__ SplatArgs a, int KP) {
+  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
+  const int b = blockIdx.x / a.T;
+  const int tile = blockIdx.x - b * a.T;
+  const ScaleDesc &s = a.sc[find_scale(a, tile)];
+  const int K = a.K, n = s.n;
+  const int cpp = kThreads / KP;                    // pixels per pass
+  const int c0 = threadIdx.x / KP, kp = threadIdx.x - c0 * KP;
+  if (c0 >= cpp) return;
+
+  float mux[2], muy[2], nA[2], nr[2], nE[2];
+  {
+    const float4 *gp = reinterpret_cast<const float4 *>(a.params + ((size_t)b * K + 2 * kp) * GG_PARAM_STRIDE);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float4 lo = __ldg(gp + 2 * i), hi = __ldg(gp + 2 * i + 1);
+      mux[i] = lo.x; muy[i] = lo.y; nA[i] = lo.z; nr[i] = lo.w; nE[i] = hi.x;
+    }
+  }
+  const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
+  const int row_end = min(n, row_begin + s.rows_per_tile);
+  for (int row = row_begin; row < row_end; ++row) {
+    const float y = grid_coord(row, s.step);
+    float sh[2], e[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float dy = y - muy[i];
+      sh[i] = fmaf(nr[i], dy, mux[i]);
+      e[i] = (nE[i] * dy) * dy;
+    }
+    float *mrow = s.maps + ((size_t)b * n + row) * n * K + 2 * kp;
+    for (int col = c0; col < n; col += cpp) {
+      const float x = grid_coord(col, s.step);
+      float g[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float t = x - sh[i];
+        g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+      }
+      *reinterpret_cast<float2 *>(mrow + (size_t)col * K) = make_float2(g[0], g[1]);
+    }
+  }
+}
+
 // ================================================================================= forward, flat
 // NHWC maps for ANY K with n K % 4 == 0 (the reference's own K = 6 and 12 among them).  A row of the output is n K
 // consecutive floats; thread = 4 of them = one 128-bit store, whichever (pixel, Gaussian) pairs they belong to.
@@ -874,6 +921,9 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
       err = cudaGetLastError();
     } else if (pl.maps_kind == MAPS_FLAT && (K & 3) == 0 && (K >> 2) <= kThreads) {
       launch_pdl(splat_fwd_quadg_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 2);
+      err = cudaGetLastError();
+    } else if (pl.maps_kind == MAPS_FLAT && (K & 1) == 0 && (K >> 1) <= kThreads) {
+      launch_pdl(splat_fwd_pair_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 1);
       err = cudaGetLastError();
     } else if (pl.maps_kind == MAPS_FLAT) {
       int max_rows = 1;

@@ -846,8 +846,9 @@ def test_nhwc_maps_backward_forward_differenced_vs_oracle_and_direct(gg, cuda_de
         (sum((o * q.to(cuda_device)).sum() for o, q in zip(out, w)) + (mask * wm.to(cuda_device)).sum()).backward()
         return {k: dv[k].grad for k in ("mus", "sigma", "rotx", "roty", "rotz")}
 
-    fast, direct = run(True), run(False)
+    fast, direct, again = run(True), run(False), run(True)
     for k in fast:
+        assert torch.equal(fast[k], again[k]), f"K={K} grad {k}: not bit-reproducible"      # fixed reduction order
         assert_close_norm(fast[k], lv[k].grad, GRAD_RTOL, f"K={K} grad {k} (forward-differenced)")
         assert_close_norm(direct[k], lv[k].grad, GRAD_RTOL, f"K={K} grad {k} (direct)")
         assert_close_norm(fast[k], direct[k], GRAD_RTOL, f"K={K} grad {k} fast vs direct")

@@ -854,6 +854,45 @@ def test_nhwc_maps_backward_forward_differenced_vs_oracle_and_direct(gg, cuda_de
         assert_close_norm(fast[k], direct[k], GRAD_RTOL, f"K={K} grad {k} fast vs direct")
 
 
+def test_randomised_nhwc_maps_forward_and_backward(gg, cuda_device):
+    """Seeded sweep of the NHWC maps kernels (quad / pair / flat forwards, quad- and pair-unit forward-differenced
+    backward): K 1..24, n a multiple of 8 up to 160, Gaussians from about a pixel to larger than the frame, off-screen
+    centres, all three Euler angles, with and without a silhouette gradient on top of the maps gradient."""
+    rng = torch.Generator().manual_seed(77)
+    worst_f, worst_g = 0.0, 0.0
+    for case in range(28):
+        B, K = 2, int(torch.randint(1, 25, (1,), generator=rng))
+        n = 8 * int(torch.randint(1, 21, (1,), generator=rng))
+        mus = ((torch.rand(B, K, 1, 3, generator=rng) - 0.5) * torch.tensor([3.0, 3.0, 1.0])).float()
+        q, _ = torch.linalg.qr(torch.randn(B, K, 3, 3, generator=rng, dtype=torch.float64))
+        lo, hi = torch.log(torch.tensor(3e-4, dtype=torch.float64)), torch.log(torch.tensor(0.6, dtype=torch.float64))
+        var = torch.exp(torch.rand(B, K, 3, generator=rng, dtype=torch.float64) * (hi - lo) + lo)
+        sig = (q * var[..., None, :]) @ q.transpose(-1, -2)
+        rot = [(torch.rand(B, 1, generator=rng) - 0.5) * a for a in (40.0, 360.0, 40.0)]
+        with_mask = bool(torch.randint(0, 2, (1,), generator=rng))
+        lv = [x.clone().requires_grad_(True) for x in (mus, sig, rot[1])]
+        ref = rp.get_landmarks(lv[0], lv[1], rot[0], lv[2], rot[2], 0, 0, -2.5, sizes=(n,))[0]
+        if not torch.isfinite(ref).all() or float(ref.detach().abs().max()) < 1e-6 or float(ref.detach().max()) > 1.5:
+            continue                       # degenerate geometry (a blob through the camera plane) / empty frame
+        w = torch.randn(B, n, n, K, generator=rng)
+        wm = torch.randn(B, n, n, 1, generator=rng)
+        ((ref * w).sum() + ((ref.sum(-1, keepdim=True) * wm).sum() if with_mask else 0.0)).backward()
+        dv = [x.to(cuda_device).requires_grad_(True) for x in (mus, sig, rot[1])]
+        out, mask = gg.get_landmarks_with_mask(dv[0], dv[1], rot[0].to(cuda_device), dv[2], rot[2].to(cuda_device),
+                                               0, 0, -2.5, sizes=(n,))
+        ef = max(max_rel(out[0], ref), max_rel(mask, ref.detach().sum(-1, keepdim=True)))
+        worst_f = max(worst_f, ef)
+        assert ef <= FWD_RTOL, f"case {case} (n={n}, K={K}): forward {ef:.2e}"
+        ((out[0] * w.to(cuda_device)).sum() + ((mask * wm.to(cuda_device)).sum() if with_mask else 0.0)).backward()
+        for a, b, nm in zip(dv, lv, ("mus", "sigma", "roty")):
+            if float(b.grad.abs().max()) < 1e-12:
+                continue
+            eg = max_rel(a.grad, b.grad)
+            worst_g = max(worst_g, eg)
+            assert eg <= GRAD_RTOL, f"case {case} (n={n}, K={K}, mask={with_mask}): grad {nm} {eg:.2e}"
+    print(f"worst forward {worst_f:.2e}, worst gradient {worst_g:.2e}")
+
+
 def test_second_device_in_the_same_process(gg, cuda_device):
     """Tensors on cuda:1 while cuda:0 is PyTorch's current device (and the other way round): the library follows the
     tensors' device on every call.  Needs two GPUs."""

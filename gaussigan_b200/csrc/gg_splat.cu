@@ -732,6 +732,22 @@ void quad_geometry(ScaleDesc &d, int n, int KQ, int passes) {
   d.step = n > 1 ? (1.0f - (-1.0f)) / (float)(n - 1) : 0.0f;
 }
 
+// tiles of the persistent maps backward (gg_splat_tma.cu): whole rows, about GG_FAST_TILE_KB of upstream gradient
+// each, whatever K is.  Measured at B = 64, 256 x 256 (profiles/r1_maps_mode_timings.txt): 128 KB tiles 49.9 us at
+// K = 16 and 26.6 us at K = 6; 32 KB tiles 55.2 / 30.8 us (per-item bookkeeping), 512 KB tiles balance worse
+void fast_bwd_geometry(ScaleDesc &d, int n, int K) {
+  static const int tile_kb = env_int("GG_FAST_TILE_KB", 128);
+  d.n = n;
+  d.contig = 0;
+  d.cta = kThreads;
+  d.spr = d.sprc = d.rpp = d.chunks = 0;
+  const long long row_bytes = (long long)n * K * 4;
+  long long rows = ((long long)tile_kb * 1024 + row_bytes / 2) / row_bytes;
+  d.rows_per_tile = (int)(rows < 1 ? 1 : rows > n ? n : rows);
+  d.tiles = (n + d.rows_per_tile - 1) / d.rows_per_tile;
+  d.step = n > 1 ? (1.0f - (-1.0f)) / (float)(n - 1) : 0.0f;
+}
+
 bool quad_ok(int K, int *shift) {
   if (K < 4 || (K & 3)) return false;
   int KQ = K >> 2;
@@ -840,7 +856,8 @@ static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool
   for (int i = 0; i < nscales; ++i) {
     if (has_maps[i]) {
       ScaleDesc &d = pl.maps.sc[pl.maps.nscales++];
-      if (pl.maps_kind != MAPS_STRIP) quad_geometry(d, sizes[i], (K + 3) >> 2, quad_passes(backward));
+      if (pl.maps_fast_bwd) fast_bwd_geometry(d, sizes[i], K);
+      else if (pl.maps_kind != MAPS_STRIP) quad_geometry(d, sizes[i], (K + 3) >> 2, quad_passes(backward));
       else strip_geometry(d, sizes[i], rpt);
       d.tile_begin = tb_maps;
       tb_maps += d.tiles;

@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(kThreads, GG_TMA_MINBLOCKS) splat_bwd_quad_tma
 // (g_{j+1} = g_j r_j, r_{j+1} = r_j c: two exponentials per strip instead of eight); the two lanes of every FP32x2
 // register are two GAUSSIANS of the unit, which is how the gradient arrives, so nothing is repacked.
 //
-// A warp slice is 32 / KU strips (KU = units per pixel) of contiguous upstream gradient, at most 4 KB, one bulk
-// copy; strips of a slice may lie in different rows (n % 8 == 0 keeps a strip inside one row), so any n that is a
+// A warp slice is 32 / KU strips (KU = units per pixel; twice that for pair units, two strips per thread) of
+// contiguous upstream gradient, at most 4 KB, one bulk copy; strips of a slice may lie in different rows (n % 8 == 0 keeps a strip inside one row), so any n that is a
 // multiple of 8 works, including the 32 x 32 scale of the pyramid.  Bank conflicts: the 8 lanes of an LDS.128 phase
 // are 8/KQ strips x KQ quads reading the same pixel index j, and strips are 128 KQ bytes apart -- the same banks.
 // For power-of-two KQ <= 4 odd strips therefore run the recurrence BACKWARDS (from pixel 7, step -h: only the sign
@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
   const int spw = 32 / KU;                   // strips per warp slice; lanes beyond spw * KU idle
   const bool lane_ok = sl < spw;
   const bool pow2 = (KU & (KU - 1)) == 0;
-  const int slice_bytes = spw * 32 * K;      // a strip is 8 pixels x K floats
+  constexpr int SPT = NP == 2 ? 1 : 2;       // strips per thread and slice: pair units take two (4 KB copies again)
+  const int slice_bytes = SPT * spw * 32 * K;   // a strip is 8 pixels x K floats
   const bool flip = NP == 2 && pow2 && KU <= 4 && (sl & 1);     // odd strips run from pixel 7 down to pixel 0
   const int dir = flip ? -1 : 1;
   const bool kodd = (K & 1) != 0;
@@ -510,73 +511,83 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
     const bool use_gmask = WITH_GMASK && s.mask != nullptr;
     const float hs = flip ? -h : h;                // signed step of this thread's traversal
     const f32x2 h8 = pin2(bc(8.0f * hs)), nhs = pin2(bc(-hs)), hh = pin2(bc(h * h));
-    const int nslices = (cur.nstrips + spw - 1) / spw;
+    const int nslices = (cur.nstrips + SPT * spw - 1) / (SPT * spw);
     const int my_slices = nslices > warp ? (nslices - warp + kWarps - 1) / kWarps : 0;   // slices warp, warp+8, ...
-    int g = warp * spw + sl;                       // strip index inside the tile
+    int g = warp * SPT * spw + sl;                 // first strip of this thread inside the tile
     int rrel = 0, cs = g;                          // its row inside the tile and its position inside the row
     while (cs >= strips_per_row) { cs -= strips_per_row; ++rrel; }
     for (int i = 0; i < my_slices; ++i) {
-      const bool valid = lane_ok && g < cur.nstrips;
-      const int col0 = valid ? cs * 8 : 0;
-      const int row = cur.row_begin + (valid ? rrel : 0);
-      const int cstart = flip ? col0 + 7 : col0;
-      const float x0 = grid_coord(cstart, h);
-      float gm[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) gm[j] = 0.f;
-      if (use_gmask && valid) {
-        const float4 *mp = reinterpret_cast<const float4 *>(s.mask + ((size_t)b * n + row) * n + col0);
-        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-        const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gm[j] = flip ? mm[7 - j] : mm[j];
-      }
-      const f32x2 y2 = bc(grid_coord(row, h)), x02 = bc(x0);
-      f32x2 dy[NP], tr[NP], e[NP], gg[NP], rr[NP], M0[NP], M1[NP], M2[NP];   // tr = t at the moments' reference point
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        dy[p] = sub2(y2, muy[p]);
-        tr[p] = fma2(nnr[p], dy[p], sub2(x02, mux[p]));
-        e[p] = mul2(mul2(nE[p], dy[p]), dy[p]);
-        gg[p] = ex2_2(fma2(mul2(nA[p], tr[p]), tr[p], e[p]));
-        rr[p] = ex2_2(fma2(rb[p], tr[p], rc[p]));
-      }
-      mbar_wait_u32(bar_u32 + (uint32_t)stage * 8u, phase);
-      const uint32_t sp = sp_u32 + (uint32_t)stage * kFastStageBytes;
-      if (!valid) {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) M0[p] = M1[p] = M2[p] = pack2(0.f, 0.f);
-      } else if (!steep) {
-        f32x2 Bs[NP], Cs[NP];
-        strip_sums_recurrence<NP, WITH_GMASK>(sp, dstride, kodd, vm, gm, gg, rr, cc, M0, Bs, Cs);
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {   // moments about the point one step past the strip: xi_j = -(8 - j) hs
-          tr[p] = add2(tr[p], h8);
-          M1[p] = mul2(Bs[p], nhs);
-          M2[p] = mul2(sub2(add2(Cs[p], Cs[p]), Bs[p]), hh);
+      for (int ss = 0; ss < SPT; ++ss) {           // the thread's strips of this slice: g, g + spw
+        int rs = rrel, cq = cs;
+        if (ss > 0) {
+          cq += ss * spw;
+          while (cq >= strips_per_row) { cq -= strips_per_row; ++rs; }
         }
-      } else {
-        f32x2 nsh[NP];
+        const bool valid = lane_ok && g + ss * spw < cur.nstrips;
+        const int col0 = valid ? cq * 8 : 0;
+        const int row = cur.row_begin + (valid ? rs : 0);
+        const int cstart = flip ? col0 + 7 : col0;
+        const float x0 = grid_coord(cstart, h);
+        float gm[8];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) nsh[p] = fma2(nnr[p], dy[p], sub2(bc(0.f), mux[p]));
-        strip_sums_direct<NP, WITH_GMASK>(sp, dstride, kodd, vm, gm, cstart, dir, h, x0, nA, e, nsh, M0, M1, M2);
-      }
-      __syncwarp();                                    // every lane is done with the stage
-      issue_next();
-      // strip-local moments (about the reference point) -> moments of t = tr + xi, then the row weights
+        for (int j = 0; j < 8; ++j) gm[j] = 0.f;
+        if (use_gmask && valid) {
+          const float4 *mp = reinterpret_cast<const float4 *>(s.mask + ((size_t)b * n + row) * n + col0);
+          const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+          const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        const f32x2 m1 = fma2(tr[p], M0[p], M1[p]);
-        const f32x2 m2 = fma2(tr[p], add2(M1[p], m1), M2[p]);
-        const f32x2 d0 = mul2(dy[p], M0[p]);
-        T[p][0] = add2(T[p][0], m2);
-        T[p][3] = add2(T[p][3], m1);
-        T[p][1] = fma2(dy[p], m1, T[p][1]);
-        T[p][4] = add2(T[p][4], d0);
-        T[p][2] = fma2(dy[p], d0, T[p][2]);
+          for (int j = 0; j < 8; ++j) gm[j] = flip ? mm[7 - j] : mm[j];
+        }
+        const f32x2 y2 = bc(grid_coord(row, h)), x02 = bc(x0);
+        f32x2 dy[NP], tr[NP], e[NP], gg[NP], rr[NP], M0[NP], M1[NP], M2[NP];   // tr = t at the moments' reference point
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          dy[p] = sub2(y2, muy[p]);
+          tr[p] = fma2(nnr[p], dy[p], sub2(x02, mux[p]));
+          e[p] = mul2(mul2(nE[p], dy[p]), dy[p]);
+          gg[p] = ex2_2(fma2(mul2(nA[p], tr[p]), tr[p], e[p]));
+          rr[p] = ex2_2(fma2(rb[p], tr[p], rc[p]));
+        }
+        if (ss == 0) mbar_wait_u32(bar_u32 + (uint32_t)stage * 8u, phase);
+        const uint32_t sp = sp_u32 + (uint32_t)stage * kFastStageBytes + (uint32_t)(ss * spw * 32 * K);
+        if (!valid) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) M0[p] = M1[p] = M2[p] = pack2(0.f, 0.f);
+        } else if (!steep) {
+          f32x2 Bs[NP], Cs[NP];
+          strip_sums_recurrence<NP, WITH_GMASK>(sp, dstride, kodd, vm, gm, gg, rr, cc, M0, Bs, Cs);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {   // moments about the point one step past the strip: xi_j = -(8 - j) hs
+            tr[p] = add2(tr[p], h8);
+            M1[p] = mul2(Bs[p], nhs);
+            M2[p] = mul2(sub2(add2(Cs[p], Cs[p]), Bs[p]), hh);
+          }
+        } else {
+          f32x2 nsh[NP];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) nsh[p] = fma2(nnr[p], dy[p], sub2(bc(0.f), mux[p]));
+          strip_sums_direct<NP, WITH_GMASK>(sp, dstride, kodd, vm, gm, cstart, dir, h, x0, nA, e, nsh, M0, M1, M2);
+        }
+        if (ss == SPT - 1) {
+          __syncwarp();                                  // every lane is done with the stage
+          issue_next();
+        }
+        // strip-local moments (about the reference point) -> moments of t = tr + xi, then the row weights
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const f32x2 m1 = fma2(tr[p], M0[p], M1[p]);
+          const f32x2 m2 = fma2(tr[p], add2(M1[p], m1), M2[p]);
+          const f32x2 d0 = mul2(dy[p], M0[p]);
+          T[p][0] = add2(T[p][0], m2);
+          T[p][3] = add2(T[p][3], m1);
+          T[p][1] = fma2(dy[p], m1, T[p][1]);
+          T[p][4] = add2(T[p][4], d0);
+          T[p][2] = fma2(dy[p], d0, T[p][2]);
+        }
       }
-      g += kWarps * spw;
-      cs += kWarps * spw;
+      g += kWarps * SPT * spw;
+      cs += kWarps * SPT * spw;
       while (cs >= strips_per_row) { cs -= strips_per_row; ++rrel; }
       if (++stage == kFastStages) { stage = 0; phase ^= 1u; }
     }

@@ -6,9 +6,15 @@
 
 namespace gg {
 
+#ifndef GG_MAX_VISIBLE_SLOPE
+#define GG_MAX_VISIBLE_SLOPE 3.0f
+#endif
+#ifndef GG_MAX_SHARPNESS
+#define GG_MAX_SHARPNESS 512.0f
+#endif
 constexpr float kMaxSlope = 13.0f;     // largest |d(exponent)/d(pixel)| the recurrence is trusted with (range safety)
-constexpr float kMaxVisibleSlope = 3.0f;   // ... and where the Gaussian is visible (accuracy)
-constexpr float kMaxSharpness = 512.0f;    // largest |nA| = a log2(e): bounds the error of stepping by exactly h
+constexpr float kMaxVisibleSlope = GG_MAX_VISIBLE_SLOPE;   // ... and where the Gaussian is visible (accuracy)
+constexpr float kMaxSharpness = GG_MAX_SHARPNESS;    // largest |nA| = a log2(e): bounds the error of stepping by exactly h
 
 // Per-Gaussian constants of the recurrence at grid step h:
 //   c0 = mu_x, mu_y, nA, -nr      c1 = nE, 2 nA h, nA h^2, c = exp2(2 nA h^2)      steep: evaluate directly instead

@@ -325,28 +325,29 @@ __device__ __forceinline__ void strip_sums_recurrence(uint32_t sp, int dstride, 
 }
 
 // The same strip with one exponential per pixel on the reference's own float32 grid (units that contain a narrow or
-// very distant Gaussian): S0 = sum u, S1 = sum u xi, S2 = sum u xi^2 about the strip's first pixel, xi_j = x_j - x_0
-// (exact), t_j = x_j - (mu_x + nr dy) formed exactly as the direct kernels do; nsh = -(mu_x + nr dy).
+// very distant Gaussian): S0 = sum u, S1 = sum u t, S2 = sum u t^2 with t_j = x_j - (mu_x + nr dy) formed exactly as
+// the direct kernels do (nsh = -(mu_x + nr dy)) and accumulated about the Gaussian's own centre line -- a needle
+// much narrower than the strip would lose (strip length / sigma)^2 of its second moment's precision to cancellation
+// if the sums were taken about the strip's end as above.
 template <int NP, bool WITH_GMASK>
 __device__ __forceinline__ void strip_sums_direct(uint32_t sp, int dstride, bool kodd, f32x2 vm, const float (&gm)[8],
-                                                  int cstart, int dir, float h, float x0, const f32x2 (&nA)[NP],
+                                                  int cstart, int dir, float h, const f32x2 (&nA)[NP],
                                                   const f32x2 (&e)[NP], const f32x2 (&nsh)[NP], f32x2 (&S0)[NP],
                                                   f32x2 (&S1)[NP], f32x2 (&S2)[NP]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     f32x2 G[NP];
     load_unit<NP>(sp + (uint32_t)(j * dstride), kodd, vm, G);
-    const float xj = grid_coord(cstart + dir * j, h);
-    const f32x2 xi = bc(xj - x0);
+    const f32x2 xj = bc(grid_coord(cstart + dir * j, h));
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       if (WITH_GMASK) G[p] = add2(G[p], bc(gm[j]));
-      const f32x2 t = add2(bc(xj), nsh[p]);
+      const f32x2 t = add2(xj, nsh[p]);
       const f32x2 u = mul2(ex2_2(fma2(nA[p], mul2(t, t), e[p])), G[p]);
-      const f32x2 v = mul2(u, xi);
+      const f32x2 v = mul2(u, t);
       S0[p] = j == 0 ? u : add2(S0[p], u);
       S1[p] = j == 0 ? v : add2(S1[p], v);
-      S2[p] = j == 0 ? mul2(v, xi) : fma2(v, xi, S2[p]);
+      S2[p] = j == 0 ? mul2(v, t) : fma2(v, t, S2[p]);
     }
   }
 }
@@ -567,7 +568,9 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
           f32x2 nsh[NP];
 #pragma unroll
           for (int p = 0; p < NP; ++p) nsh[p] = fma2(nnr[p], dy[p], sub2(bc(0.f), mux[p]));
-          strip_sums_direct<NP, WITH_GMASK>(sp, dstride, kodd, vm, gm, cstart, dir, h, x0, nA, e, nsh, M0, M1, M2);
+          strip_sums_direct<NP, WITH_GMASK>(sp, dstride, kodd, vm, gm, cstart, dir, h, nA, e, nsh, M0, M1, M2);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) tr[p] = pack2(0.f, 0.f);      // the sums are already about t = 0
         }
         if (ss == SPT - 1) {
           __syncwarp();                                  // every lane is done with the stage

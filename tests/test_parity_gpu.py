@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star; norm-relative):
     gradients: max|g - ref|   <= 1e-4 * max|ref|
 Nothing here reads /root/reference (it does not exist on the GPU box).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -860,7 +862,7 @@ def test_randomised_nhwc_maps_forward_and_backward(gg, cuda_device):
     centres, all three Euler angles, with and without a silhouette gradient on top of the maps gradient."""
     rng = torch.Generator().manual_seed(77)
     worst_f, worst_g = 0.0, 0.0
-    for case in range(28):
+    for case in range(int(os.environ.get("GG_SWEEP_CASES", "28"))):      # larger values for a soak run
         B, K = 2, int(torch.randint(1, 25, (1,), generator=rng))
         n = 8 * int(torch.randint(1, 21, (1,), generator=rng))
         mus = ((torch.rand(B, K, 1, 3, generator=rng) - 0.5) * torch.tensor([3.0, 3.0, 1.0])).float()

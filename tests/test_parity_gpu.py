@@ -780,7 +780,7 @@ def test_randomised_shapes_and_scales_fast_mask_path(gg, cuda_device, restore_mo
     and focal: the forward-differenced kernels (with their steepness guard) stay inside the path's tolerances."""
     rng = torch.Generator().manual_seed(2024)
     worst_f, worst_g = 0.0, 0.0
-    for case in range(36):
+    for case in range(int(os.environ.get("GG_SWEEP_CASES", "36"))):      # larger values for a soak run
         B, K = 2, int(torch.randint(1, 9, (1,), generator=rng))
         n = int(torch.randint(9, 200, (1,), generator=rng))
         mus = ((torch.rand(B, K, 1, 3, generator=rng) - 0.5) * torch.tensor([3.0, 3.0, 1.0])).float()

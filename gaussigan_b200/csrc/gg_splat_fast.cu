@@ -27,8 +27,7 @@
 //
 // Backward.  Strip sums are taken about the strip's first pixel, u = g Gbar; S0 += u; S1 += u xi; S2 += u xi^2 with
 // xi_j = x_j - x_0 on the reference's grid (four packed instructions per pixel pair, only Gbar in registers), and
-// re-centred to the sheared coordinate t = t0 + xi per row.  Guarded Gaussians are summed about their own centre line
-// (u t, u t^2 with the t of the direct evaluation): re-centring a needle would cancel (strip length / sigma)^2.
+// re-centred to the sheared coordinate t = t0 + xi per row.
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
 #include "gg_fast.cuh"
@@ -342,40 +341,20 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
       const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
       f32x2 G[8];
       eval_strip(c0, c1, steep, t0, e, dy, pos.colA, h, G);
-      f32x2 S0 = mul2(G[0], W0[p][0]), m1, m2;
-      if (!steep) {
-        f32x2 u1 = mul2(G[1], W0[p][1]);
-        f32x2 S1 = mul2(u1, bc(xi1[1])), S2 = mul2(u1, bc(xi2[1]));
-        S0 = add2(S0, u1);
+      f32x2 S0 = mul2(G[0], W0[p][0]);
+      f32x2 u1 = mul2(G[1], W0[p][1]);
+      f32x2 S1 = mul2(u1, bc(xi1[1])), S2 = mul2(u1, bc(xi2[1]));
+      S0 = add2(S0, u1);
 #pragma unroll
-        for (int j = 2; j < 8; ++j) {
-          const f32x2 u = mul2(G[j], W0[p][j]);
-          S0 = add2(S0, u);
-          S1 = fma2(u, bc(xi1[j]), S1);
-          S2 = fma2(u, bc(xi2[j]), S2);
-        }
-        // strip-local moments (about x_0) -> moments of t = t0 + xi
-        m1 = fma2(t0, S0, S1);
-        m2 = fma2(t0, add2(S1, m1), S2);
-      } else {
-        // guarded Gaussian (a needle much narrower than the strip): sums about its own centre line, with the t of
-        // the direct evaluation -- re-centring from x_0 would cancel (strip length / sigma)^2 of the second moment
-        const f32x2 sh = fma2(bc(-c0.w), dy, bc(c0.x));
-        f32x2 tj = sub2(bc(x0), sh);
-        f32x2 v = mul2(S0, tj);
-        m1 = v;
-        m2 = mul2(v, tj);
-#pragma unroll
-        for (int j = 1; j < 8; ++j) {
-          const f32x2 u = mul2(G[j], W0[p][j]);
-          tj = sub2(bc(grid_coord(pos.colA + j, h)), sh);
-          v = mul2(u, tj);
-          S0 = add2(S0, u);
-          m1 = add2(m1, v);
-          m2 = fma2(v, tj, m2);
-        }
+      for (int j = 2; j < 8; ++j) {
+        const f32x2 u = mul2(G[j], W0[p][j]);
+        S0 = add2(S0, u);
+        S1 = fma2(u, bc(xi1[j]), S1);
+        S2 = fma2(u, bc(xi2[j]), S2);
       }
-      // ... then the row weights
+      // strip-local moments (about x_0) -> moments of t = t0 + xi, then the row weights
+      const f32x2 m1 = fma2(t0, S0, S1);
+      const f32x2 m2 = fma2(t0, add2(S1, m1), S2);
       const f32x2 d0 = mul2(dy, S0);
       if (p == 0) {
         P20 = m2; P10 = m1; P11 = mul2(dy, m1); P01 = d0; P02 = mul2(dy, d0);

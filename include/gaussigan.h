@@ -111,13 +111,17 @@ GG_API int gg_splat_fwd(const float *params, int B, int K, int nscales, const in
                  int device, void *stream);
 
 /* Number of [K,GG_MOMENTS] partial blocks per batch element that gg_splat_bwd writes for this
- * configuration (T); < 0 on error.  has_gmaps_host / has_gmasks_host: per-scale 0/1 flags. */
+ * configuration (T); < 0 on error.  has_gmaps_host / has_gmasks_host: per-scale 0/1 flags.  T depends
+ * on the arithmetic mode (gg_set_fast_mask): query it after the mode is set. */
 GG_API int gg_splat_bwd_tiles(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,
                        const int *has_gmasks_host, int layout);
 
 /* Backward of the raster: upstream gradients w.r.t. maps and/or masks -> per-tile partial moments
  * partials [B,T,K,GG_MOMENTS] (every slot is written; no zero-fill needed; deterministic -- no
- * atomics).  T must equal gg_splat_bwd_tiles(...) for the same arguments. */
+ * atomics; the sum over the T slots of a batch element is what gg_project_bwd / gg_conic_bwd consume,
+ * individual slots may be zero).  T must equal gg_splat_bwd_tiles(...) for the same arguments.
+ * Every K and n is accepted in both layouts; NHWC gradients of the maps with n % 8 == 0 take the
+ * bulk-copy kernel (any K <= 128 that is a multiple of 4, any other K <= 64). */
 GG_API int gg_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes_host,
                  const float *const *gmaps_host, const float *const *gmasks_host, int layout,
                  float *partials, int T, int device, void *stream);

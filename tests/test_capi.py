@@ -69,6 +69,18 @@ def test_tile_planner():
     assert lib.gg_splat_bwd_tiles(6, 1, ia([100]), ia([1]), ia([0]), 1) > 0
     # nothing requested -> zero tiles
     assert lib.gg_splat_bwd_tiles(6, 1, ia([100]), ia([0]), ia([0]), 0) == 0
+    # NHWC maps with n % 8 == 0: tiles of the persistent bulk-copy backward are sized in bytes (128 KB of upstream
+    # gradient by default), whatever K is; the direct kernels (gg_set_fast_mask(0)) plan by CTA passes instead
+    for K, n in ((16, 256), (6, 256), (12, 128), (5, 64), (64, 512), (128, 32)):
+        t = lib.gg_splat_bwd_tiles(K, 1, ia([n]), ia([1]), ia([0]), 0)
+        rows = -(-n // t)                                   # rows per tile
+        assert t == -(-n // rows) and rows * n * K * 4 <= 2 * 128 * 1024 or rows == 1, (K, n, t)
+    prev = lib.gg_set_fast_mask(0)
+    try:
+        assert lib.gg_splat_bwd_tiles(16, 1, ia([256]), ia([1]), ia([0]), 0) == 32       # 32 CTA passes of 256 quads
+        assert lib.gg_splat_bwd_tiles(6, 1, ia([256]), ia([1]), ia([0]), 0) > 0          # strip kernels
+    finally:
+        lib.gg_set_fast_mask(prev)
 
 
 def test_public_api_rejects_cpu_tensors_and_bad_shapes():

@@ -876,7 +876,7 @@ static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool
 
 int plan_bwd_tiles(int K, int nscales, const int *sizes, const int *has_gmaps, const int *has_gmasks, int layout) {
   Plan pl;
-  bool hm[GG_MAX_SCALES], hk[GG_MAX_SCALES];
+  bool hm[GG_MAX_SCALES] = {}, hk[GG_MAX_SCALES] = {};
   for (int i = 0; i < nscales; ++i) { hm[i] = has_gmaps && has_gmaps[i]; hk[i] = has_gmasks && has_gmasks[i]; }
   make_plan(pl, K, nscales, sizes, hm, hk, layout, true);
   return pl.tiles_mask + pl.tiles_maps;
@@ -908,7 +908,7 @@ static cudaError_t launch_bwd_strip(const SplatArgs &a, int gin_mode, int B, cud
 
 cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, const int *sizes, float *const *maps,
                              float *const *masks, int layout, cudaStream_t st) {
-  bool hm[GG_MAX_SCALES], hk[GG_MAX_SCALES];
+  bool hm[GG_MAX_SCALES] = {}, hk[GG_MAX_SCALES] = {};
   for (int i = 0; i < nscales; ++i) { hm[i] = maps && maps[i]; hk[i] = masks && masks[i]; }
   Plan pl;
   make_plan(pl, K, nscales, sizes, hm, hk, layout, false);
@@ -960,7 +960,7 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
 cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes,
                              const float *const *gmaps, const float *const *gmasks, int layout, float *partials,
                              int T, cudaStream_t st) {
-  bool hm[GG_MAX_SCALES], hk[GG_MAX_SCALES];
+  bool hm[GG_MAX_SCALES] = {}, hk[GG_MAX_SCALES] = {};
   for (int i = 0; i < nscales; ++i) { hm[i] = gmaps && gmaps[i]; hk[i] = gmasks && gmasks[i]; }
   Plan pl;
   make_plan(pl, K, nscales, sizes, hm, hk, layout, true);

@@ -160,7 +160,6 @@ int gg_mask_l1_loss_bwd(const float *mask, const void *target, int target_kind, 
                         float *loss_partials, int device, void *stream) {
   if (B < 0 || n < 1) return fail(GG_E_SHAPE, "gg_mask_l1_loss_bwd: bad B=%d n=%d", B, n);
   if (B == 0) return GG_OK;
-  if (((size_t)B * n * n) & 3) return fail(GG_E_SHAPE, "gg_mask_l1_loss_bwd: B*n*n must be a multiple of 4");
   if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32) return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
   if (!mask || !target || !gmask || !loss_partials) return fail(GG_E_NULL, "gg_mask_l1_loss_bwd: NULL pointer");
   if (!aligned16(mask) || !aligned16(gmask) || (reinterpret_cast<uintptr_t>(target) & 3))

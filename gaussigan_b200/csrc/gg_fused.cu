@@ -14,12 +14,22 @@ namespace gg {
 
 template <int KIND>   // 0: uint8 raw target, 1: float32 target already in [-1, 1]
 __global__ void __launch_bounds__(256) mask_l1_loss_bwd_kernel(const float *__restrict__ mask,
-                                                               const void *__restrict__ target, size_t N4,
+                                                               const void *__restrict__ target, size_t N,
                                                                float inv_n, float *__restrict__ gmask,
                                                                float *__restrict__ partials) {
   pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   __shared__ float red[8];
   float acc = 0.f;
+  const size_t N4 = N >> 2;
+  if (blockIdx.x == 0 && threadIdx.x < (N & 3)) {   // the 1-3 elements past the last whole vector
+    const size_t i = 4 * N4 + threadIdx.x;
+    const float t = KIND == 0
+        ? __fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char *>(target) + i), 127.5f), 1.0f), 1.0f), 0.5f)
+        : __fmul_rn(__fadd_rn(__ldg(reinterpret_cast<const float *>(target) + i), 1.0f), 0.5f);
+    const float r = t - __ldg(mask + i);
+    acc += fabsf(r);
+    gmask[i] = r > 0.f ? -inv_n : (r < 0.f ? inv_n : 0.f);
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 m = __ldg(reinterpret_cast<const float4 *>(mask) + i);
     float t[4];
@@ -62,10 +72,9 @@ __global__ void __launch_bounds__(256) mask_l1_loss_bwd_kernel(const float *__re
 cudaError_t launch_mask_l1_loss_bwd(const float *mask, const void *target, int kind, int B, int n, float *gmask,
                                     float *partials, int npartials, cudaStream_t st) {
   size_t N = (size_t)B * n * n;
-  if (N & 3) return cudaErrorInvalidValue;
   float inv_n = 1.0f / (float)N;
-  if (kind == 0) launch_pdl(mask_l1_loss_bwd_kernel<0>, dim3(npartials), dim3(256), 0, st, mask, target, N / 4, inv_n, gmask, partials);
-  else launch_pdl(mask_l1_loss_bwd_kernel<1>, dim3(npartials), dim3(256), 0, st, mask, target, N / 4, inv_n, gmask, partials);
+  if (kind == 0) launch_pdl(mask_l1_loss_bwd_kernel<0>, dim3(npartials), dim3(256), 0, st, mask, target, N, inv_n, gmask, partials);
+  else launch_pdl(mask_l1_loss_bwd_kernel<1>, dim3(npartials), dim3(256), 0, st, mask, target, N, inv_n, gmask, partials);
   return cudaGetLastError();
 }
 

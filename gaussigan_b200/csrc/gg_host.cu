@@ -92,7 +92,6 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
     return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
   if (target_kind == GG_TARGET_BITS && (K > 64 || !gg::fast_mask()))
     return fail(GG_E_SHAPE, "GG_TARGET_BITS: K <= 64 and the forward-differenced kernels only");
-  if (((size_t)B * n * n) & 3) return fail(GG_E_SHAPE, "gg_silhouette_step_host: B*n*n must be a multiple of 4");
   if (!mus_host || !sigma_host || !rotx_host || !roty_host || !rotz_host || !target_host || !loss_partials_host ||
       !dmus_host || !dsigma_host || !drot_host || !workspace)
     return fail(GG_E_NULL, "gg_silhouette_step_host: NULL pointer");

@@ -360,6 +360,49 @@ def test_unfused_loss_kernel_matches_fused(gg, cuda_device):
     assert torch.equal(gm.cpu(), m.grad)
 
 
+def test_randomised_fused_loss_step_equals_three_kernel_path(gg, cuda_device):
+    """Seeded sweep over (B, K <= 64, n) and the three target formats: the fused silhouette + L1 + backward kernel
+    gives the same silhouette and the same gradients, bit for bit, as splat forward -> loss kernel -> splat backward
+    (same arithmetic, same reduction order), and the same loss up to the order of the per-CTA partial sums."""
+    from gaussigan_b200._lib import lib, check
+    from gaussigan_b200.plan import SilhouetteLossStep, SilhouetteStep
+    rng = torch.Generator().manual_seed(5)
+    for case in range(int(os.environ.get("GG_SWEEP_CASES", "18"))):
+        B = int(torch.randint(1, 6, (1,), generator=rng))
+        K = int(torch.randint(1, 65, (1,), generator=rng))
+        n = int(torch.randint(1, 150, (1,), generator=rng))
+        kind = int(torch.randint(0, 3, (1,), generator=rng))          # 0: uint8, 1: float32, 2: bits
+        inp = rp.synth_inputs(B, K, seed=1000 + case)
+        d = _dev(inp, cuda_device)
+        args = (d["mus"].reshape(B, K, 3).contiguous(), d["sigma"], *(d[k].reshape(B).contiguous() for k in ("rotx", "roty", "rotz")))
+        raw = torch.randint(0, 256, (B, n, n), generator=rng, dtype=torch.uint8)
+        if kind == 0:
+            tgt = raw.to(cuda_device)
+        elif kind == 1:
+            tgt = (raw.float() / 127.5 - 1.0).to(cuda_device)
+        else:
+            raw = (raw > 127).to(torch.uint8) * 255
+            tgt = torch.from_numpy(np.packbits((raw > 0).numpy(), axis=-1, bitorder="little")).to(cuda_device)
+        fused = SilhouetteLossStep(B, K, n, cuda_device, want_mask=True)
+        fused.bind(*args)
+        fdm, fds, fdr = (t.clone() for t in fused.loss_backward(tgt, bits=kind == 2))
+        plain = SilhouetteStep(B, K, n, cuda_device)
+        plain.bind(*args)
+        mask = plain.forward()
+        gm = torch.empty_like(mask)
+        lp = torch.empty(296, device=cuda_device)
+        t3 = tgt if kind != 2 else raw.to(cuda_device)                  # the loss kernel takes uint8 / float32
+        check(lib.gg_mask_l1_loss_bwd(mask.data_ptr(), t3.data_ptr(), 1 if kind == 1 else 0, B, n, gm.data_ptr(),
+                                      lp.data_ptr(), cuda_device.index or 0,
+                                      torch.cuda.current_stream().cuda_stream), "loss")
+        pdm, pds, pdr = plain.backward(gm)
+        what = f"case {case} (B={B}, K={K}, n={n}, kind={kind})"
+        assert torch.equal(fused.mask, mask), what
+        assert torch.equal(fdm, pdm) and torch.equal(fds, pds) and torch.equal(fdr, pdr), what
+        loss3 = float(lp.double().sum()) / (B * n * n)
+        assert abs(fused.loss() - loss3) <= 1e-6 * max(abs(loss3), 1e-30), what
+
+
 # ---------------------------------------------------------------- consumers (SURVEY 8 a3-a5, 8f)
 def test_mask_recon_loss_bis_autograd(gg, cuda_device):
     B, K, n = 5, 12, 128
@@ -657,12 +700,12 @@ def test_batches_beyond_one_grid_dimension(gg, cuda_device):
     assert abs(step.loss() - want) <= 1e-6 * abs(want)
 
 
-@pytest.mark.parametrize("pinned", [True, False])
-def test_host_buffer_step_many_gaussians_and_pageable_buffers(gg, cuda_device, pinned):
+@pytest.mark.parametrize("pinned,B,n", [(True, 3, 64), (False, 3, 64), (True, 1, 33)])
+def test_host_buffer_step_many_gaussians_and_pageable_buffers(gg, cuda_device, pinned, B, n):
     """K > 64 takes the five-launch path (splat, loss kernel, splat backward); pageable host buffers take the
     copy path instead of the in-place (zero-copy) access of pinned ones.  Same numbers as the oracle either way."""
     from gaussigan_b200.host import HostInputs, HostSilhouetteStep
-    B, K, n = 3, 80, 64
+    K = 80                                              # B = 1, n = 33: a pixel count that is not a multiple of 4
     inp = rp.synth_inputs(B, K, seed=123)
     tgt = rp.synth_target_masks(B, n, seed=8)
     mask_ref, loss_ref, dmu_ref, dsig_ref, drot_ref = rp.render_loss_and_grads(inp, tgt, n)

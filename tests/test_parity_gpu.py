@@ -342,6 +342,36 @@ def test_host_buffer_step_matches_oracle(gg, cuda_device):
     assert host.h2d_bytes == B * K * 3 * 4 + B * K * 9 * 8 + 3 * B * 4 + B * n * n and host.LAUNCHES_PER_STEP == 3
 
 
+def test_randomised_host_step_equals_device_step(gg, cuda_device):
+    """Seeded sweep: the host-buffer step (pinned host arrays in, gradients out; zero-copy for the small arrays,
+    uint8 / float32 / bit-packed targets; K <= 64 fused, K > 64 five launches) returns exactly what the same kernels
+    return when driven from device tensors."""
+    from gaussigan_b200.host import HostSilhouetteStep
+    from gaussigan_b200.plan import SilhouetteLossStep
+    rng = torch.Generator().manual_seed(9)
+    for case in range(int(os.environ.get("GG_SWEEP_CASES", "12"))):
+        B = int(torch.randint(1, 6, (1,), generator=rng))
+        K = int(torch.randint(1, 65, (1,), generator=rng))
+        n = int(torch.randint(1, 130, (1,), generator=rng))
+        kind = int(torch.randint(0, 3, (1,), generator=rng))          # 0: uint8, 1: float32, 2: bits
+        inp = rp.synth_inputs(B, K, seed=2000 + case)
+        tgt = rp.synth_target_masks(B, n, seed=case)                  # {-1,+1}: exact in all three formats
+        host = HostSilhouetteStep(B, K, n, cuda_device, depth=2, want_mask=True,
+                                  target_dtype=torch.float32 if kind == 1 else torch.uint8, target_bits=kind == 2)
+        h = host.make_host_inputs(inp, tgt)
+        res = host.submit(h).wait()
+        d = _dev(inp, cuda_device)
+        step = SilhouetteLossStep(B, K, n, cuda_device, want_mask=True)
+        step.bind(d["mus"].reshape(B, K, 3).contiguous(), d["sigma"], *(d[k].reshape(B).contiguous() for k in ("rotx", "roty", "rotz")))
+        dm, ds, dr = step.loss_backward(h.target.to(cuda_device), bits=kind == 2)
+        torch.cuda.synchronize()
+        what = f"case {case} (B={B}, K={K}, n={n}, kind={kind})"
+        assert torch.equal(res.mask.cpu(), step.mask.cpu()), what
+        assert torch.equal(res.dmus.cpu(), dm.cpu()) and torch.equal(res.dsigma.cpu(), ds.cpu()), what
+        assert torch.equal(res.drot.cpu(), dr.cpu()), what
+        assert abs(res.loss - step.loss()) <= 1e-6 * max(abs(step.loss()), 1e-30), what
+
+
 def test_unfused_loss_kernel_matches_fused(gg, cuda_device):
     """gg_mask_l1_loss_bwd (used when K > 64) against the oracle's loss and Abs gradient."""
     from gaussigan_b200._lib import lib, check

@@ -489,6 +489,30 @@ def test_colorize_both_sources(gg, cuda_device):
     assert u.dtype == torch.uint8 and np.array_equal(u.cpu().numpy(), expect)
 
 
+def test_randomised_colorize_shapes(gg, cuda_device):
+    """Seeded sweep of the viz composite (mask/mask_gen_dynamic.py:221-231) over K and n (odd sizes, K not a multiple
+    of 4): from maps it is exact, from the Gaussians within the forward tolerance, and uint8 frames agree with the
+    float ones to the truncation step."""
+    rng = torch.Generator().manual_seed(21)
+    for case in range(int(os.environ.get("GG_SWEEP_CASES", "14"))):
+        B = int(torch.randint(1, 4, (1,), generator=rng))
+        K = int(torch.randint(1, 40, (1,), generator=rng))
+        n = int(torch.randint(1, 140, (1,), generator=rng))
+        inp = rp.synth_inputs(B, K, seed=3000 + case)
+        colors = torch.rand(K, 3, generator=rng)
+        maps = rp.get_landmarks(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0, 0, -2., sizes=(n,))[0]
+        ref = rp.colorize_landmark_maps(maps, colors)
+        d = _dev(inp, cuda_device)
+        what = f"case {case} (B={B}, K={K}, n={n})"
+        a = gg.colorize_landmark_maps(maps.to(cuda_device), colors.to(cuda_device))
+        assert torch.equal(a.cpu(), ref), what
+        b = gg.colorize_gaussians(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., colors.to(cuda_device), size=n)
+        assert_close_norm(b, ref, FWD_RTOL, what)
+        u = gg.colorize_gaussians(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., colors.to(cuda_device),
+                                  size=n, out="u8")
+        assert u.dtype == torch.uint8 and int((u.cpu().int() - (b.cpu() * 255).int()).abs().max()) <= 1, what
+
+
 def test_turntable_matches_per_angle_reference_loop(gg, cuda_device):
     K, n = 6, 256
     g = rp.synth_inputs(1, K, seed=56)

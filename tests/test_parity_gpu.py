@@ -80,6 +80,38 @@ def test_get_gaussian_maps_2d_vs_golden(gg, cuda_device):
         gg.get_gaussian_maps_2d(mu, sg, [32, 48])
 
 
+def test_randomised_get_gaussian_maps_2d(gg, cuda_device):
+    """Seeded sweep of the raster-only boundary (the frozen-graph inputs mu2d / sigma2d, mask/infer_masks.py:394-395):
+    K 1..24, any n, float32 and float64 inputs, positive-definite 2x2 covariances from a pixel to the frame size;
+    maps and the gradients w.r.t. mu2d and sigma2d against the oracle."""
+    rng = torch.Generator().manual_seed(31)
+    for case in range(int(os.environ.get("GG_SWEEP_CASES", "16"))):
+        B = int(torch.randint(1, 4, (1,), generator=rng))
+        K = int(torch.randint(1, 25, (1,), generator=rng))
+        n = int(torch.randint(2, 150, (1,), generator=rng))
+        dt = torch.float64 if bool(torch.randint(0, 2, (1,), generator=rng)) else torch.float32
+        mu = ((torch.rand(B, K, 2, generator=rng, dtype=torch.float64) - 0.5) * 2.4)
+        ang = torch.rand(B, K, generator=rng, dtype=torch.float64) * 3.14159
+        lo, hi = torch.log(torch.tensor(4.0 / n ** 2, dtype=torch.float64)), torch.log(torch.tensor(0.5, dtype=torch.float64))
+        var = torch.exp(torch.rand(B, K, 2, generator=rng, dtype=torch.float64) * (hi - lo) + lo)    # sigma >= 1 pixel
+        c, s_ = torch.cos(ang), torch.sin(ang)
+        R = torch.stack([torch.stack([c, -s_], -1), torch.stack([s_, c], -1)], -2)
+        sg = (R * var[..., None, :]) @ R.transpose(-1, -2)
+        mu, sg = mu.to(dt), sg.to(dt)
+        lm, ls = mu.double().clone().requires_grad_(True), sg.double().clone().requires_grad_(True)
+        ref = rp.get_gaussian_maps_2d(lm, ls, [n, n])
+        w = torch.randn(B, n, n, K, generator=rng)
+        (ref * w).sum().backward()
+        dm, ds = mu.to(cuda_device).requires_grad_(True), sg.to(cuda_device).requires_grad_(True)
+        out = gg.get_gaussian_maps_2d(dm, ds, [n, n])
+        what = f"case {case} (B={B}, K={K}, n={n}, {dt})"
+        assert_close_norm(out, ref, FWD_RTOL, what + " maps")
+        (out * w.to(cuda_device)).sum().backward()
+        assert dm.grad.dtype == dt and ds.grad.dtype == dt
+        assert_close_norm(dm.grad, lm.grad, GRAD_RTOL, what + " grad mu2d")
+        assert_close_norm(ds.grad, ls.grad, GRAD_RTOL, what + " grad sigma2d")
+
+
 # ------------------------------------------------------------------- BASELINE.json configurations
 def test_config1_forward_b16_k8_128(gg, cuda_device):
     inp = rp.synth_inputs(16, 8, seed=56)

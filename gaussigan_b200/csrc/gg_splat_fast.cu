@@ -27,7 +27,8 @@
 //
 // Backward.  Strip sums are taken about the strip's first pixel, u = g Gbar; S0 += u; S1 += u xi; S2 += u xi^2 with
 // xi_j = x_j - x_0 on the reference's grid (four packed instructions per pixel pair, only Gbar in registers), and
-// re-centred to the sheared coordinate t = t0 + xi per row.
+// re-centred to the sheared coordinate t = t0 + xi per row (CENTRE kernels, used for launches with a scale below 64
+// pixels: guarded Gaussians are summed about their own centre line instead, see the kernel).
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
 #include "gg_fast.cuh"
@@ -177,7 +178,9 @@ __global__ void __launch_bounds__(NW * 32) splat_fwd_mask_fast_kernel(const __gr
 //                against the target gives dL/dmask = -sign(0.5 (t + 1) - m) / N (mask/mask_gen_dynamic.py:785-787)
 //                and the loss partial; then the same CTA runs the backward.  K <= kKBlock.
 // NW = warps per CTA; the register cap keeps 80 registers per thread at every CTA size
-template <int NP, bool FUSED, int NW>
+// CENTRE: guarded Gaussians accumulate their moments about their own centre line (launches with a scale below 64
+//         pixels, where a guarded Gaussian can be far sub-pixel; costs 4 % of the kernel, so not at the large scales)
+template <int NP, bool FUSED, int NW, bool CENTRE>
 __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW : 1) splat_bwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
   __shared__ float4 sc[kKBlock * 3];
   __shared__ __align__(16) float stage[NW][kStageCols][kStagePad];
@@ -341,20 +344,41 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
       const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
       f32x2 G[8];
       eval_strip(c0, c1, steep, t0, e, dy, pos.colA, h, G);
-      f32x2 S0 = mul2(G[0], W0[p][0]);
-      f32x2 u1 = mul2(G[1], W0[p][1]);
-      f32x2 S1 = mul2(u1, bc(xi1[1])), S2 = mul2(u1, bc(xi2[1]));
-      S0 = add2(S0, u1);
+      f32x2 S0 = mul2(G[0], W0[p][0]), m1, m2;
+      if (!(CENTRE && steep)) {
+        f32x2 u1 = mul2(G[1], W0[p][1]);
+        f32x2 S1 = mul2(u1, bc(xi1[1])), S2 = mul2(u1, bc(xi2[1]));
+        S0 = add2(S0, u1);
 #pragma unroll
-      for (int j = 2; j < 8; ++j) {
-        const f32x2 u = mul2(G[j], W0[p][j]);
-        S0 = add2(S0, u);
-        S1 = fma2(u, bc(xi1[j]), S1);
-        S2 = fma2(u, bc(xi2[j]), S2);
+        for (int j = 2; j < 8; ++j) {
+          const f32x2 u = mul2(G[j], W0[p][j]);
+          S0 = add2(S0, u);
+          S1 = fma2(u, bc(xi1[j]), S1);
+          S2 = fma2(u, bc(xi2[j]), S2);
+        }
+        // strip-local moments (about x_0) -> moments of t = t0 + xi
+        m1 = fma2(t0, S0, S1);
+        m2 = fma2(t0, add2(S1, m1), S2);
+      } else {
+        // CENTRE kernels, guarded Gaussian (a needle much narrower than the strip): sums about its own centre line,
+        // with the t of the direct evaluation -- re-centring from x_0 cancels (strip length / sigma)^2 of the second
+        // moment, which only matters on coarse grids, where such Gaussians are sub-pixel
+        const f32x2 sh = fma2(bc(-c0.w), dy, bc(c0.x));
+        f32x2 tj = sub2(bc(x0), sh);
+        f32x2 v = mul2(S0, tj);
+        m1 = v;
+        m2 = mul2(v, tj);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+          const f32x2 u = mul2(G[j], W0[p][j]);
+          tj = sub2(bc(grid_coord(pos.colA + j, h)), sh);
+          v = mul2(u, tj);
+          S0 = add2(S0, u);
+          m1 = add2(m1, v);
+          m2 = fma2(v, tj, m2);
+        }
       }
-      // strip-local moments (about x_0) -> moments of t = t0 + xi, then the row weights
-      const f32x2 m1 = fma2(t0, S0, S1);
-      const f32x2 m2 = fma2(t0, add2(S1, m1), S2);
+      // ... then the row weights
       const f32x2 d0 = mul2(dy, S0);
       if (p == 0) {
         P20 = m2; P10 = m1; P11 = mul2(dy, m1); P01 = d0; P02 = mul2(dy, d0);
@@ -410,20 +434,22 @@ cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_
   return cudaGetLastError();
 }
 
-template <bool FUSED>
+template <bool FUSED, bool CENTRE>
 static void launch_bwd_fast_t(const SplatArgs &a, dim3 grid, int rpt, cudaStream_t st) {
   const int cta = a.sc[0].cta;
-  if (rpt == 4) launch_pdl(splat_bwd_mask_fast_kernel<2, FUSED, 8>, grid, dim3(256), 0, st, a);
-  else if (cta == 128) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 4>, grid, dim3(128), 0, st, a);
-  else if (cta == 160) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 5>, grid, dim3(160), 0, st, a);
-  else if (cta == 192) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 6>, grid, dim3(192), 0, st, a);
-  else launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 8>, grid, dim3(256), 0, st, a);
+  if (rpt == 4) launch_pdl(splat_bwd_mask_fast_kernel<2, FUSED, 8, CENTRE>, grid, dim3(256), 0, st, a);
+  else if (cta == 128) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 4, CENTRE>, grid, dim3(128), 0, st, a);
+  else if (cta == 160) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 5, CENTRE>, grid, dim3(160), 0, st, a);
+  else if (cta == 192) launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 6, CENTRE>, grid, dim3(192), 0, st, a);
+  else launch_pdl(splat_bwd_mask_fast_kernel<1, FUSED, 8, CENTRE>, grid, dim3(256), 0, st, a);
 }
 
 cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)B * a.T), (unsigned)((a.K + kKBlock - 1) / kKBlock));
-  if (fused) launch_bwd_fast_t<true>(a, grid, rpt, st);
-  else launch_bwd_fast_t<false>(a, grid, rpt, st);
+  bool coarse = false;      // a scale below 64 pixels: guarded Gaussians can be far sub-pixel there
+  for (int i = 0; i < a.nscales; ++i) coarse = coarse || a.sc[i].n < 64;
+  if (fused) { if (coarse) launch_bwd_fast_t<true, true>(a, grid, rpt, st); else launch_bwd_fast_t<true, false>(a, grid, rpt, st); }
+  else { if (coarse) launch_bwd_fast_t<false, true>(a, grid, rpt, st); else launch_bwd_fast_t<false, false>(a, grid, rpt, st); }
   return cudaGetLastError();
 }
 

@@ -1047,12 +1047,12 @@ def test_second_device_in_the_same_process(gg, cuda_device):
             assert torch.equal(a, b)
 
 
-def test_planned_dynamic_object_step_equals_autograd_chain(gg, cuda_device):
+@pytest.mark.parametrize("B,K,n", [(5, 16, 96), (1, 1, 8), (3, 6, 33), (2, 12, 40), (4, 37, 64), (2, 64, 17)])
+def test_planned_dynamic_object_step_equals_autograd_chain(gg, cuda_device, B, K, n):
     """DynamicObjectStep (config 3 as a fixed launch sequence, graph-captured) against the autograd chain
     sigma_from_frame -> deform -> mask_recon_loss_bis, which test_config3_full_cuda_pipeline pins to the oracle."""
     from gaussigan_b200.plan import DynamicObjectStep
-    B, K, n = 5, 16, 96
-    g = torch.Generator().manual_seed(77)
+    g = torch.Generator().manual_seed(77 + K)
     th = lambda *s: torch.tanh(torch.randn(*s, generator=g)).to(cuda_device)
     v0, v1, u_raw, cmu = th(K, 3), th(K, 3), torch.randn(K, 3, generator=g).to(cuda_device), th(K, 3)
     mu_t, scale, ang, theta_raw = th(B, K, 3), th(B, K, 3), th(B, K, 3), th(B)

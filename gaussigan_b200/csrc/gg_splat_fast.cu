@@ -13,7 +13,7 @@
 // same quantity for the two rows, so the whole per-(Gaussian,row) set-up (dy, t0, the two exponents), the
 // recurrence and the moment folding run as packed FFMA2/FMUL2/FADD2: half the issue slots of the scalar form.
 //
-// Accuracy (tools/study/recurrence_accuracy.py, float32 emulation against the float64 oracle, reference
+// Accuracy (tests/studies/recurrence_accuracy.py, float32 emulation against the float64 oracle, reference
 // activation ranges): silhouette max|err|/max = 8e-7 (direct form: 1e-7; tolerance 1e-5).
 //
 // Guard.  The recurrence is only used where the per-pixel change of the exponent is small,

@@ -1,7 +1,7 @@
 """Accuracy of the forward-differenced kernels against the direct ones on the GPU (development study): seeded sweeps
 over coarse (8-24 px) and reference-sized (32-64 px) grids, Gaussians from far sub-pixel to larger than the frame; prints
 the worst gradient errors of both arithmetic modes against the float64 oracle.  Found the re-centring cancellation of
-guarded Gaussians.  Run on a GPU box: python tools/study/fast_vs_direct_accuracy.py"""
+guarded Gaussians.  Run on a GPU box: python tests/studies/fast_vs_direct_accuracy.py"""
 import sys, torch
 import os; ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import gaussigan_b200 as gg

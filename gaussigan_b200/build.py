@@ -62,15 +62,31 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     fp = _fingerprint()
     if not force and out.exists() and stamp.exists() and stamp.read_text().strip() == fp:
         return out
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(out), *map(str, _sources())]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    # one object per translation unit, compiled concurrently (the serial build is ~45 s), then one link
+    objdir = LIBDIR / "obj"
+    objdir.mkdir(exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src: Path):
+        obj = objdir / (src.stem + ".o")
+        cmd = [_nvcc(), *cflags, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        done = list(pool.map(compile_one, _sources()))
+    for src, obj, res in done:
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name} ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+        if verbose:
+            print(f"== {src.name}\n{res.stderr}", file=sys.stderr)
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *[str(o) for _, o, _ in done]]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr, file=sys.stderr)
+        raise RuntimeError(f"link failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
     stamp.write_text(fp)
     return out
 

@@ -10,8 +10,10 @@ One "step" = one pass of the hot path over one batch: projection -> splat (sum-c
 angles (mask/mask_gen_dynamic.py:233-323, 785-786 and their tf.gradients).
 
 Numbers on the JSON line
-  value     whole-job silhouettes/s with inputs resident in HBM; each step is one CUDA-graph replay of the
-            4 kernels; R rotating buffer sets (> L2) so no step re-reads what the previous one left in L2.
+  value     whole-job silhouettes/s with inputs resident in HBM.  The K steps of --steps are captured as CUDA-graph
+            chains (4 kernels per step, programmatic-dependent-launch edges) over R rotating buffer sets (> L2); that
+            K-step pass is repeated until the timed region is >= 0.5 s, every repetition device-timed, and the
+            MEDIAN repetition is reported (max over ranks per repetition).
   e2e       same metric through the public host-buffer call (gaussigan_b200.host.HostSilhouetteStep):
             pinned-host inputs copied H2D and loss+gradients copied D2H inside the timed region, every step.
   roofline  dominant kernel (backward splat): algorithmic issue slots / measured duration vs the FP32 issue
@@ -78,7 +80,7 @@ class ClockSampler:
             return None
         time.sleep(0.12)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if (t0 is None or t0 <= t <= t1)] or [r for _, r in self.rows]
+        rows = [r for t, r in self.rows if (t0 is None or t0 <= t <= t1)]      # samples INSIDE the timed region only
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -111,13 +113,16 @@ def cpu_oracle_rate(budget_s: float, sample_B: int, min_iters: int = 2):
         times.append(time.perf_counter() - t0)
         if len(times) >= 50:
             break
-    best = min(times)
-    return dict(value=sample_B / best, unit=UNIT, cores=cores, kind="port",
+    mean = sum(times) / len(times)
+    return dict(value=sample_B / mean, best_value=sample_B / min(times), unit=UNIT, cores=cores, kind="port",
                 sample=f"{sample_B} of {B_PER_GPU} silhouettes of the C2 batch (K={K_GAUSS}, {SIZE}x{SIZE}, fwd+bwd, "
-                       f"float64 torch-CPU restatement of the reference), best of {len(times)} passes")
+                       f"float64 torch-CPU restatement of the reference), mean of {len(times)} passes (best_value = best pass)")
 
 
 def run_reference(args):
+    """The reference algorithm (float64 torch-CPU restatement, all host threads) on the SAME config as the GPU arm:
+    every step is the full batch of 64 silhouettes, evaluated as 4 chunks of 16 to bound host memory (the renderer
+    has no cross-sample term, so the chunks are the same arithmetic)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -125,26 +130,38 @@ def run_reference(args):
     from oracle import reference_port as rp
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_B = 16
-    inp = rp.synth_inputs(sample_B, K_GAUSS, seed=56)
-    tgt = rp.synth_target_masks(sample_B, SIZE)
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 2))
+    chunk = 16
+    inp = rp.synth_inputs(B_PER_GPU, K_GAUSS, seed=56)
+    tgt = rp.synth_target_masks(B_PER_GPU, SIZE)
+    chunks = [({k: v[i:i + chunk] for k, v in inp.items()}, tgt[i:i + chunk]) for i in range(0, B_PER_GPU, chunk)]
+
+    def one_step():
+        for ci, ct in chunks:
+            rp.render_loss_and_grads(ci, ct, SIZE)
+
+    steps = max(1, min(args.steps, 40))          # ~0.9 s per step on 16 cores: the whole run stays within a minute or so
+    warm = max(1, min(args.warmup, 5))
     for _ in range(warm):
-        rp.render_loss_and_grads(inp, tgt, SIZE)
-    t0 = time.perf_counter()
+        one_step()
+    times = []
     for _ in range(steps):
-        rp.render_loss_and_grads(inp, tgt, SIZE)
-    dt = (time.perf_counter() - t0) / steps
-    val = sample_B / dt
-    sample = (f"each step = {sample_B} of {B_PER_GPU} silhouettes of the C2 batch, fwd+bwd, float64 torch-CPU "
-              f"restatement of mask/mask_gen_dynamic.py:112-143,233-323,785-787 (TensorFlow 1.12 is not installable)")
+        t0 = time.perf_counter()
+        one_step()
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / steps
+    val = B_PER_GPU / dt
+    sample = (f"each step = the full C2 batch ({B_PER_GPU} silhouettes, K={K_GAUSS}, {SIZE}x{SIZE}, fwd+bwd) in "
+              f"{len(chunks)} chunks of {chunk}; float64 torch-CPU restatement of "
+              f"mask/mask_gen_dynamic.py:112-143,233-323,785-787 (TensorFlow 1.12 is not installable); value = mean over "
+              f"the {steps} timed steps, best step {B_PER_GPU / min(times):.1f} silhouettes/s")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"mask renderer fwd+bwd, batch {B_PER_GPU}, K={K_GAUSS}, {SIZE}x{SIZE} (BASELINE configs[1])",
-                   "sample_batch": sample_B},
+        "config": {"workload": f"mask renderer fwd+bwd, batch {B_PER_GPU} per GPU, K={K_GAUSS}, {SIZE}x{SIZE} (BASELINE configs[1]); "
+                               "projection in float64, splat in float32",
+                   "global_batch": B_PER_GPU, "steps_requested": args.steps, "warmup_requested": args.warmup},
+        "best_value": B_PER_GPU / min(times),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -152,12 +169,18 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+CHAIN_MAX = 256          # steps per captured CUDA graph (4 kernel nodes each); longer step counts replay it
+MIN_REGION_S = 0.5       # every timed region lasts at least this long
+
+
 def run_gpu(args):
+    import math
     import torch
     import torch.distributed as dist
     from gaussigan_b200.plan import SilhouetteStep
     from gaussigan_b200.host import HostSilhouetteStep
     from gaussigan_b200 import synth              # synthetic inputs; the oracle is used by the cpu_baseline leg only
+    from gaussigan_b200._lib import lib, check, ptr_array, int_array, LAYOUT_NHWC
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -166,10 +189,14 @@ def run_gpu(args):
         sys.exit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from gaussigan_b200.host import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local)           # before any pinned allocation: host buffers land next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, n = B_PER_GPU, K_GAUSS, SIZE
     peaks = _peaks()
+    KSTEPS = max(1, args.steps)
+    WARM = max(3, args.warmup)
 
     # ---- synthetic inputs of the reference's activation ranges, R rotating sets (inputs > L2)
     R = args.rotate
@@ -184,7 +211,6 @@ def run_gpu(args):
         step.bind(mus, sig, rx, ry, rz)
         # upstream gradient of mean|0.5*(t+1) - m| w.r.t. m for a random-sign residual
         gm = (-(torch.sign(torch.randn(B, n, n, device=dev))) / float(B * n * n)).contiguous()
-        step.capture(gm)
         sets.append((step, gm, inp, tgt))
     rot_bytes = R * 2 * B * n * n * 4
 
@@ -193,57 +219,81 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- R * ROUNDS consecutive steps (cycling through the buffer sets) captured into ONE graph: the programmatic-dependent-launch
-    # edges between kernels then also span step boundaries; the remainder of the step count replays single steps
-    def capture_chain(steps_fn):
+    def max_over_ranks(values):
+        t = torch.tensor(values, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def capture(fn):
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            steps_fn()
+            fn()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            steps_fn()
+            fn()
         return g
 
-    ROUNDS = 4                      # passes over the R buffer sets per graph: R * ROUNDS steps per replay
+    def make_pass(step_fn, nsteps):
+        """A callable that enqueues EXACTLY ``nsteps`` consecutive steps: step i is ``step_fn(i)`` (buffer set i % R).
+        The steps are captured in CUDA graphs of up to CHAIN_MAX steps, so the programmatic-dependent-launch edges
+        between kernels also span step boundaries."""
+        C = min(nsteps, CHAIN_MAX)
+        main = capture(lambda: [step_fn(i) for i in range(C)])
+        rem = nsteps % C
+        tail = capture(lambda: [step_fn(i) for i in range(rem)]) if rem else None
 
-    def all_sets_once():
-        for _ in range(ROUNDS):
-            for st_, gm_, _, _ in sets:
-                st_.forward()
-                st_.backward(gm_)
+        def run_pass():
+            for _ in range(nsteps // C):
+                main.replay()
+            if tail is not None:
+                tail.replay()
+        run_pass.graphs = (main, tail)
+        return run_pass
 
-    chain = capture_chain(all_sets_once)
+    def timed_passes(run_pass, steps_per_pass, warm_steps=WARM, sampler=None):
+        """Warm up (>= warm_steps steps), then repeat the pass until the region lasts >= MIN_REGION_S (same count on
+        every rank); every pass is timed with CUDA events on the launch stream, max over ranks per pass."""
+        for _ in range(max(1, math.ceil(warm_steps / steps_per_pass))):
+            run_pass()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(); run_pass(); c1.record()
+        torch.cuda.synchronize(dev)
+        t_cal = max_over_ranks([c0.elapsed_time(c1)])[0] * 1e-3
+        reps = int(min(max(3, math.ceil(MIN_REGION_S / max(t_cal, 1e-6))), 50000))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.15)
+        barrier()
+        w0 = time.perf_counter()
+        ev[0].record()
+        for r in range(reps):
+            run_pass()
+            ev[r + 1].record()
+        barrier()
+        w1 = time.perf_counter()
+        per_pass = max_over_ranks([ev[r].elapsed_time(ev[r + 1]) for r in range(reps)])
+        med = statistics.median(per_pass)
+        return {"ms_per_step": med / steps_per_pass, "best_ms_per_step": min(per_pass) / steps_per_pass,
+                "mean_ms_per_step": sum(per_pass) / reps / steps_per_pass, "reps": reps,
+                "timed_region_s": sum(per_pass) * 1e-3, "wall": (w0, w1)}
 
-    def run_steps(nsteps):
-        for _ in range(nsteps // (R * ROUNDS)):
-            chain.replay()
-        for i in range(nsteps % (R * ROUNDS)):
-            sets[i % R][0].graph.replay()
+    # ---- headline: EXACTLY --steps consecutive steps per pass, strictly one after the other
+    def plain_step(i):
+        st_, gm_, _, _ = sets[i % R]
+        st_.forward()
+        st_.backward(gm_)
 
-    # ---- timed region: W warm-up steps, then exactly K steps, device-timed, max over ranks
-    run_steps(max(3, args.warmup))
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    ms_per_step = ms / args.steps
+    headline_pass = make_pass(plain_step, KSTEPS)
+    sampler = ClockSampler(local) if rank == 0 else None
+    hl = timed_passes(headline_pass, KSTEPS, sampler=sampler)
+    clocks = sampler.stop(*hl["wall"]) if rank == 0 else None
+    ms_per_step = hl["ms_per_step"]
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- secondary: the same steps as TWO independent chains inside one graph (even / odd buffer sets on two
@@ -252,69 +302,51 @@ def run_gpu(args):
     # `value` above executes the steps strictly one after the other.
     two_chains = None
     try:
+        NTC = min(max(2 * R, (KSTEPS // 2) * 2), CHAIN_MAX)
+
         def forked_sets():
             cur = torch.cuda.current_stream(dev)
             s2 = torch.cuda.Stream(dev)
             s2.wait_stream(cur)
-            for _ in range(ROUNDS):
-                for j, (st_, gm_, _, _) in enumerate(sets):
-                    with torch.cuda.stream(s2 if j % 2 else cur):
-                        st_.forward()
-                        st_.backward(gm_)
+            for j in range(NTC):
+                st_, gm_, _, _ = sets[j % R]
+                with torch.cuda.stream(s2 if j % 2 else cur):
+                    st_.forward()
+                    st_.backward(gm_)
             cur.wait_stream(s2)
 
-        fork_chain = capture_chain(forked_sets)
-        nrep = max(1, args.steps // (R * ROUNDS))
-        for _ in range(3):
-            fork_chain.replay()
-        barrier()
-        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a_.record()
-        for _ in range(nrep):
-            fork_chain.replay()
-        b_.record()
-        barrier()
-        tms = a_.elapsed_time(b_) / (nrep * R * ROUNDS)
-        if world > 1:
-            t = torch.tensor([tms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tms = float(t.item())
-        two_chains = {"value": world * B / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms,
+        fork_chain = capture(forked_sets)
+        tc = timed_passes(fork_chain.replay, NTC)
+        two_chains = {"value": world * B / (tc["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": tc["ms_per_step"],
+                      "steps_per_pass": NTC, "reps": tc["reps"],
                       "note": "same steps, two independent chains (even/odd batches) in one CUDA graph"}
         del fork_chain
     except Exception as exc:                      # pragma: no cover
         two_chains = {"value": None, "error": repr(exc)}
 
     # ---- dominant kernel (backward splat) alone, same rotating buffers, CUDA events on the launch stream
-    from gaussigan_b200._lib import lib, check, ptr_array, LAYOUT_NHWC
-    st = torch.cuda.current_stream(dev).cuda_stream
+    st = lambda: torch.cuda.current_stream(dev).cuda_stream      # looked up per call: captures run on a side stream
     gps = [ptr_array([s[1].data_ptr()]) for s in sets]
 
     def bwd_only(i):
         s = sets[i % R][0]
         check(lib.gg_splat_bwd(s.params.data_ptr(), B, K, 1, s._sizes, s._null_ptrs, gps[i % R], LAYOUT_NHWC,
-                               s.partials.data_ptr(), s.T, dev.index, st), "gg_splat_bwd")
+                               s.partials.data_ptr(), s.T, dev.index, st()), "gg_splat_bwd")
 
     def fwd_only(i):
         s = sets[i % R][0]
         check(lib.gg_splat_fwd(s.params.data_ptr(), B, K, 1, s._sizes, s._null_ptrs, s._mask_ptrs, LAYOUT_NHWC,
-                               dev.index, st), "gg_splat_fwd")
+                               dev.index, st()), "gg_splat_fwd")
 
-    def kernel_us(fn, reps):
-        for i in range(5):
-            fn(i)
-        torch.cuda.synchronize(dev)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(reps):
-            fn(i)
-        b.record()
-        torch.cuda.synchronize(dev)
-        return a.elapsed_time(b) / reps * 1e3
+    def kernel_us(fn, nlaunch=64):
+        """Average duration of one launch of ``fn`` inside a graph of ``nlaunch`` back-to-back launches (rotating
+        buffers; consecutive launches are chained by programmatic dependent launch, as in the step)."""
+        g = capture(lambda: [fn(i) for i in range(nlaunch)])
+        r = timed_passes(g.replay, nlaunch, warm_steps=nlaunch)
+        return r["ms_per_step"] * 1e3
 
-    reps = max(20, min(args.steps, 200))
-    us_bwd = kernel_us(bwd_only, reps)
-    us_fwd = kernel_us(fwd_only, reps)
+    us_bwd = kernel_us(bwd_only)
+    us_fwd = kernel_us(fwd_only)
     pxk = B * n * n * K
     issue_peak = SM_COUNT * FP32_LANES * peaks["sm_max_mhz"] * 1e6              # lane issue slots / s
     ach = SLOTS_BWD * pxk / (us_bwd * 1e-6)
@@ -324,9 +356,9 @@ def run_gpu(args):
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get("splat_bwd_mask_dram_bytes_per_launch")
-    # executed FP32-pipe work of the forward-differenced kernels, counted in their SASS inner loops:
-    # backward 55 packed + 6 scalar FP32-pipe instructions per (Gaussian, 2 rows x 8 px) = 7.3 lane-ops per
-    # (pixel, Gaussian); forward 27 packed + 4 scalar = 3.6.  The pipe retires 128 lane-ops/clk/SM.
+    # executed FP32-pipe work of the forward-differenced kernels, counted in their SASS inner loops (DESIGN.md 4,
+    # profiles/r2_sass_*): backward 55 packed + 6 scalar FP32-pipe instructions per (Gaussian, 2 rows x 8 px) = 7.3
+    # lane-ops per (pixel, Gaussian); forward 27 packed + 4 scalar = 3.6.  The pipe retires 128 lane-ops/clk/SM.
     EXEC_BWD, EXEC_FWD = 7.3, 3.6
     roofline = {
         "kernel": "gg::splat_bwd_mask_fast_kernel (mask gradient -> per-Gaussian moments, forward-differenced strips)",
@@ -334,6 +366,8 @@ def run_gpu(args):
         "achieved": ach / 1e12, "peak": issue_peak / 1e12,
         "unit": "T lane-slots/s (17 algorithmic issue slots per pixel-Gaussian, SURVEY.md 8d)",
         "frac": ach / issue_peak, "traffic": traffic, "us_per_launch": us_bwd,
+        "us_per_launch_note": "average over a CUDA graph of 64 back-to-back launches on rotating buffers, chained by "
+                              "programmatic dependent launch (the next launch's prologue overlaps this one's tail)",
         "peak_source": f"148 SMs x 128 FP32 lanes x sm_max_mhz ({peaks['source']} MEASURED_PEAKS.json); no tensor cores: not a contraction",
         "note": "frac > 1 is expected: the kernel forward-differences the Gaussians along each strip, so it executes "
                 "7.3 FP32 lane-ops + 0.25 MUFU.EX2 per pixel-Gaussian instead of the 17 slots of the algorithmic count",
@@ -359,37 +393,17 @@ def run_gpu(args):
             fs = SilhouetteLossStep(B, K, n, dev)
             fs.bind(*st_._inputs)
             raw = ((tgt.reshape(B, n, n) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).to(dev)
-            fs.capture_loss(raw)
             fsets.append((fs, raw))
-        def all_fused_once():
-            for _ in range(ROUNDS):
-                for fs_, raw_ in fsets:
-                    fs_.loss_backward(raw_)
 
-        fchain = capture_chain(all_fused_once)
+        def fused_step(i):
+            fs_, raw_ = fsets[i % R]
+            fs_.loss_backward(raw_)
 
-        def run_fused(nsteps):
-            for _ in range(nsteps // (R * ROUNDS)):
-                fchain.replay()
-            for i in range(nsteps % (R * ROUNDS)):
-                fsets[i % R][0].graph.replay()
-
-        run_fused(2 * R + 1)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        run_fused(args.steps)
-        b.record()
-        barrier()
-        fms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([fms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            fms = float(t.item())
-        fused = {"value": world * B / (fms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": fms / args.steps,
-                 "launches_per_step": SilhouetteLossStep.LAUNCHES_PER_STEP,
+        fr = timed_passes(make_pass(fused_step, KSTEPS), KSTEPS)
+        fused = {"value": world * B / (fr["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": fr["ms_per_step"],
+                 "launches_per_step": SilhouetteLossStep.LAUNCHES_PER_STEP, "reps": fr["reps"],
                  "note": "mask_recon_loss_bis fused into the splat kernel: the silhouette and dL/dmask never reach HBM"}
-        del fsets, fchain
+        del fsets
     except Exception as exc:                      # pragma: no cover
         fused = {"value": None, "error": repr(exc)}
 
@@ -397,7 +411,6 @@ def run_gpu(args):
     # forward and read back as upstream gradients by the backward; kernels alone, two rotating buffers (> L2)
     maps_mode = None
     try:
-        from gaussigan_b200._lib import int_array
         mbufs = [torch.randn((B, n, n, K), device=dev) for _ in range(2)]
         mptrs = [ptr_array([m.data_ptr()]) for m in mbufs]
         msz, mnull = int_array((n,)), ptr_array([None])
@@ -407,13 +420,13 @@ def run_gpu(args):
 
         def maps_bwd(i):
             check(lib.gg_splat_bwd(p0.data_ptr(), B, K, 1, msz, mptrs[i % 2], mnull, LAYOUT_NHWC, mpart.data_ptr(), mT,
-                                   dev.index, st), "gg_splat_bwd(maps)")
+                                   dev.index, st()), "gg_splat_bwd(maps)")
 
         def maps_fwd(i):
-            check(lib.gg_splat_fwd(p0.data_ptr(), B, K, 1, msz, mptrs[i % 2], mnull, LAYOUT_NHWC, dev.index, st),
+            check(lib.gg_splat_fwd(p0.data_ptr(), B, K, 1, msz, mptrs[i % 2], mnull, LAYOUT_NHWC, dev.index, st()),
                   "gg_splat_fwd(maps)")
 
-        us_mb, us_mf = kernel_us(maps_bwd, 20), kernel_us(maps_fwd, 20)
+        us_mb, us_mf = kernel_us(maps_bwd, 16), kernel_us(maps_fwd, 16)
         mbytes = B * n * n * K * 4
         maps_mode = {"workload": f"NHWC maps [{B},{n},{n},{K}] float32, {mbytes / 1e6:.0f} MB per launch, kernels alone",
                      "bwd_us": us_mb, "bwd_gbs": mbytes / us_mb / 1e3, "bwd_frac_of_hbm": mbytes / us_mb / 1e3 / peaks["hbm_gbs"],
@@ -425,86 +438,49 @@ def run_gpu(args):
         maps_mode = {"error": repr(exc)}
 
     # ---- training-time exchange: the shared (canonical-Gaussian) gradients summed over batch and ranks after every step.
-    # (a) gaussigan_b200.dist.P2PSharedGradReducer: one single-CTA kernel over NVLink peer memory, captured in the same
-    #     graph as the steps; (b) the same with a local torch sum + one NCCL all_reduce per step (eager).
+    # (a) gaussigan_b200.dist.P2PSharedGradReducer: peer-memory kernels over NVLink captured in the same graph as the
+    #     steps; (b) the same with a local torch sum + one NCCL all_reduce per step (eager).
     allreduce = None
     if world > 1:
-        from gaussigan_b200.dist import P2PSharedGradReducer, reduce_shared_grads
-
-        def timed(run, nsteps):
-            run(2 * R * ROUNDS)
-            barrier()
-            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a_.record()
-            run(nsteps)
-            b_.record()
-            barrier()
-            t_ = torch.tensor([a_.elapsed_time(b_)], device=dev, dtype=torch.float64)
-            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-            return float(t_.item()) / nsteps
-
-        def nccl_steps(nsteps):
-            for i in range(nsteps):
-                s0 = sets[i % R][0]
-                s0.graph.replay()
-                reduce_shared_grads([s0.dmus, s0.dsigma])
-
-        nsteps = (args.steps // (R * ROUNDS)) * (R * ROUNDS) or R * ROUNDS      # same count on every rank, whole graphs
-        ams = timed(nccl_steps, nsteps)
-        allreduce = {"nccl": {"value": world * B / (ams * 1e-3), "unit": UNIT, "ms_per_step": ams,
-                              "note": "local torch sum + one eager NCCL all_reduce(SUM) per step"},
-                     "payload_bytes": K * 12 * 8}
-        try:
-            red = P2PSharedGradReducer(K, dev)
-
-            def steps_with_exchange():
-                for _ in range(ROUNDS):
-                    for st_, gm_, _, _ in sets:
-                        st_.forward()
-                        st_.backward(gm_)
-                        red(st_.dmus, st_.dsigma)
-
-            pchain = capture_chain(steps_with_exchange)
-            dist.barrier()
-
-            def p2p_steps(nsteps_):
-                for _ in range(nsteps_ // (R * ROUNDS)):
-                    pchain.replay()
-
-            pms = timed(p2p_steps, nsteps)
-            red.check()
-            allreduce.update({"value": world * B / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms,
-                              "note": "every step followed by gg_shared_grad_allreduce_p2p (one kernel: local batch sum, "
-                                      "stores into the peers' slots over NVLink, flag exchange, rank-ordered sum), all in "
-                                      "the step graph"})
-            del pchain
-        except Exception as exc:                  # pragma: no cover - e.g. no peer access
-            allreduce.update({"value": allreduce["nccl"]["value"], "unit": UNIT, "ms_per_step": ams,
-                              "note": "P2P reducer unavailable (" + repr(exc)[:120] + "): NCCL number"})
+        allreduce = bench_allreduce(args, sets, R, B, K, world, dev, capture, timed_passes, make_pass, KSTEPS)
 
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
-    e2e = None
-    try:
-        host = HostSilhouetteStep(B, K, n, dev, depth=6)
+    def e2e_leg(target_bits):
+        host = HostSilhouetteStep(B, K, n, dev, depth=6, target_bits=target_bits)
         hsets = [host.make_host_inputs(s[2], s[3]) for s in sets[:min(R, 4)]]
         # the first transfers out of freshly pinned buffers run at a fraction of the steady PCIe rate on this pool's
         # hosts (measured: 390 us per 4 MiB for the first ~100 copies, ~110 us after): warm the path up properly
-        for i in range(max(1500, args.warmup)):
+        for i in range(max(1500, WARM)):
             host.submit(hsets[i % len(hsets)])
         host.drain()
         barrier()
+        # calibrate, then ONE timed region of `passes` x --steps consecutive submits (>= MIN_REGION_S), drained once
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(64):
+            host.submit(hsets[i % len(hsets)])
+        host.drain()
+        c1.record()
+        torch.cuda.synchronize(dev)
+        t_step = max_over_ranks([c0.elapsed_time(c1) / 64.0])[0] * 1e-3
+        passes = int(min(max(1, math.ceil(MIN_REGION_S / max(t_step * KSTEPS, 1e-6))), 100000))
+        nsub = passes * KSTEPS
+        barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(args.steps):
+        for i in range(nsub):
             host.submit(hsets[i % len(hsets)])
         host.drain()
         b.record()
         barrier()
-        ems = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ems], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
+        ems = max_over_ranks([a.elapsed_time(b)])[0]
+        return host, hsets, {"value": world * B / (ems / nsub * 1e-3), "unit": UNIT, "ms_per_step": ems / nsub,
+                             "steps_timed": nsub, "timed_region_s": ems * 1e-3,
+                             "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes}
+
+    e2e = None
+    try:
+        host, hsets, e2e = e2e_leg(False)
         # raw pinned-host -> device bandwidth for the target masks of one step, issued the way the e2e path issues them
         # (one copy per slot stream): what bounds the e2e number
         hb = hsets[0].target
@@ -521,20 +497,20 @@ def run_gpu(args):
                 cur.wait_stream(st_)
 
         copies(200)
-        torch.cuda.synchronize(dev)
+        barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        copies(200)
+        copies(400)
         c1.record()
-        torch.cuda.synchronize(dev)
-        h2d_us = c0.elapsed_time(c1) / 200 * 1e3
-        e2e = {"value": world * B / (ems / args.steps * 1e-3), "unit": UNIT,
-               "h2d_copy_alone_us": h2d_us, "h2d_copy_alone_gbs": hb.numel() * hb.element_size() / (h2d_us * 1e-6) / 1e9,
-               "bound": "PCIe host->device copy of the uint8 target masks (4.19 MB/step): compare ms_per_step with "
-                        "h2d_copy_alone_us (the same copies alone, one per slot stream, no kernels)",
-               "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
-               "ms_per_step": ems / args.steps, "api": "gaussigan_b200.host.HostSilhouetteStep.submit (pinned host buffers)",
-               "launches_per_step": host.LAUNCHES_PER_STEP}
+        barrier()
+        h2d_us = max_over_ranks([c0.elapsed_time(c1) / 400 * 1e3])[0]
+        e2e.update({"h2d_copy_alone_us": h2d_us,
+                    "h2d_copy_alone_gbs": hb.numel() * hb.element_size() / (h2d_us * 1e-6) / 1e9,
+                    "bound": "PCIe host->device copy of the uint8 target masks (4.19 MB/step): compare ms_per_step with "
+                             "h2d_copy_alone_us (the same copies alone, one per slot stream, all ranks at once, no kernels)",
+                    "api": "gaussigan_b200.host.HostSilhouetteStep.submit (pinned host buffers) -> gg_silhouette_step_host",
+                    "launches_per_step": host.LAUNCHES_PER_STEP, "host_numa": numa})
+        del host, hsets, dbs
     except Exception as exc:                      # pragma: no cover - reported, never hidden
         e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
 
@@ -543,55 +519,241 @@ def run_gpu(args):
     # 8-bit images, so the headline e2e above stays on uint8 targets.
     e2e_bits = None
     try:
-        hostb = HostSilhouetteStep(B, K, n, dev, depth=6, target_bits=True)
-        hsb = [hostb.make_host_inputs(s[2], s[3]) for s in sets[:min(R, 4)]]
-        for i in range(500):
-            hostb.submit(hsb[i % len(hsb)])
-        hostb.drain()
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(args.steps):
-            hostb.submit(hsb[i % len(hsb)])
-        hostb.drain()
-        b.record()
-        barrier()
-        bms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([bms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            bms = float(t.item())
-        e2e_bits = {"value": world * B / (bms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": bms / args.steps,
-                    "h2d_bytes_per_step": hostb.h2d_bytes, "d2h_bytes_per_step": hostb.d2h_bytes,
-                    "note": "binary target masks packed 1 bit/pixel (lossless for the synthetic discs; not the reference's format)"}
+        _, _, e2e_bits = e2e_leg(True)
+        e2e_bits["note"] = "binary target masks packed 1 bit/pixel (lossless for the synthetic discs; not the reference's format)"
     except Exception as exc:                      # pragma: no cover
         e2e_bits = {"value": None, "error": repr(exc)}
+
+    # ---- the other BASELINE.json configs, measured in the same run on every rank (value = whole job)
+    configs = bench_configs(world, rank, dev, peaks, capture, timed_passes, max_over_ranks, barrier)
 
     if rank == 0:
         cpu = cpu_oracle_rate(args.cpu_budget, 16) if world == 1 and not args.no_cpu else None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": KSTEPS,
+            "warmup": WARM, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "reps": hl["reps"], "timed_region_s": hl["timed_region_s"], "best_ms_per_step": hl["best_ms_per_step"],
+            "mean_ms_per_step": hl["mean_ms_per_step"],
             "config": {"workload": f"mask renderer fwd+bwd, batch {B} per GPU, K={K}, {n}x{n} (BASELINE configs[1]); "
                                    "projection in float64, splat in float32",
                        "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": f"{R} rotating input/output sets = {rot_bytes / 1e6:.0f} MB > 126 MB L2",
-                       "step": "project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd; 32 steps per CUDA-graph replay, kernels chained by programmatic dependent launch"},
+                       "step": "project_fwd, splat_fwd(mask), splat_bwd(mask), project_bwd, strictly serial",
+                       "timing": f"one pass = exactly {KSTEPS} consecutive steps captured as CUDA graph(s) of "
+                                 f"{min(KSTEPS, CHAIN_MAX)} steps (programmatic-dependent-launch edges, also across step "
+                                 f"boundaries); {hl['reps']} passes back to back = {hl['timed_region_s']:.2f} s timed region, each "
+                                 "pass timed with CUDA events; value = median pass, max over ranks per pass"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "e2e_binary_targets": e2e_bits,
             "fused_loss": fused, "two_chains": two_chains, "maps_mode": maps_mode,
-            "allreduce": allreduce,
-            "gpu_launches": args.steps * SilhouetteStep.LAUNCHES_PER_STEP,
+            "allreduce": allreduce, "configs": configs,
+            "gpu_launches": hl["reps"] * KSTEPS * SilhouetteStep.LAUNCHES_PER_STEP,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def bench_allreduce(args, sets, R, B, K, world, dev, capture, timed_passes, make_pass, KSTEPS):
+    import torch
+    import torch.distributed as dist
+    from gaussigan_b200.dist import P2PSharedGradReducer, reduce_shared_grads
+
+    nst = max(R, min(KSTEPS, CHAIN_MAX))
+
+    def nccl_pass():
+        for i in range(nst):
+            s0 = sets[i % R][0]
+            s0.forward()
+            s0.backward(sets[i % R][1])
+            reduce_shared_grads([s0.dmus, s0.dsigma])
+
+    ar = timed_passes(nccl_pass, nst)
+    out = {"nccl": {"value": world * B / (ar["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": ar["ms_per_step"],
+                    "note": "local torch sum + one eager NCCL all_reduce(SUM) per step"},
+           "payload_bytes": K * 12 * 8}
+    try:
+        red = P2PSharedGradReducer(K, dev)
+
+        def step_with_exchange(i):
+            st_, gm_, _, _ = sets[i % R]
+            st_.forward()
+            st_.backward(gm_)
+            red(st_.dmus, st_.dsigma)
+
+        run = make_pass(step_with_exchange, nst)
+        dist.barrier()
+        pr = timed_passes(run, nst)
+        red.check()
+        out.update({"value": world * B / (pr["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": pr["ms_per_step"],
+                    "note": "every step followed by the peer-memory exchange of the shared-parameter gradients "
+                            "(gaussigan_b200.dist.P2PSharedGradReducer: local batch sum, stores into the peers' slots over "
+                            "NVLink, flag exchange, rank-ordered sum), all in the step graph"})
+    except Exception as exc:                  # pragma: no cover - e.g. no peer access
+        out.update({"value": out["nccl"]["value"], "unit": UNIT, "ms_per_step": ar["ms_per_step"],
+                    "note": "P2P reducer unavailable (" + repr(exc)[:120] + "): NCCL number"})
+    return out
+
+
+def bench_configs(world, rank, dev, peaks, capture, timed_passes, max_over_ranks, barrier):
+    """BASELINE.json configs other than the headline, each on every rank at once (value = whole job over all ranks).
+    c1/c3/c4/cycle_l1 keep the per-GPU batch fixed (weak scaling); c5 shards the fixed batch of 4096 (strong)."""
+    import torch
+    from gaussigan_b200 import synth
+    from gaussigan_b200._lib import GG_MOMENTS, GG_PARAM_STRIDE, LAYOUT_NHWC, check, int_array, lib, ptr_array
+    from gaussigan_b200.plan import DynamicObjectStep, SilhouetteStep
+    issue_peak = SM_COUNT * FP32_LANES * peaks["sm_max_mhz"] * 1e6
+    st = lambda: torch.cuda.current_stream(dev).cuda_stream      # looked up per call: captures run on a side stream
+    out = {}
+
+    def inputs(B, K, seed):
+        base = synth.synth_inputs(min(B, 256), K, seed=seed, device=dev)
+        rep = (B + 255) // 256
+        f = lambda t: t.repeat(rep, *([1] * (t.dim() - 1)))[:B].contiguous().to(dev)
+        return (f(base["mus"].reshape(-1, K, 3)), f(base["sigma"]), f(base["rotx"].reshape(-1)),
+                f(base["roty"].reshape(-1)), f(base["rotz"].reshape(-1)))
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as exc:                  # pragma: no cover - reported, never hidden
+            out[name] = {"value": None, "error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+
+    def maps_forward(B, K, sizes, nsets, label):
+        sets = []
+        for r in range(nsets):
+            mus, sig, rx, ry, rz = inputs(B, K, 56 + 1000 * rank + r)
+            params = torch.empty(B, K, GG_PARAM_STRIDE, device=dev)
+            maps = [torch.empty(B, s, s, K, device=dev) for s in sizes]
+            sets.append((mus, sig, rx, ry, rz, params, maps, ptr_array([m.data_ptr() for m in maps])))
+        sz, nul = int_array(sizes), ptr_array([None] * len(sizes))
+
+        def step(i):
+            mus, sig, rx, ry, rz, params, _, mp = sets[i % nsets]
+            check(lib.gg_project_fwd(mus.data_ptr(), sig.data_ptr(), 1, rx.data_ptr(), ry.data_ptr(), rz.data_ptr(), 0., 0.,
+                                     -2., 1., B, K, None, None, params.data_ptr(), dev.index, st()), "gg_project_fwd")
+            check(lib.gg_splat_fwd(params.data_ptr(), B, K, len(sizes), sz, mp, nul, LAYOUT_NHWC, dev.index, st()), "gg_splat_fwd")
+
+        nst = 8 * nsets
+        g = capture(lambda: [step(i) for i in range(nst)])
+        r = timed_passes(g.replay, nst, warm_steps=nst)
+        byts = sum(B * s * s * K * 4 for s in sizes)
+        gbs = byts / (r["ms_per_step"] * 1e-3) / 1e9
+        return {"workload": label, "value": world * B / (r["ms_per_step"] * 1e-3), "unit": UNIT,
+                "ms_per_step": r["ms_per_step"], "launches_per_step": 2, "bytes_written_per_step": byts,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"]},
+                "reps": r["reps"], "rotating_sets": nsets}
+
+    guarded("c1", lambda: maps_forward(16, 8, (128,), 8, "BASELINE configs[0]: maps forward, batch 16 per GPU, K=8, 128x128 "
+                                                       "(launch-bound: two small kernels per step)"))
+
+    def c3():
+        B, K, n = 256, 16, 256
+        nsets = 2                                   # 2 x (67 MB u8 targets) + workspaces; > L2 together with the partials
+        steps = []
+        for r in range(nsets):
+            g = torch.Generator().manual_seed(5 + 1000 * rank + r)
+            tt = lambda *s: torch.tanh(torch.randn(*s, generator=g)).to(dev)
+            ps = DynamicObjectStep(B, K, n, dev)
+            ps.bind(tt(K, 3), tt(K, 3), torch.randn(K, 3, generator=g).to(dev), tt(K, 3), tt(B, K, 3), tt(B, K, 3),
+                    tt(B, K, 3), tt(B))
+            tgt = synth.synth_target_masks(B, n, seed=4 + r)
+            raw = ((tgt.reshape(B, n, n) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).to(dev)
+            steps.append((ps, raw))
+        nst = 4 * nsets
+        gr = capture(lambda: [steps[i % nsets][0].loss_backward(steps[i % nsets][1]) for i in range(nst)])
+        r = timed_passes(gr.replay, nst, warm_steps=nst)
+        pxk = B * n * n * K
+        rate = B / (r["ms_per_step"] * 1e-3)
+        return {"workload": "BASELINE configs[2]: dynamic-object mask step (frame -> Sigma, SVD, per-frame deformation, "
+                            "render, fused L1 loss, full backward), batch 256 per GPU, K=16, 256x256",
+                "value": world * rate, "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                "launches_per_step": DynamicObjectStep.LAUNCHES_PER_STEP,
+                "roofline": {"bound": "fp32_pipe", "achieved": 26 * pxk * rate / B / 1e12, "peak": issue_peak / 1e12,
+                             "unit": "T lane-slots/s (26 algorithmic issue slots per pixel-Gaussian)",
+                             "frac": 26 * pxk * rate / B / issue_peak},
+                "reps": r["reps"], "api": "gaussigan_b200.plan.DynamicObjectStep (one CUDA graph)"}
+
+    guarded("c3", c3)
+    guarded("c4", lambda: maps_forward(128, 16, (32, 64, 128, 256), 2,
+                                       "BASELINE configs[3]: K=16 per-Gaussian maps at the 32/64/128/256 pyramid (NHWC), forward, "
+                                       "batch 128 per GPU"))
+
+    def c5():
+        BT, K, n = 4096, 64, 512
+        B = (BT + world - 1) // world
+        mus, sig, rx, ry, rz = inputs(B, K, 56 + rank)
+        step = SilhouetteStep(B, K, n, dev)
+        step.bind(mus, sig, rx, ry, rz)
+        gm = (torch.randn(B, n, n, device=dev) / (BT * n * n)).contiguous()
+        nst = 2
+
+        def one(i):
+            step.forward()
+            step.backward(gm)
+
+        g = capture(lambda: [one(i) for i in range(nst)])
+        r = timed_passes(g.replay, nst, warm_steps=nst)
+        pxk = BT * n * n * K
+        rate = BT / (r["ms_per_step"] * 1e-3)
+        return {"workload": f"BASELINE configs[4]: mask fwd+bwd, batch 4096, K=64, 512x512, batch-sharded x{world} "
+                            f"({B} per GPU), no data-path collective; gradients and masks of one step: "
+                            f"{2 * B * n * n * 4 / 1e9:.1f} GB per GPU (> L2)",
+                "value": rate, "unit": UNIT, "scaling": "strong", "ms_per_step": r["ms_per_step"], "launches_per_step": 4,
+                "roofline": {"bound": "fp32_pipe", "achieved": 26 * pxk / (r["ms_per_step"] * 1e-3) / 1e12,
+                             "peak": world * issue_peak / 1e12,
+                             "unit": "T lane-slots/s (26 algorithmic issue slots per pixel-Gaussian)",
+                             "frac": 26 * pxk / (r["ms_per_step"] * 1e-3) / (world * issue_peak)},
+                "reps": r["reps"]}
+
+    guarded("c5", c5)
+
+    def cycle():
+        B, K, n = B_PER_GPU, K_GAUSS, SIZE
+        nsets = 4
+        T = lib.gg_cycle_tiles(n)
+        nl = lib.gg_cycle_loss_count(B, K, n)
+        sets = []
+        for r in range(nsets):
+            ps = []
+            for side in range(2):
+                mus, sig, rx, ry, rz = inputs(B, K, 1 + 2 * r + side + 1000 * rank)
+                p = torch.empty(B, K, GG_PARAM_STRIDE, device=dev)
+                check(lib.gg_project_fwd(mus.data_ptr(), sig.data_ptr(), 1, rx.data_ptr(), ry.data_ptr(), rz.data_ptr(), 0., 0.,
+                                         -2., 1., B, K, None, None, p.data_ptr(), dev.index, st()), "gg_project_fwd")
+                ps.append(p)
+            sets.append((ps[0], ps[1], torch.empty(B, T, K, GG_MOMENTS, device=dev), torch.empty(B, T, K, GG_MOMENTS, device=dev),
+                         torch.empty(nl, device=dev)))
+
+        def one(i):
+            pa, pb, qa, qb, lp = sets[i % nsets]
+            check(lib.gg_cycle_l1_fused(pa.data_ptr(), pb.data_ptr(), B, K, n, qa.data_ptr(), qb.data_ptr(), T, lp.data_ptr(),
+                                        dev.index, st()), "gg_cycle_l1_fused")
+
+        nst = 8 * nsets
+        g = capture(lambda: [one(i) for i in range(nst)])
+        r = timed_passes(g.replay, nst, warm_steps=nst)
+        pxk = B * n * n * K
+        ex2 = 2 * pxk / (r["ms_per_step"] * 1e-3)                     # one exponential per (pixel, Gaussian) and render
+        mufu_peak = SM_COUNT * 16 * peaks["sm_max_mhz"] * 1e6
+        return {"workload": "gm_cycle_loss (mask_gen_dynamic.py:791) of two renders + both gradient moment sets in one kernel, "
+                            f"batch {B} per GPU, K={K}, {n}x{n}; the two [B,n,n,K] maps ({2 * pxk * 4 / 1e6:.0f} MB) are never written",
+                "value": world * B / (r["ms_per_step"] * 1e-3), "unit": "silhouette pairs/s", "ms_per_step": r["ms_per_step"],
+                "launches_per_step": 1,
+                "roofline": {"bound": "mufu", "achieved": ex2 / 1e12, "peak": mufu_peak / 1e12, "unit": "T MUFU.EX2/s",
+                             "frac": ex2 / mufu_peak, "peak_source": "148 SMs x 16 MUFU lanes x sm_max_mhz"},
+                "reps": r["reps"]}
+
+    guarded("cycle_l1", cycle)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--steps", type=int, default=2048)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="gaussigan_b200", choices=["gaussigan_b200", "reference"])
     ap.add_argument("--rotate", type=int, default=8, help="rotating buffer sets (inputs larger than L2)")

@@ -56,6 +56,8 @@ SIGNATURES = {
     "gg_sigma_from_frame_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "gg_p2p_buffer_bytes": (C.c_size_t, [_i, _i]),
     "gg_shared_grad_allreduce_p2p": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
+    "gg_shared_grad_post_p2p": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp]),
+    "gg_shared_grad_wait_p2p": (_i, [_i, _vp, _i, _i, _vp, _i, _vp]),
     "gg_svd3_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
     "gg_svd3_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_deform_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
@@ -67,7 +69,7 @@ SIGNATURES = {
     "gg_silhouette_step_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "gg_silhouette_step_loss_count": (_i, [_i, _i, _i]),
     "gg_silhouette_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _i, _i, _i,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _vp]),
+                                     _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i, _vp]),
     "gg_splat_bwd": (_i, [_vp, _i, _i, _i, _ip, _pp, _pp, _i, _vp, _i, _i, _vp]),
 }
 

@@ -1,5 +1,6 @@
 // gg_capi.cu -- the extern "C" surface declared in include/gaussigan.h: argument validation,
 // device selection, error reporting.  No compute here.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -9,17 +10,22 @@
 
 namespace gg {
 
-static int g_pdl = -1;
+// process-wide switch; an atomic, so concurrent readers/writers are well defined (see gaussigan.h for the thread rules)
+static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
-  if (g_pdl < 0) {
-    const char *v = std::getenv("GG_PDL");
-    g_pdl = (v && v[0] == '0') ? 0 : 1;
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char *e = std::getenv("GG_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+    int expected = -1;
+    g_pdl.compare_exchange_strong(expected, v, std::memory_order_relaxed);
+    v = g_pdl.load(std::memory_order_relaxed);
   }
-  return g_pdl != 0;
+  return v != 0;
 }
 int set_pdl(int enable) {
   const int prev = pdl_enabled() ? 1 : 0;
-  g_pdl = enable ? 1 : 0;
+  g_pdl.store(enable ? 1 : 0, std::memory_order_relaxed);
   return prev;
 }
 
@@ -41,14 +47,20 @@ int cuda_fail(cudaError_t e, const char *where) {
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int set_device(int device) {
-  // the caller (PyTorch, another library) may change the current device between calls: ask, do not remember
+// Makes `device` current for the duration of one entry point and restores the caller's device on exit: in a
+// single-process multi-GPU program the thread's current device (which PyTorch allocations and stream lookups follow)
+// must not change under the caller's feet.
+DeviceGuard::DeviceGuard(int device) : prev(-1), status(GG_OK) {
   int current = -1;
-  if (cudaGetDevice(&current) != cudaSuccess || current != device) {
+  if (cudaGetDevice(&current) != cudaSuccess) { cudaGetLastError(); current = -1; }
+  if (current != device) {
     cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (e != cudaSuccess) { status = cuda_fail(e, "cudaSetDevice"); return; }
+    prev = current;
   }
-  return GG_OK;
+}
+DeviceGuard::~DeviceGuard() {
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 int check_bk(int B, int K) {
@@ -89,7 +101,8 @@ int gg_project_fwd(const float *mus, const void *sigma, int sigma_is_f64, const 
   if (B == 0) return GG_OK;
   if (!mus || !sigma || !rotx || !roty || !rotz || !params) return fail(GG_E_NULL, "gg_project_fwd: NULL input");
   if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_project_fwd: params must be 16-byte aligned");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_project_fwd(mus, sigma, sigma_is_f64, rotx, roty, rotz, tx, ty, tz, focal, B, K, mu2d,
                                          sigma2d, params, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_project_fwd");
@@ -103,7 +116,8 @@ int gg_project_bwd(const float *mus, const void *sigma, int sigma_is_f64, const 
   if (B == 0) return GG_OK;
   if (!mus || !sigma || !rotx || !roty || !rotz) return fail(GG_E_NULL, "gg_project_bwd: NULL input");
   if (T < 0 || (T > 0 && !partials)) return fail(GG_E_WORKSPACE, "gg_project_bwd: T=%d but partials is NULL", T);
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_project_bwd(mus, sigma, sigma_is_f64, rotx, roty, rotz, tx, ty, tz, focal, B, K,
                                          partials, T, gmu2d, gsigma2d, dmus, dsigma, drot, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_project_bwd");
@@ -115,7 +129,8 @@ int gg_conic_fwd(const void *mu2d, const void *sigma2d, int is_f64, int B, int K
   if (B == 0) return GG_OK;
   if (!mu2d || !sigma2d || !params) return fail(GG_E_NULL, "gg_conic_fwd: NULL input");
   if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_conic_fwd: params must be 16-byte aligned");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_conic_fwd(mu2d, sigma2d, is_f64, B * K, params, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_conic_fwd");
 }
@@ -126,7 +141,8 @@ int gg_conic_bwd(const void *mu2d, const void *sigma2d, int is_f64, int B, int K
   if (B == 0) return GG_OK;
   if (!mu2d || !sigma2d) return fail(GG_E_NULL, "gg_conic_bwd: NULL input");
   if (T <= 0 || !partials) return fail(GG_E_WORKSPACE, "gg_conic_bwd: needs T > 0 partials (T=%d)", T);
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_conic_bwd(mu2d, sigma2d, is_f64, B, K, partials, T, dmu2d, dsigma2d,
                                        (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_conic_bwd");
@@ -150,7 +166,8 @@ int gg_splat_fwd(const float *params, int B, int K, int nscales, const int *size
     if ((long long)B * sizes_host[i] * sizes_host[i] > (1ll << 40)) return fail(GG_E_SHAPE, "scale %d too large", i);
   }
   if (!any) return fail(GG_E_NULL, "gg_splat_fwd: no output requested");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_splat_fwd(params, B, K, nscales, sizes_host, maps_host, masks_host, layout,
                                        (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_splat_fwd");
@@ -164,7 +181,8 @@ int gg_mask_l1_loss_bwd(const float *mask, const void *target, int target_kind, 
   if (!mask || !target || !gmask || !loss_partials) return fail(GG_E_NULL, "gg_mask_l1_loss_bwd: NULL pointer");
   if (!aligned16(mask) || !aligned16(gmask) || (reinterpret_cast<uintptr_t>(target) & 3))
     return fail(GG_E_ALIGN, "gg_mask_l1_loss_bwd: mask/gmask need 16-byte, target 4-byte alignment");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_mask_l1_loss_bwd(mask, target, target_kind, B, n, gmask, loss_partials,
                                               GG_LOSS_PARTIALS, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_mask_l1_loss_bwd");
@@ -186,7 +204,8 @@ int gg_silhouette_loss_fused(const float *params, const void *target, int target
   if (!aligned16(params) || (mask_out && !aligned16(mask_out)) || (target_kind != GG_TARGET_BITS && !aligned16(target)))
     return fail(GG_E_ALIGN, "gg_silhouette_loss_fused: params/target/mask_out must be 16-byte aligned");
   if (T != gg::fused_loss_tiles(K, n)) return fail(GG_E_WORKSPACE, "gg_silhouette_loss_fused: T=%d, expected %d", T, gg::fused_loss_tiles(K, n));
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_silhouette_loss_fused(params, target, target_kind, B, K, n, mask_out, partials,
                                                    loss_partials, T, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_silhouette_loss_fused");
@@ -212,7 +231,8 @@ int gg_cycle_l1_fused(const float *params_a, const float *params_b, int B, int K
     return fail(GG_E_NULL, "gg_cycle_l1_fused: NULL pointer");
   if (!aligned16(params_a) || !aligned16(params_b)) return fail(GG_E_ALIGN, "gg_cycle_l1_fused: params must be 16-byte aligned");
   if (T != gg::cycle_tiles(n)) return fail(GG_E_WORKSPACE, "gg_cycle_l1_fused: T=%d, expected %d", T, gg::cycle_tiles(n));
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_cycle_l1_fused(params_a, params_b, B, K, n, partials_a, partials_b, loss_partials, T,
                                             (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_cycle_l1_fused");
@@ -227,7 +247,8 @@ int gg_colorize(const float *params, const float *maps, const float *colors, int
   if ((params == nullptr) == (maps == nullptr)) return fail(GG_E_NULL, "gg_colorize: exactly one of params / maps");
   if (!colors || !out) return fail(GG_E_NULL, "gg_colorize: NULL pointer");
   if (params && (!aligned16(params) || K > 1024)) return fail(GG_E_ALIGN, "gg_colorize: params alignment / K <= 1024");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = params ? gg::launch_colorize_params(params, colors, B, K, n, out, out_mode, (cudaStream_t)stream)
                          : gg::launch_colorize_maps(maps, colors, (size_t)B * n * n, K, out, out_mode,
                                                     (cudaStream_t)stream);
@@ -239,7 +260,8 @@ int gg_sigma_from_frame_fwd(const float *v0, const float *v1, const float *u, in
   if (N < 0) return fail(GG_E_SHAPE, "N < 0");
   if (N == 0) return GG_OK;
   if (!v0 || !v1 || !u || !sigma) return fail(GG_E_NULL, "gg_sigma_from_frame_fwd: NULL pointer");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_sigma_from_frame_fwd(v0, v1, u, N, sigma, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_sigma_from_frame_fwd");
 }
@@ -249,7 +271,8 @@ int gg_sigma_from_frame_bwd(const float *v0, const float *v1, const float *u, co
   if (N < 0) return fail(GG_E_SHAPE, "N < 0");
   if (N == 0) return GG_OK;
   if (!v0 || !v1 || !u || !gsigma || !dv0 || !dv1 || !du) return fail(GG_E_NULL, "gg_sigma_from_frame_bwd: NULL pointer");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_sigma_from_frame_bwd(v0, v1, u, gsigma, N, dv0, dv1, du, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_sigma_from_frame_bwd");
 }
@@ -259,22 +282,41 @@ size_t gg_p2p_buffer_bytes(int K, int world) {
   return gg::p2p_buffer_bytes(K, world);
 }
 
-int gg_shared_grad_allreduce_p2p(const float *dmus, const double *dsigma, int B, int K, const void *peers_dev, int world,
-                                 int rank, double *out, int device, void *stream) {
+int gg_shared_grad_post_p2p(const float *dmus, const double *dsigma, int B, int K, const void *peers_dev, int world,
+                            int rank, int device, void *stream) {
   if (int r = check_bk(B, K)) return r;
   if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(GG_E_SHAPE, "bad world/rank (%d/%d)", world, rank);
-  if (!dmus || !dsigma || !peers_dev || !out) return fail(GG_E_NULL, "gg_shared_grad_allreduce_p2p: NULL pointer");
-  if (int r = set_device(device)) return r;
-  cudaError_t e = gg::launch_shared_grad_allreduce(dmus, dsigma, B, K, reinterpret_cast<const unsigned long long *>(peers_dev),
-                                                   world, rank, out, (cudaStream_t)stream);
-  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_shared_grad_allreduce_p2p");
+  if (!dmus || !dsigma || !peers_dev) return fail(GG_E_NULL, "gg_shared_grad_post_p2p: NULL pointer");
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
+  cudaError_t e = gg::launch_shared_grad_post(dmus, dsigma, B, K, reinterpret_cast<const unsigned long long *>(peers_dev),
+                                              world, rank, (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_shared_grad_post_p2p");
+}
+
+int gg_shared_grad_wait_p2p(int K, const void *peers_dev, int world, int rank, double *out, int device, void *stream) {
+  if (K <= 0) return fail(GG_E_SHAPE, "K must be > 0");
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(GG_E_SHAPE, "bad world/rank (%d/%d)", world, rank);
+  if (!peers_dev || !out) return fail(GG_E_NULL, "gg_shared_grad_wait_p2p: NULL pointer");
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
+  cudaError_t e = gg::launch_shared_grad_wait(K, reinterpret_cast<const unsigned long long *>(peers_dev), world, rank, out,
+                                              (cudaStream_t)stream);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_shared_grad_wait_p2p");
+}
+
+int gg_shared_grad_allreduce_p2p(const float *dmus, const double *dsigma, int B, int K, const void *peers_dev, int world,
+                                 int rank, double *out, int device, void *stream) {
+  if (int r = gg_shared_grad_post_p2p(dmus, dsigma, B, K, peers_dev, world, rank, device, stream)) return r;
+  return gg_shared_grad_wait_p2p(K, peers_dev, world, rank, out, device, stream);
 }
 
 int gg_svd3_fwd(const double *A, int N, double *U, double *S, double *V, int device, void *stream) {
   if (N < 0) return fail(GG_E_SHAPE, "N < 0");
   if (N == 0) return GG_OK;
   if (!A || !U || !S) return fail(GG_E_NULL, "gg_svd3_fwd: NULL pointer");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_svd3_fwd(A, N, U, S, V, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_svd3_fwd");
 }
@@ -284,7 +326,8 @@ int gg_svd3_bwd(const double *U, const double *S, const double *V, const double 
   if (N < 0) return fail(GG_E_SHAPE, "N < 0");
   if (N == 0) return GG_OK;
   if (!U || !S || !V || !gA) return fail(GG_E_NULL, "gg_svd3_bwd: NULL pointer");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_svd3_bwd(U, S, V, gU, gS, N, gA, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_svd3_bwd");
 }
@@ -296,7 +339,8 @@ int gg_deform_fwd(const float *mu_t, const float *scale, const float *ang, const
   if (B == 0) return GG_OK;
   if (!mu_t || !scale || !ang || !cmu || !U || !S || !mus || !sigmas) return fail(GG_E_NULL, "gg_deform_fwd: NULL pointer");
   if ((theta == nullptr) != (theta_raw == nullptr)) return fail(GG_E_NULL, "gg_deform_fwd: theta and theta_raw go together");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_deform_fwd(mu_t, scale, ang, cmu, U, S, theta_raw, B, K, mus, sigmas, theta,
                                         (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_deform_fwd");
@@ -309,7 +353,8 @@ int gg_deform_bwd(const float *scale, const float *ang, const double *U, const d
   if (B == 0) return GG_OK;
   if (!scale || !ang || !U || !S || !dmu_t || !dscale || !dang || !dcmu || !dU || !dS)
     return fail(GG_E_NULL, "gg_deform_bwd: NULL pointer");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_deform_bwd(scale, ang, U, S, gmus, gsig, gtheta, B, K, dtheta_raw, dmu_t, dscale, dang,
                                         dcmu, dU, dS, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_deform_bwd");
@@ -344,7 +389,8 @@ int gg_splat_bwd(const float *params, int B, int K, int nscales, const int *size
   int need = gg::plan_bwd_tiles(K, nscales, sizes_host, hm, hk, layout);
   if (need != T || T <= 0)
     return fail(GG_E_WORKSPACE, "gg_splat_bwd: T=%d but this configuration writes %d partial tiles", T, need);
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaError_t e = gg::launch_splat_bwd(params, B, K, nscales, sizes_host, gmaps_host, gmasks_host, layout, partials,
                                        T, (cudaStream_t)stream);
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_splat_bwd");

@@ -44,12 +44,21 @@ StepLayout step_layout(int B, int K, int n, int target_kind) {
   return L;
 }
 
-// device-usable alias of a pinned host pointer (UVA), or NULL when the memory is pageable / unknown
+// device-usable alias of a pinned host range [host, host + bytes) (UVA), or NULL when any of it is pageable /
+// unknown: both ends must resolve to pinned memory with consecutive device addresses (a partly registered buffer
+// would otherwise fault in the kernel)
 template <typename T>
-static T *mapped_or_null(T *host) {
-  cudaPointerAttributes at;
+static T *mapped_or_null(T *host, size_t bytes) {
+  if (bytes == 0) return nullptr;
+  cudaPointerAttributes at, at_end;
   if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+  const char *last = reinterpret_cast<const char *>(host) + bytes - 1;
+  if (cudaPointerGetAttributes(&at_end, last) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at_end.type != cudaMemoryTypeHost || at_end.devicePointer == nullptr) return nullptr;
+  if (reinterpret_cast<const char *>(at_end.devicePointer) - reinterpret_cast<const char *>(at.devicePointer) !=
+      (ptrdiff_t)(bytes - 1))
+    return nullptr;
   return reinterpret_cast<T *>(const_cast<void *>(static_cast<const void *>(at.devicePointer)));
 }
 
@@ -82,8 +91,9 @@ int gg_silhouette_step_loss_count(int B, int K, int n) {
 int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, const float *rotx_host,
                             const float *roty_host, const float *rotz_host, const void *target_host, int target_kind,
                             double tx, double ty, double tz, double focal, int B, int K, int n,
-                            float *loss_partials_host, float *dmus_host, double *dsigma_host, float *drot_host,
-                            float *mask_host, void *workspace, size_t workspace_bytes, int device, void *stream) {
+                            float *loss_partials_host, int loss_partials_capacity, float *dmus_host,
+                            double *dsigma_host, float *drot_host, float *mask_host, void *workspace,
+                            size_t workspace_bytes, int device, void *stream) {
   if (int r = check_bk(B, K)) return r;
   const int sizes[1] = {n};
   if (int r = check_scales(K, 1, sizes)) return r;
@@ -98,8 +108,12 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
   const gg::StepLayout L = gg::step_layout(B, K, n, target_kind);
   if (workspace_bytes < L.total)
     return fail(GG_E_WORKSPACE, "gg_silhouette_step_host: workspace %zu < required %zu bytes", workspace_bytes, L.total);
+  if (loss_partials_capacity < L.nloss)
+    return fail(GG_E_WORKSPACE, "gg_silhouette_step_host: loss_partials_host holds %d floats, this configuration writes %d "
+                "(gg_silhouette_step_loss_count; it depends on the arithmetic mode)", loss_partials_capacity, L.nloss);
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(GG_E_ALIGN, "workspace must be 256-byte aligned");
-  if (int r = set_device(device)) return r;
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
   cudaStream_t st = (cudaStream_t)stream;
   char *w = reinterpret_cast<char *>(workspace);
   float *d_mus = reinterpret_cast<float *>(w + L.mus);
@@ -124,9 +138,11 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
   // pinned (cudaHostAlloc / cudaHostRegister, device-accessible through UVA) the two projection kernels read and
   // write them in place over PCIe and the nine small copies disappear from the copy-engine queues; only the target
   // mask (the bulk of the bytes) goes through the DMA engine.  Pageable buffers take the copy path.
-  const float *k_mus = mapped_or_null(mus_host);
-  const double *k_sigma = mapped_or_null(sigma_host);
-  const float *k_rx = mapped_or_null(rotx_host), *k_ry = mapped_or_null(roty_host), *k_rz = mapped_or_null(rotz_host);
+  const size_t nbk = (size_t)B * K;
+  const float *k_mus = mapped_or_null(mus_host, nbk * 3 * 4);
+  const double *k_sigma = mapped_or_null(sigma_host, nbk * 9 * 8);
+  const float *k_rx = mapped_or_null(rotx_host, (size_t)B * 4), *k_ry = mapped_or_null(roty_host, (size_t)B * 4),
+              *k_rz = mapped_or_null(rotz_host, (size_t)B * 4);
   const bool in_place_in = zero_copy_enabled() && k_mus && k_sigma && k_rx && k_ry && k_rz;
   if (!in_place_in) {
     GG_TRY(cudaMemcpyAsync(d_mus, mus_host, (size_t)B * K * 3 * 4, cudaMemcpyHostToDevice, st), "H2D mus");
@@ -140,7 +156,7 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
   const void *k_target = d_target;
   {
     static const bool zc_target = [] { const char *v = std::getenv("GG_ZEROCOPY_TARGET"); return v && v[0] == '1'; }();
-    const void *m = zc_target ? mapped_or_null(target_host) : nullptr;
+    const void *m = zc_target ? mapped_or_null(target_host, gg::target_bytes(B, n, target_kind)) : nullptr;
     if (m) k_target = m;
     else
       GG_TRY(cudaMemcpyAsync(d_target, target_host, gg::target_bytes(B, n, target_kind), cudaMemcpyHostToDevice,
@@ -159,8 +175,8 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
     const float *gmasks[1] = {d_gmask};
     GG_TRY(gg::launch_splat_bwd(d_params, B, K, 1, sizes, nullptr, gmasks, GG_LAYOUT_NHWC, d_part, L.T, st), "splat_bwd");
   }
-  float *k_dmus = mapped_or_null(dmus_host), *k_drot = mapped_or_null(drot_host);
-  double *k_dsig = mapped_or_null(dsigma_host);
+  float *k_dmus = mapped_or_null(dmus_host, nbk * 3 * 4), *k_drot = mapped_or_null(drot_host, (size_t)B * 3 * 4);
+  double *k_dsig = mapped_or_null(dsigma_host, nbk * 9 * 8);
   const bool in_place_out = zero_copy_enabled() && k_dmus && k_dsig && k_drot;
   GG_TRY(gg::launch_project_bwd(k_mus, k_sigma, 1, k_rx, k_ry, k_rz, tx, ty, tz, focal, B, K, d_part, L.T, nullptr,
                                 nullptr, in_place_out ? k_dmus : d_dmus, in_place_out ? k_dsig : d_dsig,

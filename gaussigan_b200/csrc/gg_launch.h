@@ -61,15 +61,22 @@ cudaError_t launch_deform_bwd(const float *sc, const float *ang, const double *U
                               float *dsc, float *dang, float *dcmu, double *dU, double *dS, cudaStream_t st);
 
 size_t p2p_buffer_bytes(int K, int world);
-cudaError_t launch_shared_grad_allreduce(const float *dmus, const double *dsigma, int B, int K,
-                                         const unsigned long long *peers, int world, int rank, double *out,
-                                         cudaStream_t st);
+cudaError_t launch_shared_grad_post(const float *dmus, const double *dsigma, int B, int K,
+                                    const unsigned long long *peers, int world, int rank, cudaStream_t st);
+cudaError_t launch_shared_grad_wait(int K, const unsigned long long *peers, int world, int rank, double *out,
+                                    cudaStream_t st);
 
 namespace api {   // error/validation helpers shared by the extern "C" translation units (gg_capi.cu)
 int fail(int code, const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *where);
 bool aligned16(const void *p);
-int set_device(int device);
+struct DeviceGuard {   // RAII: make `device` current, restore the caller's device on scope exit
+  int prev, status;
+  explicit DeviceGuard(int device);
+  ~DeviceGuard();
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 int check_bk(int B, int K);
 int check_scales(int K, int nscales, const int *sizes);
 }  // namespace api

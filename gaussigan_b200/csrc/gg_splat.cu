@@ -24,6 +24,7 @@
 // (5 STS per Gaussian, conflict-free) -> 32-term serial sums by 30 lanes -> fixed-order sum over the
 // 8 warps -> one [K,5] partial per CTA written to its own slot.  No atomics, no zero-fill,
 // bit-reproducible; the O(T) sum over slots happens in float64 in the projection adjoint.
+#include <atomic>
 #include <cstdlib>
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
@@ -774,14 +775,20 @@ cudaError_t launch_bwd_mask_fast(const SplatArgs &a, bool fused, int B, int rpt,
 
 // Mask-only launches use the forward-differenced kernels of gg_splat_fast.cu unless GG_PRECISE_MASK=1 (or
 // gg_set_fast_mask(0)) asks for the direct one-exponential-per-pixel form.
-static int g_fast_mask = -1;
+static std::atomic<int> g_fast_mask{-1};
 bool fast_mask() {
-  if (g_fast_mask < 0) g_fast_mask = env_int("GG_PRECISE_MASK", 0) ? 0 : 1;
-  return g_fast_mask != 0;
+  int v = g_fast_mask.load(std::memory_order_relaxed);
+  if (v < 0) {
+    v = env_int("GG_PRECISE_MASK", 0) ? 0 : 1;
+    int expected = -1;
+    g_fast_mask.compare_exchange_strong(expected, v, std::memory_order_relaxed);
+    v = g_fast_mask.load(std::memory_order_relaxed);
+  }
+  return v != 0;
 }
 int set_fast_mask(int enable) {
   const int prev = fast_mask() ? 1 : 0;
-  g_fast_mask = enable ? 1 : 0;
+  g_fast_mask.store(enable ? 1 : 0, std::memory_order_relaxed);
   return prev;
 }
 

@@ -422,16 +422,26 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
 
 // ====================================================================================== launchers
 // rpt = rows per thread of the plan (2 or 4); the CTA size comes from the plan's geometry (sc[0].cta)
+// K * 48 bytes of staged constants exceed the 48 KB default above K = 1024 (the C ABI accepts K <= 1536): opt in
+template <typename Kern>
+static cudaError_t launch_fwd_fast_one(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const SplatArgs &a) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  launch_pdl(kern, grid, block, smem, st, a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)B * a.T));
   size_t smem = (size_t)a.K * 3 * sizeof(float4);
   const int cta = a.sc[0].cta;
-  if (rpt == 4) launch_pdl(splat_fwd_mask_fast_kernel<2, 8>, grid, dim3(256), smem, st, a);
-  else if (cta == 128) launch_pdl(splat_fwd_mask_fast_kernel<1, 4>, grid, dim3(128), smem, st, a);
-  else if (cta == 160) launch_pdl(splat_fwd_mask_fast_kernel<1, 5>, grid, dim3(160), smem, st, a);
-  else if (cta == 192) launch_pdl(splat_fwd_mask_fast_kernel<1, 6>, grid, dim3(192), smem, st, a);
-  else launch_pdl(splat_fwd_mask_fast_kernel<1, 8>, grid, dim3(256), smem, st, a);
-  return cudaGetLastError();
+  if (rpt == 4) return launch_fwd_fast_one(splat_fwd_mask_fast_kernel<2, 8>, grid, dim3(256), smem, st, a);
+  if (cta == 128) return launch_fwd_fast_one(splat_fwd_mask_fast_kernel<1, 4>, grid, dim3(128), smem, st, a);
+  if (cta == 160) return launch_fwd_fast_one(splat_fwd_mask_fast_kernel<1, 5>, grid, dim3(160), smem, st, a);
+  if (cta == 192) return launch_fwd_fast_one(splat_fwd_mask_fast_kernel<1, 6>, grid, dim3(192), smem, st, a);
+  return launch_fwd_fast_one(splat_fwd_mask_fast_kernel<1, 8>, grid, dim3(256), smem, st, a);
 }
 
 template <bool FUSED, bool CENTRE>

@@ -52,13 +52,14 @@ def reduce_shared_grads(per_sample_grads: Sequence[torch.Tensor], group=None) ->
 
 
 class P2PSharedGradReducer:
-    """``reduce_shared_grads`` for the renderer's own gradients as ONE kernel over NVLink peer memory
-    (``gg_shared_grad_allreduce_p2p``, include/gaussigan.h): local batch sum + stores into every peer's receive slot +
-    flag exchange + rank-ordered sum.  ~10x less latency than an eager NCCL ``all_reduce`` at this payload
-    (12*K numbers), bit-identical on all ranks, replayable from a CUDA graph.
+    """``reduce_shared_grads`` for the renderer's own gradients over NVLink peer memory (include/gaussigan.h):
+    ``post`` = local batch sum + stores into every peer's receive slot + flags, ``wait`` = flag wait + rank-ordered sum.
+    An order of magnitude less latency than an eager NCCL ``all_reduce`` at this payload (12*K numbers), bit-identical
+    on all ranks, replayable from a CUDA graph, and the two halves can be separated so the exchange overlaps other work.
 
         red = P2PSharedGradReducer(K, device)                  # collective: every rank of the group constructs it
         dmu_sum, dsig_sum = red(dmus, dsigma)                  # [B,K,3] f32, [B,K,3,3] f64 -> [K,3], [K,3,3] float64
+        red.post(dmus, dsigma); ...; dmu_sum, dsig_sum = red.wait()      # the same, overlapped
 
     Needs ``torch.distributed`` initialised with NCCL on one node with peer access (NVLink / NVSwitch): the exchange
     buffers come from ``torch.distributed._symmetric_memory``.  ``check()`` synchronises and raises if a peer timed out.
@@ -82,20 +83,36 @@ class P2PSharedGradReducer:
         self.peers = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=dev)
         self.out = torch.empty(12 * self.K, dtype=torch.float64, device=dev)
 
-    def __call__(self, dmus: torch.Tensor, dsigma: torch.Tensor):
+    def post(self, dmus: torch.Tensor, dsigma: torch.Tensor) -> None:
+        """First half: local batch sum, stores into every peer's slot, flags (``gg_shared_grad_post_p2p``).  Enqueue it
+        right behind the backward; at most one post may be outstanding (``wait()`` before the next ``post()``)."""
         from ._lib import check, lib
         B = dmus.shape[0]
         assert dmus.is_cuda and dmus.dtype == torch.float32 and dmus.is_contiguous() and dmus.numel() == B * self.K * 3
         assert dsigma.dtype == torch.float64 and dsigma.is_contiguous() and dsigma.numel() == B * self.K * 9
         st = torch.cuda.current_stream(self.dev).cuda_stream
-        check(lib.gg_shared_grad_allreduce_p2p(dmus.data_ptr(), dsigma.data_ptr(), B, self.K, self.peers.data_ptr(),
-                                               self.world, self.rank, self.out.data_ptr(), self.dev.index, st),
-              "gg_shared_grad_allreduce_p2p")
+        check(lib.gg_shared_grad_post_p2p(dmus.data_ptr(), dsigma.data_ptr(), B, self.K, self.peers.data_ptr(),
+                                          self.world, self.rank, self.dev.index, st), "gg_shared_grad_post_p2p")
+
+    def wait(self):
+        """Second half: wait for the peers' flags and add the slots in rank order (``gg_shared_grad_wait_p2p``), on the
+        current stream (which must be ordered after the post).  Returns ([K,3], [K,3,3]) float64 views of ``self.out``;
+        they hold NaN if a peer did not arrive within ``GG_P2P_TIMEOUT_MS``."""
+        from ._lib import check, lib
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        check(lib.gg_shared_grad_wait_p2p(self.K, self.peers.data_ptr(), self.world, self.rank, self.out.data_ptr(),
+                                          self.dev.index, st), "gg_shared_grad_wait_p2p")
         K = self.K
         return self.out[:3 * K].view(K, 3), self.out[3 * K:].view(K, 3, 3)
 
+    def __call__(self, dmus: torch.Tensor, dsigma: torch.Tensor):
+        self.post(dmus, dsigma)
+        return self.wait()
+
     def check(self) -> None:
+        """Synchronise and raise if any wait timed out (the result of that call is NaN as well)."""
         torch.cuda.synchronize(self.dev)
         err = int(self.buf.view(torch.int32)[1].item())
         if err:
-            raise RuntimeError(f"gg_shared_grad_allreduce_p2p: a peer did not arrive in call {err}")
+            raise RuntimeError(f"gg_shared_grad_wait_p2p: a peer did not arrive in call {err}; the results of that call "
+                               "are NaN and the reducer must be rebuilt")

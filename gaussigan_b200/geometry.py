@@ -3,7 +3,7 @@
 * ``sigma_from_frame(v0, v1, u)``  -- tail of ``get_musigma`` (mask/mask_gen_dynamic.py:383-401)
 * ``deform(mu_t, scale, rx, ry, rz, theta, cannmu, cannsigma)`` -- tail of the dynamic ``transform_mu_sigma``
   (mask/mask_gen_dynamic.py:426-458); the SVD of the canonical covariances (:430) is a Jacobi kernel
-  (``svd3``; ``svd="torch"`` selects ``torch.linalg.svd``), everything after it is one CUDA launch per direction.
+  (``svd3``: no cuSOLVER, no library fallback), everything after it is one CUDA launch per direction.
 
 Both take the OUTPUTS of the dense heads (the MLPs are out of scope) and are differentiable.
 """
@@ -119,21 +119,21 @@ class _Deform(torch.autograd.Function):
         return dmu_t, dsc, dang, dth, dcmu.sum(0), dU.sum(0), dS.sum(0)
 
 
-def deform(mu_t_raw, scale_raw, rx_raw, ry_raw, rz_raw, theta_raw, cannmu, cannsigma, svd: str = "cuda"):
+def deform(mu_t_raw, scale_raw, rx_raw, ry_raw, rz_raw, theta_raw, cannmu, cannsigma, factors=None):
     """mask/mask_gen_dynamic.py:426-458.  Head outputs AFTER tanh: ``mu_t_raw [B,K*3]``, ``scale_raw [B,K*3]``,
     ``r*_raw [B,K]``, ``theta_raw [B,1]``; canonical ``cannmu [1,K,1,3]`` f32, ``cannsigma [1,K,3,3]`` f64.
     Returns ``mus [B,K,1,3]`` f32, ``sigmas [B,K,3,3]`` f64, ``theta [B,1]`` f32 degrees -- ready for ``get_landmarks``.
-    ``svd`` selects who factorises the canonical covariances (:430): the library's Jacobi kernel (default) or
-    ``torch.linalg.svd``; both give the same Sigma_b (column signs of U cancel)."""
+    The canonical covariances are factorised (:430) by the library's own Jacobi kernel (``svd3``).  ``factors=(U, S)``
+    lets a caller that already holds a factorisation of ``cannsigma`` (e.g. a test feeding the same U, S to both sides
+    of a comparison) pass it in; Sigma_b does not depend on the column signs of U."""
     _require_cuda(mu_t_raw, scale_raw, rx_raw, ry_raw, rz_raw, theta_raw, cannmu, cannsigma)
     K = cannsigma.shape[-3]
     B = mu_t_raw.shape[0]
-    if svd == "cuda":        # :430, Jacobi kernel (graph-capturable)
+    if factors is None:      # :430, Jacobi kernel (graph-capturable)
         U, S = svd3(cannsigma.to(torch.float64).reshape(K, 3, 3))
-    elif svd == "torch":     # :430, cuSOLVER through torch (synchronises with the host)
-        U, S, _ = torch.linalg.svd(cannsigma.to(torch.float64).reshape(K, 3, 3), full_matrices=True)
     else:
-        raise ValueError("svd must be 'cuda' or 'torch'")
+        U, S = factors
+        U, S = U.to(torch.float64).reshape(K, 3, 3), S.to(torch.float64).reshape(K, 3)
     ang = torch.stack([rx_raw.reshape(B, K), ry_raw.reshape(B, K), rz_raw.reshape(B, K)], dim=-1)
     f = lambda t: t.float().contiguous()
     mus, sig, theta = _Deform.apply(f(mu_t_raw.reshape(B, K, 3)), f(scale_raw.reshape(B, K, 3)), f(ang),

@@ -20,6 +20,53 @@ GG_TARGET_U8, GG_TARGET_F32, GG_TARGET_BITS = 0, 1, 2
 GG_LOSS_PARTIALS = 296
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(gpu_index: int) -> dict:
+    """Bind the calling process to the CPU cores and the memory of the NUMA node GPU ``gpu_index`` hangs off.
+
+    Call it once per rank BEFORE allocating pinned host buffers: the pages of ``cudaHostAlloc`` memory are placed by
+    the allocating thread's memory policy, and with all ranks of a node left on the default policy every staging
+    buffer ends up on NUMA node 0 -- the host-to-device copies of the ranks whose GPUs sit under the other socket then
+    cross the inter-socket link and all eight share one socket's DRAM (round 1: 52.6 GB/s per GPU alone, 27.3 GB/s with
+    eight ranks).  Uses sysfs (``/sys/bus/pci/devices/<bdf>/numa_node``, ``local_cpulist``), ``os.sched_setaffinity``
+    and ``set_mempolicy(MPOL_PREFERRED)``; every step is best effort (containers may restrict cpusets) and the outcome
+    is returned for the caller to log."""
+    import os
+    info = {"gpu": int(gpu_index), "node": None, "cpus_bound": None, "mempolicy": None}
+    try:
+        prop = torch.cuda.get_device_properties(gpu_index)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read())
+        info["node"] = node
+        local = _parse_cpulist(open(base + "/local_cpulist").read())
+        allowed = os.sched_getaffinity(0)
+        use = local & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["cpus_bound"] = len(use)
+        else:
+            info["cpus_bound"] = 0 if not use else len(use)
+        if node >= 0:
+            libc = C.CDLL(None, use_errno=True)
+            mask = C.c_ulong(1 << node)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238          # x86_64
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, C.byref(mask), C.c_ulong(C.sizeof(mask) * 8))
+            info["mempolicy"] = "preferred node %d" % node if rc == 0 else "errno %d" % C.get_errno()
+    except Exception as exc:                      # pragma: no cover - depends on the host
+        info["error"] = repr(exc)[:160]
+    return info
+
+
 class HostInputs(NamedTuple):
     """Pinned host tensors: mus [B,K,3] f32, sigma [B,K,3,3] f64, rot* [B] f32 (degrees), target [B,n,n] u8|f32."""
     mus: torch.Tensor
@@ -129,7 +176,8 @@ class HostSilhouetteStep:
         check(lib.gg_silhouette_step_host(
             h.mus.data_ptr(), h.sigma.data_ptr(), h.rotx.data_ptr(), h.roty.data_ptr(), h.rotz.data_ptr(),
             h.target.data_ptr(), self.kind, *self.t, self.focal, B, K, n,
-            res.loss_partials.data_ptr(), res.dmus.data_ptr(), res.dsigma.data_ptr(), res.drot.data_ptr(),
+            res.loss_partials.data_ptr(), res.loss_partials.numel(), res.dmus.data_ptr(), res.dsigma.data_ptr(),
+            res.drot.data_ptr(),
             res.mask.data_ptr() if res.mask is not None else None,
             self.ws[i].data_ptr(), self.ws_bytes, self.dev.index, st.cuda_stream), "gg_silhouette_step_host")
         ev = torch.cuda.Event()

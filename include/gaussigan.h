@@ -17,7 +17,13 @@
  *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
  *   - the caller owns all memory; the library never allocates or frees device memory;
  *   - every launch entry takes the CUDA device ordinal and a cudaStream_t (as void*); calls are
- *     asynchronous on that stream, stateless and re-entrant; no implicit synchronisation;
+ *     asynchronous on that stream and re-entrant, with no implicit synchronisation; the thread's current
+ *     CUDA device is restored before the call returns;
+ *   - the only state is two process-wide switches, gg_set_fast_mask and gg_set_pdl (atomics: safe to flip
+ *     from any thread).  The tile count T of the backward depends on the arithmetic mode: a thread that
+ *     flips gg_set_fast_mask between another thread's gg_splat_bwd_tiles query and its launch makes that
+ *     launch fail with GG_E_WORKSPACE (every entry re-validates T and buffer capacities against the mode
+ *     in force; nothing is ever written out of bounds).  Set the mode once, before planning;
  *   - return value: 0 = ok, < 0 = error (GG_E_*); gg_last_error() gives a thread-local message;
  *     nothing throws across the ABI;
  *   - layouts: mus [B,K,3] f32; sigma [B,K,3,3] f32 or f64 (row-major); rot* [B] f32 DEGREES;
@@ -40,7 +46,7 @@ extern "C" {
 #define GG_API
 #endif
 
-#define GG_VERSION 100            /* 0.1.0 */
+#define GG_VERSION 200            /* 0.2.0 */
 #define GG_PARAM_STRIDE 8         /* floats per projected Gaussian in the staged `params` buffer */
 #define GG_MOMENTS 5              /* gradient accumulators per Gaussian */
 #define GG_MAX_SCALES 4           /* the reference's pyramid: 32, 64, 128, 256 (mask_gen_dynamic.py:315-316) */
@@ -129,8 +135,9 @@ GG_API int gg_splat_bwd(const float *params, int B, int K, int nscales, const in
 /* Arithmetic of the MASK-ONLY launches (gg_splat_fwd / gg_splat_bwd on scales that carry only a mask, and
  * gg_silhouette_loss_fused).  1 (default): Gaussians forward-differenced along each 8-pixel strip -- two
  * exponentials per strip instead of eight, FP32-pipe bound, silhouette error ~6e-7 of its maximum.  0: one
- * exponential per (pixel, Gaussian), ~1e-7.  Maps outputs always use the direct form.  Process-wide; returns the
- * previous setting.  Environment GG_PRECISE_MASK=1 selects 0 at load time. */
+ * exponential per (pixel, Gaussian), ~1e-7.  Maps outputs always use the direct form.  Process-wide (atomic); returns
+ * the previous setting.  Environment GG_PRECISE_MASK=1 selects 0 at load time.  T (gg_splat_bwd_tiles) and
+ * gg_silhouette_step_loss_count depend on it: set it before planning. */
 GG_API int gg_set_fast_mask(int enable);
 
 /* Programmatic dependent launch.  1 (default): every kernel is launched with
@@ -216,9 +223,22 @@ GG_API int gg_deform_bwd(const float *scale, const float *ang, const double *U, 
  * of `world` base addresses of the ranks' exchange buffers (peer-mapped, e.g. torch symmetric memory), each
  * gg_p2p_buffer_bytes(K, world) bytes, zero-filled once before the first call (with a barrier across ranks).
  * out [12*K] f64 = dmu sums [K,3] followed by dsigma sums [K,3,3].  Every rank must make the same sequence of calls.
- * Replayable from a CUDA graph (the call counter lives in the buffer).  If a peer does not arrive within ~1 s the
- * kernel stores the call number in word 1 of the rank's own buffer and returns without writing `out`. */
+ * Replayable from a CUDA graph (the call counters live in the buffer).
+ * Two halves, so that the exchange overlaps whatever the caller runs in between:
+ *   gg_shared_grad_post_p2p  -- local batch sum (ceil(12 K / 32) CTAs, one load round trip), stores into every peer's
+ *                               slot, flag on every peer.  Enqueue right behind the projection adjoint.
+ *   gg_shared_grad_wait_p2p  -- waits for the peers' flags, adds the slots in rank order into `out`.  Enqueue any time
+ *                               later on a stream ordered after the post (just before the optimiser step), but before
+ *                               the NEXT post: at most one post may be outstanding.
+ * gg_shared_grad_allreduce_p2p = post + wait back to back.
+ * The wait is bounded by GG_P2P_TIMEOUT_MS (environment, default 60000): on expiry the kernel fills `out` with NaN --
+ * the failure reaches the gradients -- and latches the call number in word 1 of the rank's own buffer; the exchange
+ * group must then be rebuilt (as after an NCCL abort). */
 GG_API size_t gg_p2p_buffer_bytes(int K, int world);
+GG_API int gg_shared_grad_post_p2p(const float *dmus, const double *dsigma, int B, int K, const void *peers_dev,
+                                   int world, int rank, int device, void *stream);
+GG_API int gg_shared_grad_wait_p2p(int K, const void *peers_dev, int world, int rank, double *out, int device,
+                                   void *stream);
 GG_API int gg_shared_grad_allreduce_p2p(const float *dmus, const double *dsigma, int B, int K,
                                         const void *peers_dev, int world, int rank, double *out, int device,
                                         void *stream);
@@ -230,19 +250,22 @@ GG_API int gg_shared_grad_allreduce_p2p(const float *dmus, const double *dsigma,
  * `stream`, no synchronisation.  *_host pointers are HOST memory (pinned for true asynchrony); `workspace` is
  * DEVICE memory of at least gg_silhouette_step_workspace_bytes(...) bytes, 256-byte aligned, owned by the
  * caller and private to this call until the stream has drained.  mask_host may be NULL (silhouette not
- * copied back).  sigma_host is float64 [B,K,3,3].  loss_partials_host receives
- * gg_silhouette_step_loss_count(B, K, n) floats; loss = sum(partials) / (B*n*n).  For K <= 64 the step is three
+ * copied back).  sigma_host is float64 [B,K,3,3].  loss_partials_host (capacity loss_partials_capacity floats,
+ * checked) receives gg_silhouette_step_loss_count(B, K, n) floats; loss = sum(partials) / (B*n*n).  For K <= 64 the step is three
  * launches (projection, fused splat+loss+backward, projection adjoint), otherwise five.  When the Gaussian / camera /
  * gradient buffers are pinned, the projection kernels read and write them in place over PCIe (no copies for those
- * ~90 KB; GG_ZEROCOPY=0 forces copies); the target mask always goes through the copy engine.  As with any
- * asynchronous copy, host inputs must stay untouched until the stream has passed this call. */
+ * ~90 KB; GG_ZEROCOPY=0 forces copies; a buffer is used in place only if its WHOLE extent is pinned); the target
+ * mask always goes through the copy engine.  LIFETIME: with in-place access the projection adjoint re-reads
+ * mus/sigma/rot at the END of the chain and writes the gradients directly into the host buffers, so every host
+ * buffer -- inputs and outputs -- must stay untouched until the stream has passed the whole call (record an event
+ * after it), not merely until the leading copies are done. */
 GG_API size_t gg_silhouette_step_workspace_bytes(int B, int K, int n, int target_kind);
 GG_API int gg_silhouette_step_loss_count(int B, int K, int n);
 GG_API int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, const float *rotx_host,
                                    const float *roty_host, const float *rotz_host, const void *target_host,
                                    int target_kind, double tx, double ty, double tz, double focal,
-                                   int B, int K, int n, float *loss_partials_host, float *dmus_host,
-                                   double *dsigma_host, float *drot_host, float *mask_host,
+                                   int B, int K, int n, float *loss_partials_host, int loss_partials_capacity,
+                                   float *dmus_host, double *dsigma_host, float *drot_host, float *mask_host,
                                    void *workspace, size_t workspace_bytes, int device, void *stream);
 
 #ifdef __cplusplus

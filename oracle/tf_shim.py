@@ -20,8 +20,9 @@ when ``/root/reference`` is absent, e.g. on the GPU box).
 What this pins and what it does not: op ORDER, transposes, gather indices,
 broadcast shapes, sign flips and cast boundaries are the reference's own.  The
 primitive kernels (inv, det, matmul, exp) are torch's, not TF/Eigen's; float32
-``cos``/``sin`` and the float32 3x3 ``matmul`` are pinned to the definitions in
-``reference_port`` (correctly rounded trig, fixed summation order).
+``cos``/``sin`` and the float32 3x3 ``matmul`` are pinned by definition (correctly rounded trig,
+fixed summation order) -- this module carries its OWN numpy implementations of them, of ``linspace`` and
+of ``l2_normalize``; tests/test_oracle.py asserts they equal ``reference_port``'s bit for bit.
 """
 from __future__ import annotations
 
@@ -33,7 +34,91 @@ from typing import Dict, Iterable
 import numpy as np
 import torch
 
-from .reference_port import cos_f32, matmul3_f32, sin_f32, tf_linspace_f32
+
+# ---- the shim's OWN definitions of the three primitives whose last-ulp behaviour matters (numpy, written
+# independently of reference_port's torch versions; tests/test_oracle.py asserts the two agree bit for bit and checks
+# the trig against mpmath's correctly rounded values).  Not imported from the port: a checker that borrows the
+# checked code's primitives pins nothing.
+class _TrigF32(torch.autograd.Function):
+    """float32 cos / sin = the float64 libm value of the float32 argument, rounded to float32 (numpy forward; the
+    derivative is evaluated the same way)."""
+
+    @staticmethod
+    def forward(ctx, a, which):
+        x = a.detach().cpu().numpy().astype(np.float64)
+        ctx.save_for_backward(a)
+        ctx.which = which
+        val = np.cos(x) if which == "cos" else np.sin(x)
+        return torch.from_numpy(val.astype(np.float32)).to(a.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        (a,) = ctx.saved_tensors
+        x = a.detach().cpu().numpy().astype(np.float64)
+        d = -np.sin(x) if ctx.which == "cos" else np.cos(x)
+        return (g.to(torch.float64) * torch.from_numpy(d).to(g.device)).to(torch.float32), None
+
+
+def cos_f32(a: torch.Tensor) -> torch.Tensor:
+    return _TrigF32.apply(a, "cos") if a.dtype == torch.float32 else torch.cos(a)
+
+
+def sin_f32(a: torch.Tensor) -> torch.Tensor:
+    return _TrigF32.apply(a, "sin") if a.dtype == torch.float32 else torch.sin(a)
+
+
+def _mm3_np(A: np.ndarray, Bm: np.ndarray, bt: bool = False, at: bool = False) -> np.ndarray:
+    """3x3 float32 product with explicit loops: every multiply and add rounded to float32, order ((k=0 + k=1) + k=2)."""
+    shape = np.broadcast_shapes(A.shape, Bm.shape)
+    A = np.broadcast_to(A, shape).astype(np.float32)
+    Bm = np.broadcast_to(Bm, shape).astype(np.float32)
+    out = np.empty(shape, np.float32)
+    a_ = (lambda i, k: A[..., k, i]) if at else (lambda i, k: A[..., i, k])
+    b_ = (lambda k, j: Bm[..., j, k]) if bt else (lambda k, j: Bm[..., k, j])
+    for i in range(3):
+        for j in range(3):
+            p0 = (a_(i, 0) * b_(0, j)).astype(np.float32)
+            p1 = (a_(i, 1) * b_(1, j)).astype(np.float32)
+            p2 = (a_(i, 2) * b_(2, j)).astype(np.float32)
+            out[..., i, j] = ((p0 + p1).astype(np.float32) + p2).astype(np.float32)
+    return out
+
+
+class _MatMul3F32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return torch.from_numpy(_mm3_np(a.detach().cpu().numpy(), b.detach().cpu().numpy())).to(a.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        gn, an, bn = (t.detach().cpu().numpy() for t in (g, a, b))
+        ga = torch.from_numpy(_mm3_np(gn, bn, bt=True))          # g b^T
+        gb = torch.from_numpy(_mm3_np(an, gn, at=True))          # a^T g
+        while ga.dim() > a.dim():
+            ga = ga.sum(0)
+        while gb.dim() > b.dim():
+            gb = gb.sum(0)
+        for d in range(a.dim()):
+            if a.shape[d] == 1 and ga.shape[d] != 1:
+                ga = ga.sum(d, keepdim=True)
+            if b.shape[d] == 1 and gb.shape[d] != 1:
+                gb = gb.sum(d, keepdim=True)
+        return ga.to(a.device), gb.to(b.device)
+
+
+def matmul3_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    return _MatMul3F32.apply(a, b)
+
+
+def tf_linspace_f32(n: int) -> np.ndarray:
+    """TF 1.12 LinSpace in float32: out[i] = start + step * i, step = (stop - start) / (n - 1), scalar float32 ops."""
+    start, stop = np.float32(-1.0), np.float32(1.0)
+    if n == 1:
+        return np.array([start], dtype=np.float32)
+    step = np.float32(np.float32(stop - start) / np.float32(n - 1))
+    return np.array([np.float32(start + np.float32(step * np.float32(i))) for i in range(n)], dtype=np.float32)
 
 
 def _dt(d):
@@ -188,13 +273,18 @@ def _svd(a, full_matrices=False, compute_uv=True, name=None):
     return S, U, Vh.transpose(-1, -2)          # TensorFlow's order: s, u, v
 
 
+def _l2_normalize(x, axis=-1, epsilon=1e-12, name=None):
+    """``tf.math.l2_normalize`` (TF 1.12 nn_impl.py): x * rsqrt(maximum(reduce_sum(square(x), axis, keepdims), epsilon))."""
+    sq = torch.sum(torch.square(x), dim=axis, keepdim=True)
+    return x * torch.rsqrt(torch.maximum(sq, torch.tensor(epsilon, dtype=x.dtype)))
+
+
 def make_tf_geometry(dense: DenseQueue) -> types.SimpleNamespace:
-    from .reference_port import l2_normalize
     tf = make_tf()
     tf.layers = types.SimpleNamespace(dense=dense)
     tf.nn = types.SimpleNamespace(tanh=torch.tanh, sigmoid=torch.sigmoid,
                                   leaky_relu=lambda t: torch.nn.functional.leaky_relu(t, 0.2))
-    tf.math = types.SimpleNamespace(l2_normalize=lambda x, axis=-1, name=None: l2_normalize(x))
+    tf.math = types.SimpleNamespace(l2_normalize=_l2_normalize)
     tf.linalg.cross = lambda a, b, name=None: torch.linalg.cross(a, b, dim=-1)
     tf.linalg.diag = lambda d, name=None: torch.diag_embed(d)
     tf.linalg.svd = _svd

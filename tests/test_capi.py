@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_constants():
     from gaussigan_b200 import _lib
-    assert _lib.lib.gg_version() == 100
+    assert _lib.lib.gg_version() == 200
     hdr = open(os.path.join(ROOT, "include", "gaussigan.h")).read()
     assert int(re.search(r"#define GG_PARAM_STRIDE (\d+)", hdr).group(1)) == _lib.GG_PARAM_STRIDE
     assert int(re.search(r"#define GG_MOMENTS (\d+)", hdr).group(1)) == _lib.GG_MOMENTS
@@ -117,3 +117,57 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_reference_side_stub_sizes_its_buffers():
+    """INTEGRATION.md section 3 / examples/gaussigan_binding.py: the loss-partials buffer is sized with
+    gg_silhouette_step_loss_count (1024 at B=64, K=16, n=256 -- NOT the 296 of the unfused kernel), and the library
+    rejects a buffer that is too small before touching anything (VERDICT r1 weak #9: the stub used to overflow)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gaussigan_binding", os.path.join(ROOT, "examples", "gaussigan_binding.py"))
+    stub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stub)
+    from gaussigan_b200 import _lib
+    lib = _lib.lib
+    assert stub.loss_partials_count(64, 16, 256) == lib.gg_silhouette_step_loss_count(64, 16, 256) == 64 * 16
+    assert stub.loss_partials_count(4, 65, 64) == 296                      # K > 64: the unfused loss kernel
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert "np.empty(296" not in doc and "gg_silhouette_step_loss_count" in doc
+    # capacity check happens on the host, before any CUDA call: fake (non-NULL, aligned) pointers are never touched
+    fake = C.c_void_p(1 << 20)
+    ws = lib.gg_silhouette_step_workspace_bytes(64, 16, 256, 0)
+    rc = lib.gg_silhouette_step_host(fake, fake, fake, fake, fake, fake, 0, 0., 0., -2., 1., 64, 16, 256,
+                                     fake, 296, fake, fake, fake, None, fake, ws, 0, None)
+    assert rc == -5 and "1024" in _lib.last_error()
+    rc = lib.gg_silhouette_step_host(fake, fake, fake, fake, fake, fake, 0, 0., 0., -2., 1., 64, 16, 256,
+                                     fake, 1024, fake, fake, fake, None, fake, ws - 1, 0, None)
+    assert rc == -5 and "workspace" in _lib.last_error()
+
+
+def test_mode_switches_are_safe_to_flip_from_threads():
+    """gg_set_fast_mask / gg_set_pdl are atomics; the tile count follows the mode in force, and a stale T is
+    rejected by the launch entry points (GG_E_WORKSPACE) instead of being trusted (ADVICE r1)."""
+    import threading
+    from gaussigan_b200 import _lib
+    lib, ia = _lib.lib, _lib.int_array
+    t_fast = lib.gg_splat_bwd_tiles(16, 1, ia([256]), ia([0]), ia([1]), 0)
+    stop = threading.Event()
+
+    def flipper():
+        while not stop.is_set():
+            lib.gg_set_fast_mask(0)
+            lib.gg_set_fast_mask(1)
+
+    th = threading.Thread(target=flipper)
+    th.start()
+    try:
+        seen = {lib.gg_splat_bwd_tiles(16, 1, ia([256]), ia([0]), ia([1]), 0) for _ in range(20000)}
+    finally:
+        stop.set()
+        th.join()
+        lib.gg_set_fast_mask(1)
+    assert seen <= {t_fast, 32} and t_fast in seen          # only the two modes' answers, never garbage
+    # a launch with a T that does not match the mode in force is refused on the host side
+    fake = C.c_void_p(1 << 20)
+    rc = lib.gg_splat_bwd(fake, 2, 16, 1, ia([256]), None, _lib.ptr_array([1 << 20]), 0, fake, t_fast + 1, 0, None)
+    assert rc == -5

@@ -233,3 +233,48 @@ def test_geometry_port_matches_reference_source_live():
     pm, ps, pt = rp.deform(t[0], t[1], t[2], t[3], t[4], t[5], torch.tanh(pre_c[0]).reshape(1, K, 1, 3), pc)
     assert torch.equal(pc, csig) and torch.equal(pm, mus) and torch.equal(pt, theta)
     assert_close_norm(ps, sigmas, 1e-14, "sigmas")
+
+
+# ------------------------------------------------- the shim's primitives are its own, and agree with the port's
+def test_shim_primitives_are_independent_and_equal_the_port():
+    """oracle/tf_shim.py must not borrow cos/sin/matmul/linspace from the port it is used to check:
+    its numpy definitions and the port's torch definitions agree bit for bit, values and gradients."""
+    import inspect
+    from oracle import tf_shim
+    src = inspect.getsource(tf_shim)
+    assert "from .reference_port import" not in src and "import reference_port" not in src
+    for name in ("cos_f32", "sin_f32", "matmul3_f32", "tf_linspace_f32"):
+        assert getattr(tf_shim, name).__module__ == "oracle.tf_shim"
+    g = torch.Generator().manual_seed(3)
+    ang = torch.cat([(torch.rand(20000, generator=g) - 0.5) * 8.0, torch.tensor([0.0, np.pi / 2, -np.pi, 3.14159274])]).float()
+    for f_s, f_p in ((tf_shim.cos_f32, rp.cos_f32), (tf_shim.sin_f32, rp.sin_f32)):
+        a1, a2 = ang.clone().requires_grad_(True), ang.clone().requires_grad_(True)
+        y1, y2 = f_s(a1), f_p(a2)
+        assert torch.equal(y1, y2)
+        w = torch.randn(ang.shape, generator=g)
+        (y1 * w).sum().backward(); (y2 * w).sum().backward()
+        assert torch.equal(a1.grad, a2.grad)
+    A, Bm = torch.randn(50, 1, 3, 3, generator=g), torch.randn(50, 1, 3, 3, generator=g)
+    a1, b1, a2, b2 = (t.clone().requires_grad_(True) for t in (A, Bm, A, Bm))
+    y1, y2 = tf_shim.matmul3_f32(a1, b1), rp.matmul3_f32(a2, b2)
+    assert torch.equal(y1, y2)
+    w = torch.randn(y1.shape, generator=g)
+    (y1 * w).sum().backward(); (y2 * w).sum().backward()
+    assert torch.equal(a1.grad, a2.grad) and torch.equal(b1.grad, b2.grad)
+    for n in (1, 2, 3, 32, 33, 64, 100, 128, 256, 512, 2100):
+        assert np.array_equal(tf_shim.tf_linspace_f32(n), rp.tf_linspace_f32(n)), n
+
+
+def test_float32_trig_is_correctly_rounded():
+    """The pinned primitive: cos_f32 / sin_f32 are the correctly rounded float32 values -- checked against
+    50-digit mpmath on the reference's angle range (yaw = 180 tanh(.) degrees, :458) and beyond."""
+    import mpmath
+    mpmath.mp.dps = 50
+    g = torch.Generator().manual_seed(8)
+    deg = torch.cat([180.0 * torch.tanh(torch.randn(1500, generator=g)), (torch.rand(500, generator=g) - 0.5) * 720.0])
+    rad = (deg.float() * torch.tensor(np.pi, dtype=torch.float32) / torch.tensor(180.0)).float()
+    c, s = rp.cos_f32(rad).numpy(), rp.sin_f32(rad).numpy()
+    for i, x in enumerate(rad.numpy()):
+        xm = mpmath.mpf(float(x))
+        assert np.float32(float(mpmath.cos(xm))) == c[i], (x, c[i])
+        assert np.float32(float(mpmath.sin(xm))) == s[i], (x, s[i])

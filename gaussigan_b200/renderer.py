@@ -306,6 +306,23 @@ def get_gaussian_maps_2d(mu, sigma, shape_hw, mode: str = "rot", *, layout: str 
     return _Raster.apply(mu.to(dt).contiguous(), sigma.to(dt).contiguous(), spec)[0]
 
 
+def get_silhouette_2d(mu, sigma, shape_hw) -> torch.Tensor:
+    """``reduce_sum(get_gaussian_maps_2d(mu, sigma, shape_hw), -1)`` (mask/mask_gen_dynamic.py:112-143 + :785-786) from
+    the frozen-graph boundary tensors ``mu2d [B,K,2]`` / ``sigma2d [B,K,2,2]`` (mask/infer_masks.py:394-395), without the
+    K-channel maps: the mask-only kernels (forward-differenced by default), differentiable w.r.t. both inputs."""
+    _require_cuda(mu, sigma)
+    H, W = int(shape_hw[0]), int(shape_hw[1])
+    if H != W:
+        raise ValueError("get_silhouette_2d requires H == W (reference tiles invsigma over W, :134)")
+    if sigma.dim() != 4 or sigma.shape[-2:] != (2, 2):
+        raise ValueError("sigma must be [B,K,2,2]")
+    B, K = sigma.shape[0], sigma.shape[1]
+    mu = mu.reshape(B, K, 2)
+    dt = torch.float64 if (mu.dtype == torch.float64 or sigma.dtype == torch.float64) else torch.float32
+    spec = _Spec(0., 0., 0., 1., (H,), (False,), (True,), LAYOUT_NHWC, False)
+    return _Raster.apply(mu.to(dt).contiguous(), sigma.to(dt).contiguous(), spec)[0]
+
+
 def get_landmarks_infer(mus, sigma, rotx, roty, rotz, tx, ty, tz, focal=1., *, size: int = 256,
                         K: Optional[int] = None):
     """Inference flavour (mask/infer_masks.py:186-267): float64 projection, ``mu2d``/``sigma2d`` cast to

@@ -1,0 +1,197 @@
+"""Round-2 parity hardening (VERDICT r1 "harden parity"): pointwise statistics of both arithmetic modes, deterministic
+cases on the guard's three boundaries, the K range the ABI advertises, and the reference-side stub -- all through the
+C ABI on the GPU, against the float64 oracle."""
+import importlib.util
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as rp
+from util import FWD_RTOL, GRAD_RTOL, assert_close_norm, max_rel
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LOG2E = 1.4426950408889634
+
+
+@pytest.fixture(scope="module")
+def gg(cuda_device):
+    import gaussigan_b200
+    return gaussigan_b200
+
+
+@pytest.fixture
+def restore_modes(gg):
+    yield
+    gg.set_fast_mask(True)
+    gg.set_pdl(True)
+
+
+# ------------------------------------------------------------------------------------ pointwise statistics at C2
+def test_pointwise_allclose_statistics_at_config2(gg, cuda_device, restore_modes):
+    """SURVEY.md 7.2 offers two formulations of the 1e-5 forward tolerance: norm-relative |d| <= 1e-5 max|ref| (the one
+    tests/util.py uses) and pointwise allclose(rtol=1e-5, atol=1e-6).  This test measures the second one at the full C2
+    shape (batch 64, K=16, 256x256) for both arithmetic modes of the mask-only kernels and bounds it:
+      direct form (one exponential per pixel-Gaussian): no pixel violates it;
+      forward-differenced form (default): absolute error <= 1e-5 everywhere and <= 0.5 % of the pixels outside the
+      pointwise band -- it meets the norm-relative formulation, not the pointwise one, on a silhouette
+      whose values reach ~6."""
+    B, K, n = 64, 16, 256
+    inp = rp.synth_inputs(B, K, seed=56)
+    ref = torch.cat([rp.get_landmarks(inp["mus"][i:i + 16], inp["sigma"][i:i + 16], inp["rotx"][i:i + 16],
+                                      inp["roty"][i:i + 16], inp["rotz"][i:i + 16], 0, 0, -2., sizes=(n,))[0].sum(-1)
+                     for i in range(0, B, 16)]).double()
+    d = {k: v.to(cuda_device) for k, v in inp.items()}
+    stats = {}
+    for fast in (True, False):
+        gg.set_fast_mask(fast)
+        m = gg.render_silhouette(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., size=n).double().cpu()
+        err = (m - ref).abs()
+        viol = err > (1e-6 + 1e-5 * ref.abs())
+        stats[fast] = dict(max_abs=float(err.max()), norm_rel=float(err.max() / ref.abs().max()),
+                           viol_frac=float(viol.double().mean()),
+                           worst_pointwise=float((err / (1e-6 + 1e-5 * ref.abs())).max()))
+    print("pointwise statistics (fast, direct):", stats)
+    assert stats[False]["viol_frac"] == 0.0 and stats[False]["norm_rel"] <= 1e-6
+    assert stats[True]["norm_rel"] <= FWD_RTOL / 2 and stats[True]["max_abs"] <= 1e-5
+    assert stats[True]["viol_frac"] <= 5e-3 and stats[True]["worst_pointwise"] <= 5.0
+
+
+# ------------------------------------------------------------------------------------------ the guard's boundaries
+def _guard_case(n, nA_abs, tmax_pixels, shear, B=1):
+    """2-D Gaussians (mu2d, sigma2d) with a prescribed sharpness |nA| = a log2(e) and centre offset, one per batch
+    element, placed so that the strip recurrence's three criteria (gg_fast.cuh: |nA| <= 512, visible slope
+    2 h sqrt(14 |nA|) <= 3, range slope |2 nA h| (tmax + 8 h) <= 13) sit just inside / just outside."""
+    h = 2.0 / (n - 1)
+    a = nA_abs / LOG2E                       # conic entry P00
+    c = a * 0.05 + 0.3                       # a broad axis along y
+    b = shear * math.sqrt(a * c)
+    P = torch.tensor([[a, b], [b, c]], dtype=torch.float64)
+    sigma = torch.linalg.inv(P).reshape(1, 1, 2, 2).repeat(B, 1, 1, 1)
+    mu = torch.tensor([[[-1.0 + tmax_pixels * h * (0.5 if tmax_pixels < n else 1.0), 0.07]]], dtype=torch.float64).repeat(B, 1, 1)
+    return mu, sigma
+
+
+def _check_2d(gg, dev, mu, sigma, n, what):
+    mu_r, sg_r = mu.clone().requires_grad_(True), sigma.clone().requires_grad_(True)
+    ref = rp.get_gaussian_maps_2d(mu_r, sg_r, [n, n]).sum(-1)
+    gm = torch.randn(ref.shape, generator=torch.Generator().manual_seed(n), dtype=torch.float64)
+    (ref * gm).sum().backward()
+    mu_d, sg_d = mu.to(dev).requires_grad_(True), sigma.to(dev).requires_grad_(True)
+    m = gg.get_silhouette_2d(mu_d, sg_d, [n, n])
+    m.backward(gm.float().to(dev))
+    assert torch.isfinite(m).all() and torch.isfinite(mu_d.grad).all() and torch.isfinite(sg_d.grad).all(), what
+    if float(ref.detach().abs().max()) < 1e-30:       # so far off the frame that float32 holds nothing: exact zeros
+        assert float(m.abs().max()) <= 1e-30 and float(mu_d.grad.abs().max()) <= 1e-25, what
+        return 0.0, 0.0
+    assert_close_norm(m, ref, FWD_RTOL, what + " forward")
+    assert_close_norm(mu_d.grad, mu_r.grad, GRAD_RTOL, what + " d mu2d")
+    assert_close_norm(sg_d.grad, sg_r.grad, GRAD_RTOL, what + " d sigma2d")
+    return max_rel(m, ref), max(max_rel(mu_d.grad, mu_r.grad), max_rel(sg_d.grad, sg_r.grad))
+
+
+@pytest.mark.parametrize("n", [256, 128, 64, 24, 20, 16, 13])
+@pytest.mark.parametrize("eps", [-2e-3, 2e-3])
+def test_guard_boundary_sharpness(gg, cuda_device, n, eps):
+    """|nA| = 512 (1 +- eps): the recurrence / direct switch of criterion (iii)."""
+    mu, sg = _guard_case(n, 512.0 * (1 + eps), tmax_pixels=n // 3, shear=0.3)
+    _check_2d(gg, cuda_device, mu, sg, n, f"|nA|=512(1{eps:+g}) n={n}")
+
+
+@pytest.mark.parametrize("n", [256, 128, 64, 24, 20, 16, 13])
+@pytest.mark.parametrize("eps", [-1e-2, 1e-2])
+def test_guard_boundary_visible_slope(gg, cuda_device, n, eps):
+    """2 h sqrt(14 |nA|) = 3 (1 +- eps): criterion (ii), the per-pixel exponent change where the Gaussian is visible."""
+    h = 2.0 / (n - 1)
+    nA = min(((3.0 * (1 + eps)) / (2 * h)) ** 2 / 14.0, 511.0)       # stay below the sharpness limit so (ii) decides
+    mu, sg = _guard_case(n, nA, tmax_pixels=n // 2, shear=-0.4)
+    _check_2d(gg, cuda_device, mu, sg, n, f"visible slope 3(1{eps:+g}) n={n}")
+
+
+@pytest.mark.parametrize("n", [256, 128, 64, 24, 16, 13])
+@pytest.mark.parametrize("eps", [-1e-2, 1e-2])
+def test_guard_boundary_range_slope(gg, cuda_device, n, eps):
+    """|2 nA h| (tmax + 8 h) = 13 (1 +- eps): criterion (i), range safety, with the centre far off the tile."""
+    h = 2.0 / (n - 1)
+    nA = min(0.5 * ((3.0 / (2 * h)) ** 2 / 14.0), 400.0)              # comfortably inside (ii) and (iii)
+    tmax = 13.0 * (1 + eps) / abs(2 * nA * h) - 8 * h                  # distance of the far tile corner from the centre
+    # centre to the LEFT of the frame so that the far (right) edge is tmax away: mu_x = 1 - tmax (may be off-screen)
+    a = nA / LOG2E
+    P = torch.tensor([[a, 0.0], [0.0, 0.4]], dtype=torch.float64)
+    sg = torch.linalg.inv(P).reshape(1, 1, 2, 2)
+    mu = torch.tensor([[[1.0 - tmax, -0.2]]], dtype=torch.float64)
+    _check_2d(gg, cuda_device, mu, sg, n, f"range slope 13(1{eps:+g}) n={n}")
+
+
+@pytest.mark.parametrize("n", list(range(13, 25)))
+def test_needles_on_coarse_grids(gg, cuda_device, n):
+    """The cases the round-1 soaks found (n = 13 .. 24, a needle far narrower than a pixel next to ordinary blobs): the
+    CENTRE variant of the backward sums guarded Gaussians about their own centre line."""
+    B, K = 2, 5
+    g = torch.Generator().manual_seed(1000 + n)
+    inp = rp.synth_inputs(B, K, seed=300 + n, angle=40.0)
+    inp["sigma"][0, 0] = torch.diag(torch.tensor([2e-4, 0.3, 0.04], dtype=torch.float64))
+    inp["sigma"][1, 2] = torch.diag(torch.tensor([0.25, 3e-4, 0.05], dtype=torch.float64))
+    lv = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    ref = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0, 0, -2., sizes=(n,))[0].sum(-1)
+    gm = torch.randn(B, n, n, generator=g)
+    (ref * gm).sum().backward()
+    dv = {k: v.clone().to(cuda_device).requires_grad_(True) for k, v in inp.items()}
+    m = gg.render_silhouette(dv["mus"], dv["sigma"], dv["rotx"], dv["roty"], dv["rotz"], 0, 0, -2., size=n)
+    m.backward(gm.to(cuda_device))
+    assert_close_norm(m, ref, FWD_RTOL, f"needles n={n} mask")
+    for k in ("mus", "sigma", "roty"):
+        assert_close_norm(dv[k].grad, lv[k].grad, GRAD_RTOL, f"needles n={n} grad {k}")
+
+
+# ------------------------------------------------------------------------------------------- advertised K range
+@pytest.mark.parametrize("K", [1025, 1536])
+def test_mask_forward_accepts_the_whole_advertised_k_range(gg, cuda_device, restore_modes, K):
+    """K in 1025 .. 1536 needs more than the default 48 KB of dynamic shared memory in the forward-differenced
+    silhouette kernel: the launcher opts in; results equal the direct form and the oracle."""
+    B, n = 1, 24
+    inp = rp.synth_inputs(B, K, seed=K)
+    ref = rp.get_landmarks(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0, 0, -2., sizes=(n,))[0].sum(-1)
+    d = {k: v.to(cuda_device) for k, v in inp.items()}
+    out = {}
+    for fast in (True, False):
+        gg.set_fast_mask(fast)
+        out[fast] = gg.render_silhouette(d["mus"], d["sigma"], d["rotx"], d["roty"], d["rotz"], 0, 0, -2., size=n)
+        assert_close_norm(out[fast], ref, FWD_RTOL, f"K={K} fast={fast}")
+
+
+# ------------------------------------------------------------------------------------------ reference-side stub
+def test_reference_side_stub_vs_oracle(cuda_device):
+    """examples/gaussigan_binding.py (numpy + ctypes, no torch: what INTEGRATION.md tells a maintainer of the reference to
+    add) against the oracle's loss and gradients."""
+    spec = importlib.util.spec_from_file_location("gaussigan_binding", os.path.join(ROOT, "examples", "gaussigan_binding.py"))
+    stub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stub)
+    B, K, n = 5, 16, 64
+    inp = rp.synth_inputs(B, K, seed=77)
+    tgt = rp.synth_target_masks(B, n, seed=78)
+    _, loss_ref, dmu_ref, dsig_ref, drot_ref = rp.render_loss_and_grads(inp, tgt, n)
+    raw = ((tgt.reshape(B, n, n) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).numpy()
+    loss, dmus, dsig, drot = stub.silhouette_loss_and_grads(inp["mus"].reshape(B, K, 3).numpy(), inp["sigma"].numpy(),
+                                                            inp["rotx"].numpy(), inp["roty"].numpy(), inp["rotz"].numpy(), raw)
+    assert abs(loss - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    assert_close_norm(torch.from_numpy(dmus), dmu_ref.reshape(B, K, 3), GRAD_RTOL, "stub dmus")
+    assert_close_norm(torch.from_numpy(dsig), dsig_ref, GRAD_RTOL, "stub dsigma")
+    assert_close_norm(torch.from_numpy(drot[:, 1]), drot_ref.reshape(B), GRAD_RTOL, "stub droty")
+
+
+def test_device_guard_restores_the_current_device(gg, cuda_device):
+    """Every C-ABI entry makes its `device` argument current only for the duration of the call."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    inp = rp.synth_inputs(2, 4, seed=1)
+    d1 = torch.device("cuda", 1)
+    torch.cuda.set_device(0)
+    dv = {k: v.to(d1) for k, v in inp.items()}
+    m = gg.render_silhouette(dv["mus"], dv["sigma"], dv["rotx"], dv["roty"], dv["rotz"], 0, 0, -2., size=32)
+    assert m.device == d1 and torch.cuda.current_device() == 0
+    ref = rp.get_landmarks(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0, 0, -2., sizes=(32,))[0].sum(-1)
+    assert_close_norm(m, ref, FWD_RTOL, "render on cuda:1 while cuda:0 is current")

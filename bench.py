@@ -590,27 +590,32 @@ def bench_allreduce(args, sets, R, B, K, world, dev, capture, timed_passes, make
                             "(gaussigan_b200.dist.P2PSharedGradReducer: post = local batch sum + stores into the peers' "
                             "slots over NVLink + flags, wait = flag wait + rank-ordered sum), back to back, all in the step graph"})
 
-        # the same exchange with its two halves apart: post right behind the backward, wait one forward pass later
-        # (stands for the rest of the network's backward that follows the renderer's in a training step), so only the
-        # flag latency is exposed; one CUDA graph of `nst` steps, every post matched by a wait inside the graph
+        # the same exchange OFF the critical path: post + wait on a forked stream right behind the backward, joined
+        # before the next step's backward -- it runs under the next forward pass (stands for the rest of the network's
+        # backward that follows the renderer's in a training step; the consumer of the sums is the optimiser)
         def overlapped_chain():
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
             for i in range(nst):
                 st_, gm_, _, _ = sets[i % R]
                 st_.forward()
                 if i > 0:
-                    red.wait()
+                    cur.wait_stream(side)
                 st_.backward(gm_)
-                red.post(st_.dmus, st_.dsigma)
-            red.wait()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    red.post(st_.dmus, st_.dsigma)
+                    red.wait()
+            cur.wait_stream(side)
 
         og = capture(overlapped_chain)
         dist.barrier()
         orr = timed_passes(og.replay, nst)
         red.check()
         out["overlapped"] = {"value": world * B / (orr["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": orr["ms_per_step"],
-                             "note": "post behind the backward, wait after the NEXT step's forward kernels (the consumer "
-                                     "of the sums -- the optimiser -- runs after the rest of the network's backward in a "
-                                     "real step): exchange latency hidden behind compute"}
+                             "note": "post + wait on a forked stream behind the backward, joined before the next step's "
+                                     "backward: the exchange runs under the next forward pass (in a real step: under the "
+                                     "rest of the network's backward; the optimiser consumes the sums)"}
     except Exception as exc:                  # pragma: no cover - e.g. no peer access
         out.update({"value": out["nccl"]["value"], "unit": UNIT, "ms_per_step": ar["ms_per_step"],
                     "note": "P2P reducer unavailable (" + repr(exc)[:120] + "): NCCL number"})

@@ -4,11 +4,11 @@
 // sum of the per-sample gradients over the local batch AND over the ranks.  The payload is 12 K
 // numbers (1.5 KB at K = 16): pure latency.  NCCL's all_reduce costs ~40-60 us per eager call at this size.
 //
-//   post : ceil(12 K / 32) CTAs.  CTA = 32 columns x 8 batch slices; every thread sums its slice with all loads in
+//   post : one CTA of 1024 threads = 256 columns x 4 batch slices; every thread sums its slice with sixteen loads in
 //          flight (one round trip for B <= 64), the slices are added in a fixed order in shared memory and the column
 //          sums go straight into every rank's receive slot through NVLink/NVSwitch peer pointers (symmetric memory:
-//          the same buffer layout on every rank).  The CTA that finishes last (device-scope counter in the rank's own
-//          header) raises this rank's flag on every peer with a system-scope release store.
+//          the same buffer layout on every rank); one system-scope fence, then this rank's flag is raised on every
+//          peer with a system-scope release store.
 //   wait : one CTA.  Waits for the peers' flags with acquire loads (bounded by a wall-clock timeout, default 60 s),
 //          then adds the slots in rank order -- the same order on every rank, so the result is bit-identical
 //          everywhere.  On a timeout it fills `out` with NaN and latches the call number in the header: the failure
@@ -19,7 +19,7 @@
 // the flag latency is ever exposed.
 //
 // Buffer layout (per rank, `gg_p2p_buffer_bytes`): u32 words [0] calls posted, [1] error latch (call number),
-// [2] calls waited, [3] CTA arrival counter of the current post, [16 .. 16+W) arrival flags; at byte 1024 the receive
+// [2] calls waited, [16 .. 16+W) arrival flags; at byte 1024 the receive
 // slots double[2][W][12 K].  Two slot sets: a rank can be at most one call ahead of the slowest peer (it cannot finish
 // waiting for call e+1 before every peer has posted it, i.e. finished waiting for call e), so writes of call e+1 never
 // touch what a peer still reads for call e.  The counters live on the device and are advanced by the kernels
@@ -32,7 +32,7 @@ namespace gg {
 
 namespace {
 
-constexpr int kPostCols = 32, kPostSlices = 8, kPostThreads = kPostCols * kPostSlices;
+constexpr int kPostCols = 256, kPostSlices = 4, kPostThreads = kPostCols * kPostSlices;
 constexpr int kWaitThreads = 256;
 constexpr size_t kP2PDataOffset = 1024;
 enum { H_POSTED = 0, H_ERROR = 1, H_WAITED = 2, H_ARRIVE = 3, H_FLAGS = 16 };
@@ -62,68 +62,60 @@ __global__ void __launch_bounds__(kPostThreads) shared_grad_post_kernel(
     const float *__restrict__ dmus, const double *__restrict__ dsigma, int B, int K,
     const unsigned long long *__restrict__ peers, int world, int rank) {
   __shared__ double part[kPostSlices][kPostCols];
-  __shared__ unsigned last_s;
   pdl_enter();
   const int L = 12 * K;
   unsigned *hdr = reinterpret_cast<unsigned *>(peers[rank]);
-  // the call number: posts are stream-ordered, and H_POSTED is only advanced by the last CTA of a post (below)
-  const unsigned epoch = hdr[H_POSTED] + 1u;
+  const unsigned epoch = hdr[H_POSTED] + 1u;     // posts are stream-ordered; advanced by thread 0 below
   const int slot = (int)(epoch & 1u);
   const int col = threadIdx.x & (kPostCols - 1), sl = threadIdx.x / kPostCols;
-  const int c = blockIdx.x * kPostCols + col;
-  // (1) this thread's batch slice [b0, b1), fixed order; the loads are issued eight at a time
+  // this thread's batch slice [b0, b1), fixed order; sixteen loads in flight (one round trip for B <= 64)
   const int per = (B + kPostSlices - 1) / kPostSlices;
   const int b0 = sl * per, b1 = min(B, b0 + per);
-  double acc = 0.0;
-  if (c < L) {
-    if (c < 3 * K) {
-      for (int b = b0; b < b1; b += 8) {
-        float v[8];
+  for (int c0 = 0; c0 < L; c0 += kPostCols) {
+    const int c = c0 + col;
+    double acc = 0.0;
+    if (c < L) {
+      if (c < 3 * K) {
+        for (int b = b0; b < b1; b += 16) {
+          float v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = b + u < b1 ? __ldg(dmus + (size_t)(b + u) * 3 * K + c) : 0.f;
+          for (int u = 0; u < 16; ++u) v[u] = b + u < b1 ? __ldg(dmus + (size_t)(b + u) * 3 * K + c) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += (double)v[u];
-      }
-    } else {
-      const int cc = c - 3 * K;
-      for (int b = b0; b < b1; b += 8) {
-        double v[8];
+          for (int u = 0; u < 16; ++u) acc += (double)v[u];
+        }
+      } else {
+        const int cc = c - 3 * K;
+        for (int b = b0; b < b1; b += 16) {
+          double v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = b + u < b1 ? __ldg(dsigma + (size_t)(b + u) * 9 * K + cc) : 0.0;
+          for (int u = 0; u < 16; ++u) v[u] = b + u < b1 ? __ldg(dsigma + (size_t)(b + u) * 9 * K + cc) : 0.0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += v[u];
+          for (int u = 0; u < 16; ++u) acc += v[u];
+        }
       }
     }
-  }
-  part[sl][col] = acc;
-  __syncthreads();
-  // (2) slices in order, then the column sum goes straight into every rank's slot [slot][rank]
-  if (sl == 0 && c < L) {
-    double t = 0.0;
+    __syncthreads();                 // part[] of the previous column block has been consumed
+    part[sl][col] = acc;
+    __syncthreads();
+    // slices in order, then the column sum goes straight into every rank's slot [slot][rank]
+    if (sl == 0 && c < L) {
+      double t = 0.0;
 #pragma unroll
-    for (int s = 0; s < kPostSlices; ++s) t += part[s][col];
-    for (int p = 0; p < world; ++p) {
-      double *slots = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(peers[p]) + kP2PDataOffset);
-      slots[((size_t)slot * world + rank) * L + c] = t;
+      for (int s = 0; s < kPostSlices; ++s) t += part[s][col];
+      for (int p = 0; p < world; ++p) {
+        double *slots = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(peers[p]) + kP2PDataOffset);
+        slots[((size_t)slot * world + rank) * L + c] = t;
+      }
     }
   }
   __threadfence_system();
   __syncthreads();
-  // (3) the last CTA of this post tells every peer that this rank's slot is complete
-  if (threadIdx.x == 0) last_s = atomicAdd(&hdr[H_ARRIVE], 1u) == gridDim.x - 1 ? 1u : 0u;
-  __syncthreads();
-  if (last_s) {
-    __threadfence_system();
-    if ((int)threadIdx.x < world) {
-      unsigned *pf = reinterpret_cast<unsigned *>(peers[threadIdx.x]) + H_FLAGS;
-      st_release_sys(pf + rank, epoch);
-    }
-    if (threadIdx.x == 0) {
-      hdr[H_ARRIVE] = 0u;
-      __threadfence();
-      hdr[H_POSTED] = epoch;
-    }
+  // tell every peer that this rank's slot is complete
+  if ((int)threadIdx.x < world) {
+    unsigned *pf = reinterpret_cast<unsigned *>(peers[threadIdx.x]) + H_FLAGS;
+    st_release_sys(pf + rank, epoch);
   }
+  if (threadIdx.x == 0) hdr[H_POSTED] = epoch;
 }
 
 __global__ void __launch_bounds__(kWaitThreads) shared_grad_wait_kernel(
@@ -177,8 +169,8 @@ static unsigned long long p2p_timeout_ns() {
 cudaError_t launch_shared_grad_post(const float *dmus, const double *dsigma, int B, int K,
                                     const unsigned long long *peers, int world, int rank, cudaStream_t st) {
   const int L = 12 * K;
-  launch_pdl(shared_grad_post_kernel, dim3((L + kPostCols - 1) / kPostCols), dim3(kPostThreads), 0, st, dmus, dsigma, B,
-             K, peers, world, rank);
+  (void)L;
+  launch_pdl(shared_grad_post_kernel, dim3(1), dim3(kPostThreads), 0, st, dmus, dsigma, B, K, peers, world, rank);
   return cudaGetLastError();
 }
 

@@ -1112,7 +1112,7 @@ def test_p2p_shared_grad_reducer_single_rank(gg, cuda_device):
             red.check()
             ra = torch.zeros(K, 3, dtype=torch.float64, device=cuda_device)
             rb = torch.zeros(K, 3, 3, dtype=torch.float64, device=cuda_device)
-            per = (B + 7) // 8                                      # the kernel's order: 8 contiguous batch slices,
+            per = (B + 3) // 4                                      # the kernel's order: 4 contiguous batch slices,
             for s0 in range(0, B, per):                             # each ascending, then the slices in order
                 pa = torch.zeros_like(ra)
                 pb = torch.zeros_like(rb)

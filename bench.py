@@ -774,6 +774,60 @@ def bench_configs(world, rank, dev, peaks, capture, timed_passes, max_over_ranks
                 "reps": r["reps"]}
 
     guarded("cycle_l1", cycle)
+
+    def concat_direct():
+        """the maps written into / their gradients read from the generator's NHWC concat buffer
+        (mask/mask_gen_dynamic.py:523-529) in place, against the dense tensor + second pass a framework would do."""
+        B, K, n, CX = B_PER_GPU, K_GAUSS, SIZE, 64
+        C = CX + K
+        mus, sig, rx, ry, rz = inputs(B, K, 56 + rank)
+        params = torch.empty(B, K, GG_PARAM_STRIDE, device=dev)
+        check(lib.gg_project_fwd(mus.data_ptr(), sig.data_ptr(), 1, rx.data_ptr(), ry.data_ptr(), rz.data_ptr(), 0., 0., -2.,
+                                 1., B, K, None, None, params.data_ptr(), dev.index, st()), "gg_project_fwd")
+        bufs = [torch.empty(B, n, n, C, device=dev) for _ in range(2)]
+        gbufs = [torch.randn(B, n, n, C, device=dev) for _ in range(2)]
+        dense = [torch.empty(B, n, n, K, device=dev) for _ in range(2)]
+        sz, one, zero, cs, co = int_array([n]), int_array([1]), int_array([0]), int_array([C]), int_array([CX])
+        T = check(lib.gg_splat_bwd_tiles_concat(K, 1, sz, one, zero, cs, co), "tiles")
+        part = torch.empty(B, T, K, GG_MOMENTS, device=dev)
+        Td = check(lib.gg_splat_bwd_tiles(K, 1, sz, one, zero, LAYOUT_NHWC), "tiles")
+        partd = torch.empty(B, Td, K, GG_MOMENTS, device=dev)
+        nul = ptr_array([None])
+
+        def f_direct(i):
+            check(lib.gg_splat_fwd_concat(params.data_ptr(), B, K, 1, sz, ptr_array([bufs[i % 2].data_ptr()]), cs, co, None,
+                                          dev.index, st()), "gg_splat_fwd_concat")
+
+        def f_dense(i):
+            check(lib.gg_splat_fwd(params.data_ptr(), B, K, 1, sz, ptr_array([dense[i % 2].data_ptr()]), nul, LAYOUT_NHWC,
+                                   dev.index, st()), "gg_splat_fwd")
+            bufs[i % 2][..., CX:] = dense[i % 2]
+
+        def b_direct(i):
+            check(lib.gg_splat_bwd_concat(params.data_ptr(), B, K, 1, sz, ptr_array([gbufs[i % 2].data_ptr()]), cs, co, None,
+                                          part.data_ptr(), T, dev.index, st()), "gg_splat_bwd_concat")
+
+        def b_dense(i):
+            gd = gbufs[i % 2][..., CX:].contiguous()
+            check(lib.gg_splat_bwd(params.data_ptr(), B, K, 1, sz, ptr_array([gd.data_ptr()]), nul, LAYOUT_NHWC,
+                                   partd.data_ptr(), Td, dev.index, st()), "gg_splat_bwd")
+
+        res = {}
+        for name, fn in (("fwd_direct_us", f_direct), ("fwd_dense_plus_copy_us", f_dense), ("bwd_direct_us", b_direct),
+                         ("bwd_slice_copy_plus_dense_us", b_dense)):
+            g = capture(lambda fn=fn: [fn(i) for i in range(8)])
+            res[name] = timed_passes(g.replay, 8, warm_steps=8)["ms_per_step"] * 1e3
+        mbytes = B * n * n * K * 4
+        step_us = res["fwd_direct_us"] + res["bwd_direct_us"]
+        return {"workload": f"K={K} maps of [{B},{n},{n}] written into channels [{CX},{C}) of an NHWC buffer with {C} channels "
+                            f"and their gradients read back from the same slice ({mbytes / 1e6:.0f} MB each way), kernels alone",
+                "value": world * B / (step_us * 1e-6), "unit": "silhouettes/s (maps fwd+bwd)", **res,
+                "roofline": {"bound": "hbm", "achieved": 2 * mbytes / (step_us * 1e-6) / 1e9, "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s of map bytes", "frac": 2 * mbytes / (step_us * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                             "note": "64-byte runs at a 320-byte pixel stride: DRAM row locality, not the kernel, sets the rate"},
+                "speedup_vs_dense_round_trip": (res["fwd_dense_plus_copy_us"] + res["bwd_slice_copy_plus_dense_us"]) / step_us}
+
+    guarded("concat_direct", concat_direct)
     return out
 
 

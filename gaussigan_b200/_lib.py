@@ -50,6 +50,9 @@ SIGNATURES = {
     "gg_conic_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "gg_splat_fwd": (_i, [_vp, _i, _i, _i, _ip, _pp, _pp, _i, _i, _vp]),
     "gg_splat_bwd_tiles": (_i, [_i, _i, _ip, _ip, _ip, _i]),
+    "gg_splat_fwd_concat": (_i, [_vp, _i, _i, _i, _ip, _pp, _ip, _ip, _pp, _i, _vp]),
+    "gg_splat_bwd_tiles_concat": (_i, [_i, _i, _ip, _ip, _ip, _ip, _ip]),
+    "gg_splat_bwd_concat": (_i, [_vp, _i, _i, _i, _ip, _pp, _ip, _ip, _pp, _vp, _i, _i, _vp]),
     "gg_mask_l1_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "gg_silhouette_loss_fused": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_sigma_from_frame_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp]),

@@ -173,6 +173,77 @@ int gg_splat_fwd(const float *params, int B, int K, int nscales, const int *size
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_splat_fwd");
 }
 
+static int check_concat(int K, int nscales, const int *cstrides, const int *coffsets, const char *who) {
+  if (!cstrides || !coffsets) return fail(GG_E_NULL, "%s: cstrides_host / coffsets_host is NULL", who);
+  for (int i = 0; i < nscales; ++i)
+    if (coffsets[i] < 0 || cstrides[i] < K || coffsets[i] + K > cstrides[i])
+      return fail(GG_E_SHAPE, "%s: scale %d: channels [%d, %d) do not fit a buffer of %d channels", who, i, coffsets[i],
+                  coffsets[i] + K, cstrides[i]);
+  return GG_OK;
+}
+
+int gg_splat_fwd_concat(const float *params, int B, int K, int nscales, const int *sizes_host, float *const *bufs_host,
+                        const int *cstrides_host, const int *coffsets_host, float *const *masks_host, int device,
+                        void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (int r = check_scales(K, nscales, sizes_host)) return r;
+  if (int r = check_concat(K, nscales, cstrides_host, coffsets_host, "gg_splat_fwd_concat")) return r;
+  if (B == 0) return GG_OK;
+  if (!params || !bufs_host) return fail(GG_E_NULL, "gg_splat_fwd_concat: params / bufs_host is NULL");
+  if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_splat_fwd_concat: params must be 16-byte aligned");
+  bool any = false;
+  for (int i = 0; i < nscales; ++i) {
+    float *m = bufs_host[i];
+    float *k = masks_host ? masks_host[i] : nullptr;
+    any = any || m || k;
+    if ((m && !aligned16(m)) || (k && !aligned16(k)))
+      return fail(GG_E_ALIGN, "gg_splat_fwd_concat: scale %d buffer not 16-byte aligned", i);
+  }
+  if (!any) return fail(GG_E_NULL, "gg_splat_fwd_concat: no output requested");
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
+  cudaError_t e = gg::launch_splat_fwd(params, B, K, nscales, sizes_host, bufs_host, masks_host, GG_LAYOUT_NHWC,
+                                       (cudaStream_t)stream, cstrides_host, coffsets_host);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_splat_fwd_concat");
+}
+
+int gg_splat_bwd_tiles_concat(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,
+                              const int *has_gmasks_host, const int *cstrides_host, const int *coffsets_host) {
+  if (K <= 0) return fail(GG_E_SHAPE, "K must be > 0");
+  if (int r = check_scales(K, nscales, sizes_host)) return r;
+  if (int r = check_concat(K, nscales, cstrides_host, coffsets_host, "gg_splat_bwd_tiles_concat")) return r;
+  return gg::plan_bwd_tiles(K, nscales, sizes_host, has_gmaps_host, has_gmasks_host, GG_LAYOUT_NHWC, cstrides_host,
+                            coffsets_host);
+}
+
+int gg_splat_bwd_concat(const float *params, int B, int K, int nscales, const int *sizes_host,
+                        const float *const *gbufs_host, const int *cstrides_host, const int *coffsets_host,
+                        const float *const *gmasks_host, float *partials, int T, int device, void *stream) {
+  if (int r = check_bk(B, K)) return r;
+  if (int r = check_scales(K, nscales, sizes_host)) return r;
+  if (int r = check_concat(K, nscales, cstrides_host, coffsets_host, "gg_splat_bwd_concat")) return r;
+  if (B == 0) return GG_OK;
+  if (!params || !partials) return fail(GG_E_NULL, "gg_splat_bwd_concat: params/partials is NULL");
+  if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_splat_bwd_concat: params must be 16-byte aligned");
+  int hm[GG_MAX_SCALES], hk[GG_MAX_SCALES];
+  for (int i = 0; i < nscales; ++i) {
+    const float *m = gbufs_host ? gbufs_host[i] : nullptr;
+    const float *k = gmasks_host ? gmasks_host[i] : nullptr;
+    hm[i] = m != nullptr;
+    hk[i] = k != nullptr;
+    if ((m && !aligned16(m)) || (k && !aligned16(k)))
+      return fail(GG_E_ALIGN, "gg_splat_bwd_concat: scale %d gradient buffer not 16-byte aligned", i);
+  }
+  const int need = gg::plan_bwd_tiles(K, nscales, sizes_host, hm, hk, GG_LAYOUT_NHWC, cstrides_host, coffsets_host);
+  if (need != T || T <= 0)
+    return fail(GG_E_WORKSPACE, "gg_splat_bwd_concat: T=%d but this configuration writes %d partial tiles", T, need);
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
+  cudaError_t e = gg::launch_splat_bwd(params, B, K, nscales, sizes_host, gbufs_host, gmasks_host, GG_LAYOUT_NHWC, partials,
+                                       T, (cudaStream_t)stream, cstrides_host, coffsets_host);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_splat_bwd_concat");
+}
+
 int gg_mask_l1_loss_bwd(const float *mask, const void *target, int target_kind, int B, int n, float *gmask,
                         float *loss_partials, int device, void *stream) {
   if (B < 0 || n < 1) return fail(GG_E_SHAPE, "gg_mask_l1_loss_bwd: bad B=%d n=%d", B, n);

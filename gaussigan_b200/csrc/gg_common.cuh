@@ -32,6 +32,8 @@ struct ScaleDesc {
   int contig;      // 1: a strip is 8 CONSECUTIVE pixels (gg_splat_fast.cu); 0: two half-row quads (gg_strip.cuh)
   int cta;         // threads per CTA this geometry was planned for (kThreads except in gg_splat_fast.cu)
   float step;      // float32 (2 / (n-1)), TF 1.12 LinSpace step (mask_gen_dynamic.py:121-122)
+  int cstride;     // NHWC maps: floats from one pixel to the next (K when dense; C_total when the K channels live at
+                   // channel offset c0 of a wider concat buffer -- `maps` then points at channel c0 of pixel 0)
   float *maps;     // forward outputs / backward upstream gradients (const in the backward)
   float *mask;
 };

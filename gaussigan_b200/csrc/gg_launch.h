@@ -15,12 +15,16 @@ cudaError_t launch_conic_fwd(const void *mu2d, const void *sigma2d, int f64, int
 cudaError_t launch_conic_bwd(const void *mu2d, const void *sigma2d, int f64, int B, int K, const float *partials,
                              int T, double *dmu2d, double *dsigma2d, cudaStream_t st);
 
-int plan_bwd_tiles(int K, int nscales, const int *sizes, const int *has_gmaps, const int *has_gmasks, int layout);
+// cstrides / coffsets (NHWC, may be NULL = dense [B,n,n,K]): channels per pixel of the buffer a scale's maps live in and
+// the channel at which they start (concat-direct, mask/mask_gen_dynamic.py:523-529)
+int plan_bwd_tiles(int K, int nscales, const int *sizes, const int *has_gmaps, const int *has_gmasks, int layout,
+                   const int *cstrides = nullptr, const int *coffsets = nullptr);
 cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, const int *sizes, float *const *maps,
-                             float *const *masks, int layout, cudaStream_t st);
+                             float *const *masks, int layout, cudaStream_t st, const int *cstrides = nullptr,
+                             const int *coffsets = nullptr);
 cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes,
                              const float *const *gmaps, const float *const *gmasks, int layout, float *partials,
-                             int T, cudaStream_t st);
+                             int T, cudaStream_t st, const int *cstrides = nullptr, const int *coffsets = nullptr);
 
 cudaError_t launch_mask_l1_loss_bwd(const float *mask, const void *target, int kind, int B, int n, float *gmask,
                                     float *partials, int npartials, cudaStream_t st);

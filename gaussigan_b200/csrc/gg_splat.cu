@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
+#include "gg_launch.h"
 
 namespace gg {
 
@@ -105,10 +106,10 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_strip_kernel(const __grid_
       } else if (OUT == 2) {
         if (rv[r]) {
           int row = pos.row0 + r * s.rpp;
-          float *q = s.maps + ((size_t)b * n + row) * n * K + k;
+          float *q = s.maps + ((size_t)b * n + row) * n * s.cstride + k;
 #pragma unroll
           for (int j = 0; j < kStrip; ++j)
-            if (pos.col(j) < n) q[(size_t)pos.col(j) * K] = g[j];
+            if (pos.col(j) < n) q[(size_t)pos.col(j) * s.cstride] = g[j];
         }
       }
     }
@@ -279,10 +280,10 @@ __global__ void __launch_bounds__(kThreads) splat_bwd_strip_kernel(const __grid_
         for (int j = 0; j < kStrip; ++j) G[j] = Gc[r][j];
       } else {
         int row = pos.row0 + r * s.rpp;
-        const float *q = gmaps + ((size_t)b * n + row) * n * K + k0 + kk;
+        const float *q = gmaps + ((size_t)b * n + row) * n * s.cstride + k0 + kk;
 #pragma unroll
         for (int j = 0; j < kStrip; ++j)
-          G[j] = ((pos.col(j) < n) ? __ldg(q + (size_t)pos.col(j) * K) : 0.f) + gm[r][j];
+          G[j] = ((pos.col(j) < n) ? __ldg(q + (size_t)pos.col(j) * s.cstride) : 0.f) + gm[r][j];
       }
       const float dy = y[r] - p.y;
       const float sh = fmaf(p.w, dy, p.x);
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quad_kernel(const __grid_c
       sh[i] = fmaf(nr[i], dy, mux[i]);
       e[i] = (nE[i] * dy) * dy;
     }
-    float *mrow = s.maps + ((size_t)b * n + row) * n * K;
+    float *mrow = s.maps + ((size_t)b * n + row) * n * s.cstride + 4 * kq;
     for (int q0 = 0; q0 < quads_per_row; q0 += kThreads) {
       const int qq = q0 + threadIdx.x;
       const bool active = qq < quads_per_row;
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quad_kernel(const __grid_c
         const float t = x - sh[i];
         g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
       }
-      if (active) st_f4(mrow + (size_t)qq * 4, g[0], g[1], g[2], g[3]);
+      if (active) st_f4(mrow + (size_t)col * s.cstride, g[0], g[1], g[2], g[3]);
       if (WITH_MASK) {
         float sum = (g[0] + g[1]) + (g[2] + g[3]);
         for (int off = 1; off < KQ; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quadg_kernel(const __grid_
       sh[i] = fmaf(nr[i], dy, mux[i]);
       e[i] = (nE[i] * dy) * dy;
     }
-    float *mrow = s.maps + ((size_t)b * n + row) * n * K + 4 * kq;
+    float *mrow = s.maps + ((size_t)b * n + row) * n * s.cstride + 4 * kq;
     for (int col = c0; col < n; col += cpp) {
       const float x = grid_coord(col, s.step);
       float g[4];
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quadg_kernel(const __grid_
         const float t = x - sh[i];
         g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
       }
-      st_f4(mrow + (size_t)col * K, g[0], g[1], g[2], g[3]);
+      st_f4(mrow + (size_t)col * s.cstride, g[0], g[1], g[2], g[3]);
     }
   }
 }
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_pair_kernel(const __grid_c
       sh[i] = fmaf(nr[i], dy, mux[i]);
       e[i] = (nE[i] * dy) * dy;
     }
-    float *mrow = s.maps + ((size_t)b * n + row) * n * K + 2 * kp;
+    float *mrow = s.maps + ((size_t)b * n + row) * n * s.cstride + 2 * kp;
     for (int col = c0; col < n; col += cpp) {
       const float x = grid_coord(col, s.step);
       float g[2];
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_pair_kernel(const __grid_c
         const float t = x - sh[i];
         g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
       }
-      *reinterpret_cast<float2 *>(mrow + (size_t)col * K) = make_float2(g[0], g[1]);
+      *reinterpret_cast<float2 *>(mrow + (size_t)col * s.cstride) = make_float2(g[0], g[1]);
     }
   }
 }
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_kernel(const __gri
       e[i] = (nE[i] * dy[i]) * dy[i];
       S0[i] = S1[i] = S2[i] = 0.f;
     }
-    const float *grow = s.maps + ((size_t)b * n + row) * n * K;
+    const float *grow = s.maps + ((size_t)b * n + row) * n * s.cstride + 4 * kq;
     const bool use_gmask = WITH_GMASK && s.mask != nullptr;
     const float *mrow = use_gmask ? s.mask + ((size_t)b * n + row) * n : nullptr;
     // batches of kUQ quads per thread: all 128-bit loads of a batch are issued before any use (MLP)
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_quad_kernel(const __gri
         G[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         gmv[u] = 0.f;
         if (qq < quads_per_row) {
-          G[u] = __ldg(reinterpret_cast<const float4 *>(grow + (size_t)qq * 4));
+          G[u] = __ldg(reinterpret_cast<const float4 *>(grow + (size_t)(qq >> kq_shift) * s.cstride));
           if (use_gmask) gmv[u] = __ldg(mrow + (qq >> kq_shift));
         }
       }
@@ -835,26 +836,45 @@ struct Plan {
   bool maps_fast_bwd;      // backward of the maps through splat_bwd_nhwc_fast_kernel
   int kq_shift;
   bool maps_any_mask;
+  bool strided;            // a maps scale sits inside a wider NHWC buffer (channel stride != K or channel offset != 0)
   int tiles_mask, tiles_maps;
 };
 
+// cstrides / coffsets (NHWC only, may be NULL = dense): scale i's K channels live at channel coffsets[i] of a buffer
+// with cstrides[i] channels per pixel (the generator's concat buffer, mask/mask_gen_dynamic.py:523-529).  Vector
+// accesses need the channel offset and stride to keep their alignment; otherwise the scalar strip kernels take over.
 static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool *has_maps, const bool *has_mask,
-                      int layout, bool backward) {
+                      int layout, bool backward, const int *cstrides = nullptr, const int *coffsets = nullptr) {
   pl = Plan();
   pl.kq_shift = 0;
   int map_sizes[GG_MAX_SCALES], nmaps = 0;
+  bool strided = false, vec4 = true, vec2 = true;
   for (int i = 0; i < nscales; ++i)
-    if (has_maps[i]) map_sizes[nmaps++] = sizes[i];
+    if (has_maps[i]) {
+      map_sizes[nmaps++] = sizes[i];
+      const int cs = cstrides ? cstrides[i] : K, c0 = coffsets ? coffsets[i] : 0;
+      strided = strided || cs != K || c0 != 0;
+      vec4 = vec4 && (cs & 3) == 0 && (c0 & 3) == 0;
+      vec2 = vec2 && (cs & 1) == 0 && (c0 & 1) == 0;
+    }
+  pl.strided = strided;
   pl.maps_kind = MAPS_STRIP;
-  if (layout == GG_LAYOUT_NHWC && nmaps > 0) {
+  if (layout == GG_LAYOUT_NHWC && nmaps > 0 && !strided) {
     pl.maps_fast_bwd = backward && fast_maps_bwd() && splat_bwd_nhwc_fast_ok(K, nmaps, map_sizes);
     if (quad_ok(K, &pl.kq_shift)) pl.maps_kind = MAPS_QUAD;
     else if (backward ? pl.maps_fast_bwd : flat_fwd_ok(K, nscales, sizes, has_maps)) pl.maps_kind = MAPS_FLAT;
+  } else if (layout == GG_LAYOUT_NHWC && nmaps > 0) {
+    // concat-direct: quads with 128-bit accesses (forward: any K % 4 == 0; backward: K = 4 * 2^m, register-staged or
+    // 2-D bulk-tensor copies), pairs with 64-bit stores (forward, even K), scalar strips otherwise
+    if (quad_ok(K, &pl.kq_shift) && vec4) pl.maps_kind = MAPS_QUAD;
+    else if (!backward && (K & 3) == 0 && vec4 && (K >> 2) <= kThreads) pl.maps_kind = MAPS_FLAT;
+    else if (!backward && (K & 1) == 0 && vec2 && (K >> 1) <= kThreads) pl.maps_kind = MAPS_FLAT;
   }
   int rpt = backward ? bwd_rpt() : fwd_rpt();
   int tb_mask = 0, tb_maps = 0;
   auto add_mask_scale = [&](int n) {
     ScaleDesc &d = pl.strip_mask.sc[pl.strip_mask.nscales++];
+    d.cstride = K;
     if (fast_mask()) strip_geometry(d, n, rpt >= 4 ? 4 : 2, true, fast_cta(backward, rpt));   // row pairs
     else strip_geometry(d, n, rpt);
     d.tile_begin = tb_mask;
@@ -863,6 +883,7 @@ static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool
   for (int i = 0; i < nscales; ++i) {
     if (has_maps[i]) {
       ScaleDesc &d = pl.maps.sc[pl.maps.nscales++];
+      d.cstride = cstrides ? cstrides[i] : K;
       if (pl.maps_fast_bwd) fast_bwd_geometry(d, sizes[i], K);
       else if (pl.maps_kind != MAPS_STRIP) quad_geometry(d, sizes[i], (K + 3) >> 2, quad_passes(backward));
       else strip_geometry(d, sizes[i], rpt);
@@ -881,11 +902,12 @@ static bool make_plan(Plan &pl, int K, int nscales, const int *sizes, const bool
   return true;
 }
 
-int plan_bwd_tiles(int K, int nscales, const int *sizes, const int *has_gmaps, const int *has_gmasks, int layout) {
+int plan_bwd_tiles(int K, int nscales, const int *sizes, const int *has_gmaps, const int *has_gmasks, int layout,
+                   const int *cstrides, const int *coffsets) {
   Plan pl;
   bool hm[GG_MAX_SCALES] = {}, hk[GG_MAX_SCALES] = {};
   for (int i = 0; i < nscales; ++i) { hm[i] = has_gmaps && has_gmaps[i]; hk[i] = has_gmasks && has_gmasks[i]; }
-  make_plan(pl, K, nscales, sizes, hm, hk, layout, true);
+  make_plan(pl, K, nscales, sizes, hm, hk, layout, true, cstrides, coffsets);
   return pl.tiles_mask + pl.tiles_maps;
 }
 
@@ -914,15 +936,20 @@ static cudaError_t launch_bwd_strip(const SplatArgs &a, int gin_mode, int B, cud
 }
 
 cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, const int *sizes, float *const *maps,
-                             float *const *masks, int layout, cudaStream_t st) {
+                             float *const *masks, int layout, cudaStream_t st, const int *cstrides,
+                             const int *coffsets) {
   bool hm[GG_MAX_SCALES] = {}, hk[GG_MAX_SCALES] = {};
   for (int i = 0; i < nscales; ++i) { hm[i] = maps && maps[i]; hk[i] = masks && masks[i]; }
   Plan pl;
-  make_plan(pl, K, nscales, sizes, hm, hk, layout, false);
+  make_plan(pl, K, nscales, sizes, hm, hk, layout, false, cstrides, coffsets);
   int im = 0, ik = 0;
   for (int i = 0; i < nscales; ++i) {
     const bool own_mask_kernel = hm[i] && hk[i] && pl.maps_kind == MAPS_FLAT;
-    if (hm[i]) { pl.maps.sc[im].maps = maps[i]; pl.maps.sc[im].mask = hk[i] && !own_mask_kernel ? masks[i] : nullptr; ++im; }
+    if (hm[i]) {
+      pl.maps.sc[im].maps = maps[i] + (coffsets ? coffsets[i] : 0);
+      pl.maps.sc[im].mask = hk[i] && !own_mask_kernel ? masks[i] : nullptr;
+      ++im;
+    }
     if (hk[i] && (!hm[i] || own_mask_kernel)) { pl.strip_mask.sc[ik].maps = nullptr; pl.strip_mask.sc[ik].mask = masks[i]; ++ik; }
   }
   cudaError_t err = cudaSuccess;
@@ -966,16 +993,16 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
 
 cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, const int *sizes,
                              const float *const *gmaps, const float *const *gmasks, int layout, float *partials,
-                             int T, cudaStream_t st) {
+                             int T, cudaStream_t st, const int *cstrides, const int *coffsets) {
   bool hm[GG_MAX_SCALES] = {}, hk[GG_MAX_SCALES] = {};
   for (int i = 0; i < nscales; ++i) { hm[i] = gmaps && gmaps[i]; hk[i] = gmasks && gmasks[i]; }
   Plan pl;
-  make_plan(pl, K, nscales, sizes, hm, hk, layout, true);
+  make_plan(pl, K, nscales, sizes, hm, hk, layout, true, cstrides, coffsets);
   if (pl.tiles_mask + pl.tiles_maps != T) return cudaErrorInvalidValue;
   int im = 0, ik = 0;
   for (int i = 0; i < nscales; ++i) {
     if (hm[i]) {
-      pl.maps.sc[im].maps = const_cast<float *>(gmaps[i]);
+      pl.maps.sc[im].maps = const_cast<float *>(gmaps[i]) + (coffsets ? coffsets[i] : 0);
       pl.maps.sc[im].mask = hk[i] ? const_cast<float *>(gmasks[i]) : nullptr;
       ++im;
     } else if (hk[i]) {
@@ -1008,7 +1035,7 @@ cudaError_t launch_splat_bwd(const float *params, int B, int K, int nscales, con
       // the quad kernels add gmask to every channel only when a scale carries one; scales without a
       // gmask are handled by giving the kernel a per-scale NULL check
       static const bool use_tma = env_int("GG_TMA_BWD", 1) != 0;
-      if (use_tma && splat_bwd_quad_tma_ok(a, pl.kq_shift)) {
+      if (use_tma && !pl.strided && splat_bwd_quad_tma_ok(a, pl.kq_shift)) {
         err = launch_splat_bwd_quad_tma(a, B, pl.kq_shift, pl.maps_any_mask, st);
       } else {
         if (pl.maps_any_mask) launch_pdl(splat_bwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);

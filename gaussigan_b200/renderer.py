@@ -206,6 +206,77 @@ class _Raster(torch.autograd.Function):
         return dmu.to(mu.dtype), dsig.to(sigma.dtype), None
 
 
+class _RenderInto(torch.autograd.Function):
+    """(mus, sigma, rot*, spec, *bufs) -> bufs, with the K maps of scale i written IN PLACE into channels
+    [c0_i, c0_i + K) of the NHWC buffer bufs[i] (``gg_splat_fwd_concat``); the backward reads the same channel slice of
+    the buffers' gradients in place (``gg_splat_bwd_concat``) and hands the gradients on unchanged for the channels
+    this op did not write."""
+
+    @staticmethod
+    def forward(ctx, mus, sigma, rotx, roty, rotz, spec, offsets, *bufs):
+        dev = mus.device
+        B, K = mus.shape[0], mus.shape[1]
+        params = torch.empty((B, K, GG_PARAM_STRIDE), dtype=torch.float32, device=dev)
+        check(lib.gg_project_fwd(mus.data_ptr(), sigma.data_ptr(), int(sigma.dtype == torch.float64),
+                                 rotx.data_ptr(), roty.data_ptr(), rotz.data_ptr(),
+                                 spec.tx, spec.ty, spec.tz, spec.focal, B, K,
+                                 None, None, params.data_ptr(), dev.index, _stream(dev)), "gg_project_fwd")
+        strides = int_array([b.shape[-1] for b in bufs])
+        offs = int_array(offsets)
+        check(lib.gg_splat_fwd_concat(params.data_ptr(), B, K, len(bufs), int_array(spec.sizes),
+                                      ptr_array([b.data_ptr() for b in bufs]), strides, offs, None, dev.index,
+                                      _stream(dev)), "gg_splat_fwd_concat")
+        ctx.mark_dirty(*bufs)
+        ctx.save_for_backward(mus, sigma, rotx, roty, rotz, params)
+        ctx.spec, ctx.offsets, ctx.cstrides = spec, tuple(offsets), tuple(b.shape[-1] for b in bufs)
+        ctx.set_materialize_grads(False)
+        return bufs
+
+    @staticmethod
+    def backward(ctx, *gbufs):
+        mus, sigma, rotx, roty, rotz, params = ctx.saved_tensors
+        spec: _Spec = ctx.spec
+        dev = mus.device
+        B, K = mus.shape[0], mus.shape[1]
+        gb = [None if g is None else _clean_grad(g) for g in gbufs]
+        hm = [g is not None for g in gb]
+        none = (None,) * 7
+        if not any(hm):
+            return none + tuple(gbufs)
+        sizes, strides, offs = int_array(spec.sizes), int_array(ctx.cstrides), int_array(ctx.offsets)
+        # In place (128-bit loads of the channel slice) when the slice is a run of aligned quads of Gaussians, K = 4 * 2^m:
+        # 2.5x faster than slicing first (measured, tools/time_concat.py).  Other K: the scalar strided kernel loses to
+        # "copy the slice, then the bulk-copy backward", so that is what runs.
+        kq = K >> 2
+        in_place = K % 4 == 0 and kq & (kq - 1) == 0 and kq <= 32 and all(
+            c % 4 == 0 and o % 4 == 0 for c, o in zip(ctx.cstrides, ctx.offsets))
+        if in_place:
+            T = check(lib.gg_splat_bwd_tiles_concat(K, len(gb), sizes, int_array(hm), int_array([0] * len(gb)), strides,
+                                                    offs), "gg_splat_bwd_tiles_concat")
+            partials = torch.empty((B, T, K, GG_MOMENTS), dtype=torch.float32, device=dev)
+            check(lib.gg_splat_bwd_concat(params.data_ptr(), B, K, len(gb), sizes, ptr_array([_ptr(g) for g in gb]),
+                                          strides, offs, None, partials.data_ptr(), T, dev.index, _stream(dev)),
+                  "gg_splat_bwd_concat")
+        else:
+            dense = [None if g is None else g[..., o:o + K].contiguous() for g, o in zip(gb, ctx.offsets)]
+            partials, T = _splat_backward(params, B, K, spec, dense, [None] * len(dense))
+        need = ctx.needs_input_grad
+        dmus = torch.empty((B, K, 3), dtype=torch.float32, device=dev) if need[0] else None
+        dsigma = torch.empty((B, K, 3, 3), dtype=torch.float64, device=dev) if need[1] else None
+        drot = torch.empty((B, 3), dtype=torch.float32, device=dev) if any(need[2:5]) else None
+        check(lib.gg_project_bwd(mus.data_ptr(), sigma.data_ptr(), int(sigma.dtype == torch.float64),
+                                 rotx.data_ptr(), roty.data_ptr(), rotz.data_ptr(),
+                                 spec.tx, spec.ty, spec.tz, spec.focal, B, K, partials.data_ptr(), T, None, None,
+                                 _ptr(dmus), _ptr(dsigma), _ptr(drot), dev.index, _stream(dev)), "gg_project_bwd")
+        if dsigma is not None and sigma.dtype != torch.float64:
+            dsigma = dsigma.to(sigma.dtype)
+        return (dmus, dsigma,
+                drot[:, 0].contiguous() if need[2] else None,
+                drot[:, 1].contiguous() if need[3] else None,
+                drot[:, 2].contiguous() if need[4] else None,
+                None, None) + tuple(gbufs)        # the other channels' gradients pass through untouched
+
+
 # ----------------------------------------------------------------------------------- public API
 def _prep_inputs(mus, sigma, rotx, roty, rotz, K):
     assert mus is not None                       # mask/mask_gen_dynamic.py:234
@@ -249,6 +320,34 @@ def get_landmarks(mus, sigma, rotx, roty, rotz, tx, ty, tz, focal=1., *, K: Opti
                      (False,) * len(chunk), _layout_code(layout), False)
         out += list(_Render.apply(mus3, sig, rots[0], rots[1], rots[2], spec))
     return out
+
+
+def get_landmarks_into(bufs: Sequence[torch.Tensor], offsets: Sequence[int], mus, sigma, rotx, roty, rotz, tx, ty, tz,
+                       focal=1., *, K: Optional[int] = None) -> List[torch.Tensor]:
+    """``get_landmarks`` writing straight into the generator's concat buffers (concat-direct).
+
+    The reference does ``x = tf.concat([x, pe[i]], -1)`` at every scale (mask/mask_gen_dynamic.py:523-529,
+    rgb/rgb_gen_dynamic.py:604-610): a dense ``[B,n,n,K]`` tensor is written, read again and written a second time.
+    Here ``bufs[i]`` is the pre-allocated NHWC concat buffer ``[B,n_i,n_i,C_i]`` (float32, contiguous; the caller has
+    already put -- or will put -- ``x`` into its other channels) and the K maps of scale i land in channels
+    ``[offsets[i], offsets[i] + K)`` in one pass.  The backward reads the same channel slice of the buffer's gradient
+    in place.  Returns the buffers (autograd-connected: use the returned tensors downstream).  Scales are taken from
+    the buffers' shapes; at most 4 per call."""
+    dev, B, Kk, mus3, sig, rots = _prep_inputs(mus, sigma, rotx, roty, rotz, K)
+    bufs = list(bufs)
+    if not (1 <= len(bufs) <= _lib.GG_MAX_SCALES) or len(offsets) != len(bufs):
+        raise ValueError("1..%d buffers with one channel offset each" % _lib.GG_MAX_SCALES)
+    sizes = []
+    for b, c0 in zip(bufs, offsets):
+        _require_cuda(b)
+        if b.dtype != torch.float32 or b.dim() != 4 or b.shape[0] != B or b.shape[1] != b.shape[2] or not b.is_contiguous():
+            raise ValueError("each buffer must be a contiguous float32 NHWC tensor [B,n,n,C]")
+        if c0 < 0 or c0 + Kk > b.shape[-1]:
+            raise ValueError(f"channels [{c0}, {c0 + Kk}) do not fit a buffer with {b.shape[-1]} channels")
+        sizes.append(int(b.shape[1]))
+    spec = _Spec(float(tx), float(ty), float(tz), float(focal), tuple(sizes), (True,) * len(sizes),
+                 (False,) * len(sizes), LAYOUT_NHWC, False)
+    return list(_RenderInto.apply(mus3, sig, rots[0], rots[1], rots[2], spec, tuple(int(c) for c in offsets), *bufs))
 
 
 def get_landmarks_with_mask(mus, sigma, rotx, roty, rotz, tx, ty, tz, focal=1., *, K: Optional[int] = None,

@@ -132,6 +132,23 @@ GG_API int gg_splat_bwd(const float *params, int B, int K, int nscales, const in
                  const float *const *gmaps_host, const float *const *gmasks_host, int layout,
                  float *partials, int T, int device, void *stream);
 
+/* ---- concat-direct: the maps written into / their gradients read out of a wider NHWC buffer -------------
+ * The reference concatenates every scale's maps onto the generator's activations, tf.concat([x, pe[i]], -1)
+ * (mask/mask_gen_dynamic.py:523-529, rgb/rgb_gen_dynamic.py:604-610).  These entry points take the concat buffer
+ * itself: bufs_host[i] is the BASE of a [B,n,n,cstrides_host[i]] float32 NHWC tensor and the K maps of scale i occupy
+ * its channels [coffsets_host[i], coffsets_host[i] + K) -- no dense [B,n,n,K] tensor and no second pass over it, in
+ * either direction (the backward reads the K-channel slice of the concat gradient in place).  128-bit accesses are
+ * kept when K, cstride and coffset are multiples of 4 (64-bit for multiples of 2); other shapes take scalar accesses.
+ * Other channels of the buffer are never touched.  T comes from gg_splat_bwd_tiles_concat with the same arguments. */
+GG_API int gg_splat_fwd_concat(const float *params, int B, int K, int nscales, const int *sizes_host,
+                               float *const *bufs_host, const int *cstrides_host, const int *coffsets_host,
+                               float *const *masks_host, int device, void *stream);
+GG_API int gg_splat_bwd_tiles_concat(int K, int nscales, const int *sizes_host, const int *has_gmaps_host,
+                                     const int *has_gmasks_host, const int *cstrides_host, const int *coffsets_host);
+GG_API int gg_splat_bwd_concat(const float *params, int B, int K, int nscales, const int *sizes_host,
+                               const float *const *gbufs_host, const int *cstrides_host, const int *coffsets_host,
+                               const float *const *gmasks_host, float *partials, int T, int device, void *stream);
+
 /* Arithmetic of the MASK-ONLY launches (gg_splat_fwd / gg_splat_bwd on scales that carry only a mask, and
  * gg_silhouette_loss_fused).  1 (default): Gaussians forward-differenced along each 8-pixel strip -- two
  * exponentials per strip instead of eight, FP32-pipe bound, silhouette error ~6e-7 of its maximum.  0: one

@@ -195,3 +195,54 @@ def test_device_guard_restores_the_current_device(gg, cuda_device):
     assert m.device == d1 and torch.cuda.current_device() == 0
     ref = rp.get_landmarks(inp["mus"], inp["sigma"], inp["rotx"], inp["roty"], inp["rotz"], 0, 0, -2., sizes=(32,))[0].sum(-1)
     assert_close_norm(m, ref, FWD_RTOL, "render on cuda:1 while cuda:0 is current")
+
+
+# ------------------------------------------------------------------------------- concat-direct
+@pytest.mark.parametrize("K,cx,sizes", [
+    (16, 64, (32, 64, 128, 256)),      # quads, 128-bit accesses, the reference pyramid
+    (16, 8, (64,)), (4, 4, (40,)),     # quads, small buffers
+    (12, 32, (32, 64)),                # K % 4 == 0 but not 4 * 2^m: quadg forward, strip backward
+    (6, 64, (64, 128)),                # the reference's K = 6: pair stores (64-bit), strip backward
+    (6, 3, (48,)),                     # odd channel offset: scalar accesses
+    (5, 7, (24,)),                     # odd everything
+    (16, 6, (32,)),                    # quads of Gaussians but a channel offset that breaks 16-byte alignment
+])
+def test_concat_direct_forward_and_backward_vs_oracle(gg, cuda_device, K, cx, sizes):
+    """get_landmarks_into: the K maps land in channels [cx, cx + K) of a pre-allocated NHWC concat buffer
+    (mask/mask_gen_dynamic.py:523-529 `tf.concat([x, pe[i]], -1)`), and the backward reads that channel slice of the
+    buffer's gradient in place.  Against torch.cat([x, oracle_maps], -1) and the oracle's autograd; the channels that
+    belong to x are never touched; gradients reach x, mus, sigma and roty."""
+    B = 2
+    inp = rp.synth_inputs(B, K, seed=500 + K + cx, angle=30.0)
+    g = torch.Generator().manual_seed(K * 100 + cx)
+    xs = [torch.randn(B, n, n, cx, generator=g) for n in sizes]
+    ws = [torch.randn(B, n, n, cx + K + 3, generator=g) for n in sizes]          # + 3 trailing channels nobody writes
+    # ---- oracle
+    lv = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    maps = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0, 0, -2., sizes=sizes)
+    tail = [torch.full((B, n, n, 3), 7.0) for n in sizes]
+    cat_ref = [torch.cat([x, m, t], -1) for x, m, t in zip(xr, maps, tail)]
+    sum((c * w).sum() for c, w in zip(cat_ref, ws)).backward()
+    # ---- concat-direct
+    dv = {k: v.clone().to(cuda_device).requires_grad_(True) for k, v in inp.items()}
+    xd = [x.clone().to(cuda_device).requires_grad_(True) for x in xs]
+    bufs = []
+    for x, n in zip(xd, sizes):
+        b = torch.full((B, n, n, cx + K + 3), 7.0, device=cuda_device)
+        b[..., :cx] = x
+        bufs.append(b)
+    outs = gg.get_landmarks_into(bufs, [cx] * len(sizes), dv["mus"], dv["sigma"], dv["rotx"], dv["roty"], dv["rotz"], 0, 0, -2.)
+    for o, c in zip(outs, cat_ref):
+        assert torch.equal(o[..., :cx].cpu(), c[..., :cx].detach()) and torch.equal(o[..., cx + K:].cpu(), c[..., cx + K:])
+        assert_close_norm(o[..., cx:cx + K], c[..., cx:cx + K], FWD_RTOL, f"concat maps K={K} n={c.shape[1]}")
+    sum((o * w.to(cuda_device)).sum() for o, w in zip(outs, ws)).backward()
+    for a, b_ in zip(xd, xr):
+        assert torch.equal(a.grad.cpu(), b_.grad)                       # pass-through channels: exact
+    for k in ("mus", "sigma", "roty"):
+        assert_close_norm(dv[k].grad, lv[k].grad, GRAD_RTOL, f"concat-direct grad {k} (K={K}, cx={cx})")
+    # identical values to the dense path where that is the same kernel family
+    dense = gg.get_landmarks(dv["mus"].detach(), dv["sigma"].detach(), dv["rotx"], dv["roty"].detach(), dv["rotz"], 0, 0, -2.,
+                             sizes=sizes)
+    for o, d_ in zip(outs, dense):
+        assert_close_norm(o[..., cx:cx + K], d_, 1e-6, "concat-direct vs dense")

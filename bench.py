@@ -828,6 +828,99 @@ def bench_configs(world, rank, dev, peaks, capture, timed_passes, max_over_ranks
                 "speedup_vs_dense_round_trip": (res["fwd_dense_plus_copy_us"] + res["bwd_slice_copy_plus_dense_us"]) / step_us}
 
     guarded("concat_direct", concat_direct)
+
+    def reference_step(K):
+        """The reference's own per-step render pattern at the authors' batch size (mask/train_giraffe.sh: batch 3, K = 6;
+        train_manuel.sh: K = 12): three cameras on the same Gaussians -- pose, pose + random yaw, canonical
+        (mask/mask_gen_dynamic.py:707-709) -- at the four pyramid scales, backward through the two that train, plus the
+        cycle render of another Gaussian set (:719) forward + backward; upstream gradients are random maps.  As ONE
+        multi-view launch sequence in a CUDA graph, and as the four separate get_landmarks-style launch sequences."""
+        B, V, sizes = 3, 3, (32, 64, 128, 256)
+        g = torch.Generator().manual_seed(7 + K)
+        base = synth.synth_inputs(2 * B, K, seed=21 + K, device=dev)
+        mus = base["mus"].reshape(2 * B, K, 3).contiguous().to(dev)
+        sig = base["sigma"].contiguous().to(dev)
+        yaw = (180.0 * torch.tanh(torch.randn(V + 1, B, generator=g))).float()
+        yaw[2] = 0.0                                                       # canonical view
+        rot_y = yaw.to(dev).contiguous()
+        rot_0 = torch.zeros_like(rot_y)
+        sz = int_array(sizes)
+        nul4 = ptr_array([None] * 4)
+
+        def bufs(nimg):
+            maps = [torch.empty(nimg, s, s, K, device=dev) for s in sizes]
+            gmaps = [torch.randn(nimg, s, s, K, device=dev) for s in sizes]
+            return maps, gmaps, ptr_array([m.data_ptr() for m in maps]), ptr_array([m.data_ptr() for m in gmaps])
+
+        T = check(lib.gg_splat_bwd_tiles(K, 4, sz, int_array([1] * 4), int_array([0] * 4), LAYOUT_NHWC), "tiles")
+        # ---- multi-view: images = 3 views x B (views 0, 1 train: they come first, so their gradients are one slice)
+        mv_maps, mv_g, mv_mp, mv_gp = bufs(V * B)
+        mv_params = torch.empty(V * B, K, GG_PARAM_STRIDE, device=dev)
+        mv_part = torch.zeros(V * B, T, K, GG_MOMENTS, device=dev)          # the canonical view's slots stay zero
+        cy_maps, cy_g, cy_mp, cy_gp = bufs(B)
+        cy_params = torch.empty(B, K, GG_PARAM_STRIDE, device=dev)
+        cy_part = torch.empty(B, T, K, GG_MOMENTS, device=dev)
+        dmus, dsig = torch.empty(B, K, 3, device=dev), torch.empty(B, K, 3, 3, dtype=torch.float64, device=dev)
+        drot = torch.empty(V * B, 3, device=dev)
+        dmus_c, dsig_c, drot_c = torch.empty_like(dmus), torch.empty_like(dsig), torch.empty(B, 3, device=dev)
+        p = lambda t: t.data_ptr()
+
+        def cycle_render(i):
+            check(lib.gg_project_fwd(p(mus[B:]), p(sig[B:]), 1, p(rot_0[3]), p(rot_y[3]), p(rot_0[3]), 0., 0., -2., 1., B, K,
+                                     None, None, p(cy_params), dev.index, st()), "gg_project_fwd")
+            check(lib.gg_splat_fwd(p(cy_params), B, K, 4, sz, cy_mp, nul4, LAYOUT_NHWC, dev.index, st()), "gg_splat_fwd")
+            check(lib.gg_splat_bwd(p(cy_params), B, K, 4, sz, cy_gp, nul4, LAYOUT_NHWC, p(cy_part), T, dev.index, st()), "gg_splat_bwd")
+            check(lib.gg_project_bwd(p(mus[B:]), p(sig[B:]), 1, p(rot_0[3]), p(rot_y[3]), p(rot_0[3]), 0., 0., -2., 1., B, K,
+                                     p(cy_part), T, None, None, p(dmus_c), p(dsig_c), p(drot_c), dev.index, st()), "gg_project_bwd")
+
+        def multi_view(i):
+            check(lib.gg_project_fwd_views(p(mus), p(sig), 1, p(rot_0), p(rot_y), p(rot_0), 0., 0., -2., 1., B, V, K, None, None,
+                                           p(mv_params), dev.index, st()), "gg_project_fwd_views")
+            check(lib.gg_splat_fwd(p(mv_params), V * B, K, 4, sz, mv_mp, nul4, LAYOUT_NHWC, dev.index, st()), "gg_splat_fwd")
+            # backward through the two training views = the first 2 B images
+            check(lib.gg_splat_bwd(p(mv_params), 2 * B, K, 4, sz, mv_gp, nul4, LAYOUT_NHWC, p(mv_part), T, dev.index, st()),
+                  "gg_splat_bwd")
+            check(lib.gg_project_bwd_views(p(mus), p(sig), 1, p(rot_0), p(rot_y), p(rot_0), 0., 0., -2., 1., B, V, K, p(mv_part),
+                                           T, None, None, p(dmus), p(dsig), p(drot), dev.index, st()), "gg_project_bwd_views")
+            cycle_render(i)
+
+        # ---- the same as separate single-view launch sequences (what four get_landmarks calls cost)
+        sv = [bufs(B) for _ in range(V)]
+        sv_params = [torch.empty(B, K, GG_PARAM_STRIDE, device=dev) for _ in range(V)]
+        sv_part = [torch.empty(B, T, K, GG_MOMENTS, device=dev) for _ in range(V)]
+        sv_grads = [(torch.empty_like(dmus), torch.empty_like(dsig), torch.empty(B, 3, device=dev)) for _ in range(V)]
+
+        def separate(i):
+            for v in range(V):
+                maps_, g_, mp_, gp_ = sv[v]
+                check(lib.gg_project_fwd(p(mus), p(sig), 1, p(rot_0[v]), p(rot_y[v]), p(rot_0[v]), 0., 0., -2., 1., B, K, None,
+                                         None, p(sv_params[v]), dev.index, st()), "gg_project_fwd")
+                check(lib.gg_splat_fwd(p(sv_params[v]), B, K, 4, sz, mp_, nul4, LAYOUT_NHWC, dev.index, st()), "gg_splat_fwd")
+            for v in range(2):
+                maps_, g_, mp_, gp_ = sv[v]
+                check(lib.gg_splat_bwd(p(sv_params[v]), B, K, 4, sz, gp_, nul4, LAYOUT_NHWC, p(sv_part[v]), T, dev.index, st()),
+                      "gg_splat_bwd")
+                check(lib.gg_project_bwd(p(mus), p(sig), 1, p(rot_0[v]), p(rot_y[v]), p(rot_0[v]), 0., 0., -2., 1., B, K,
+                                         p(sv_part[v]), T, None, None, p(sv_grads[v][0]), p(sv_grads[v][1]), p(sv_grads[v][2]),
+                                         dev.index, st()), "gg_project_bwd")
+            cycle_render(i)
+
+        res = {}
+        for name, fn, nl in (("multi_view_us", multi_view, 8), ("separate_calls_us", separate, 14)):
+            gph = capture(lambda fn=fn: [fn(i) for i in range(8)])
+            res[name] = timed_passes(gph.replay, 8, warm_steps=8)["ms_per_step"] * 1e3
+            res[name.replace("_us", "_launches")] = nl
+        byts = (V + 1) * B * sum(s * s for s in sizes) * K * 4 + 3 * B * sum(s * s for s in sizes) * K * 4   # written + read
+        return {"workload": f"the reference's render pattern per training step at its own batch 3, K={K}: 3 cameras on one "
+                            "Gaussian set + the cycle render, 4 pyramid scales (NHWC maps), backward through 3 of the 4 renders",
+                "value": world * B / (res["multi_view_us"] * 1e-6), "unit": "training-step batches of 3 silhouettes/s x 3",
+                **res, "speedup": res["separate_calls_us"] / res["multi_view_us"],
+                "roofline": {"bound": "launch latency", "achieved": byts / (res["multi_view_us"] * 1e-6) / 1e9,
+                             "peak": peaks["hbm_gbs"], "unit": "GB/s of map bytes", "frac": byts / (res["multi_view_us"] * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                             "note": f"{byts / 1e6:.1f} MB per step: the step is launch-latency bound at this batch size"}}
+
+    guarded("reference_step_k6", lambda: reference_step(6))
+    guarded("reference_step_k12", lambda: reference_step(12))
     return out
 
 

@@ -7,7 +7,7 @@ interface.  Importing it loads ``lib/libgaussigan_sm100.so`` and fails loudly if
 """
 from ._lib import GaussiganError, lib as _capi, set_fast_mask, set_pdl  # noqa: F401  (import = load the shared library)
 from .renderer import (REFERENCE_SIZES, get_gaussian_maps_2d, get_landmarks, get_landmarks_infer,
-                       get_landmarks_into, get_landmarks_with_mask, get_silhouette_2d, project, render_silhouette)
+                       get_landmarks_into, get_landmarks_views, get_landmarks_with_mask, get_silhouette_2d, project, render_silhouette)
 
 from .consumers import (colorize_gaussians, colorize_landmark_maps, gm_cycle_loss, mask_recon_loss_bis,  # noqa: E402
                         turntable)
@@ -17,5 +17,5 @@ from .interchange import decoder_feed, load_reference_gaussians, save_reference_
 __all__ = ["set_fast_mask", "set_pdl", "svd3", "deform", "sigma_from_frame", "colorize_gaussians", "colorize_landmark_maps", "gm_cycle_loss", "mask_recon_loss_bis", "turntable",
            "decoder_feed", "load_reference_gaussians", "save_reference_gaussians",
            "REFERENCE_SIZES", "GaussiganError", "get_gaussian_maps_2d", "get_landmarks", "get_landmarks_infer",
-           "get_landmarks_into", "get_landmarks_with_mask", "get_silhouette_2d", "project", "render_silhouette"]
+           "get_landmarks_into", "get_landmarks_views", "get_landmarks_with_mask", "get_silhouette_2d", "project", "render_silhouette"]
 __version__ = "0.2.0"

@@ -46,6 +46,9 @@ SIGNATURES = {
     "gg_project_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "gg_project_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _vp, _i, _vp, _vp,
                             _vp, _vp, _vp, _i, _vp]),
+    "gg_project_fwd_views": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "gg_project_bwd_views": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _i, _vp, _i, _vp, _vp,
+                                  _vp, _vp, _vp, _i, _vp]),
     "gg_conic_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "gg_conic_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "gg_splat_fwd": (_i, [_vp, _i, _i, _i, _ip, _pp, _pp, _i, _i, _vp]),

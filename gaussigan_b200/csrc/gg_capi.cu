@@ -123,6 +123,37 @@ int gg_project_bwd(const float *mus, const void *sigma, int sigma_is_f64, const 
   return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_project_bwd");
 }
 
+int gg_project_fwd_views(const float *mus, const void *sigma, int sigma_is_f64, const float *rotx, const float *roty,
+                         const float *rotz, double tx, double ty, double tz, double focal, int Bg, int V, int K,
+                         double *mu2d, double *sigma2d, float *params, int device, void *stream) {
+  if (V < 1 || V > 64) return fail(GG_E_SHAPE, "V must be in 1..64 (got %d)", V);
+  if (int r = check_bk(Bg * V, K)) return r;
+  if (Bg == 0) return GG_OK;
+  if (!mus || !sigma || !rotx || !roty || !rotz || !params) return fail(GG_E_NULL, "gg_project_fwd_views: NULL input");
+  if (!aligned16(params)) return fail(GG_E_ALIGN, "gg_project_fwd_views: params must be 16-byte aligned");
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
+  cudaError_t e = gg::launch_project_fwd(mus, sigma, sigma_is_f64, rotx, roty, rotz, tx, ty, tz, focal, Bg * V, K, mu2d,
+                                         sigma2d, params, (cudaStream_t)stream, V);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_project_fwd_views");
+}
+
+int gg_project_bwd_views(const float *mus, const void *sigma, int sigma_is_f64, const float *rotx, const float *roty,
+                         const float *rotz, double tx, double ty, double tz, double focal, int Bg, int V, int K,
+                         const float *partials, int T, const double *gmu2d, const double *gsigma2d, float *dmus,
+                         double *dsigma, float *drot, int device, void *stream) {
+  if (V < 1 || V > 64) return fail(GG_E_SHAPE, "V must be in 1..64 (got %d)", V);
+  if (int r = check_bk(Bg * V, K)) return r;
+  if (Bg == 0) return GG_OK;
+  if (!mus || !sigma || !rotx || !roty || !rotz) return fail(GG_E_NULL, "gg_project_bwd_views: NULL input");
+  if (T < 0 || (T > 0 && !partials)) return fail(GG_E_WORKSPACE, "gg_project_bwd_views: T=%d but partials is NULL", T);
+  DeviceGuard guard(device);
+  if (guard.status) return guard.status;
+  cudaError_t e = gg::launch_project_bwd(mus, sigma, sigma_is_f64, rotx, roty, rotz, tx, ty, tz, focal, Bg * V, K,
+                                         partials, T, gmu2d, gsigma2d, dmus, dsigma, drot, (cudaStream_t)stream, V);
+  return e == cudaSuccess ? GG_OK : cuda_fail(e, "gg_project_bwd_views");
+}
+
 int gg_conic_fwd(const void *mu2d, const void *sigma2d, int is_f64, int B, int K, float *params, int device,
                  void *stream) {
   if (int r = check_bk(B, K)) return r;

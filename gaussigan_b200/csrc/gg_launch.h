@@ -6,11 +6,11 @@ namespace gg {
 
 cudaError_t launch_project_fwd(const float *mus, const void *sigma, int f64, const float *rx, const float *ry,
                                const float *rz, double tx, double ty, double tz, double focal, int B, int K,
-                               double *mu2d, double *sigma2d, float *params, cudaStream_t st);
+                               double *mu2d, double *sigma2d, float *params, cudaStream_t st, int nviews = 1);
 cudaError_t launch_project_bwd(const float *mus, const void *sigma, int f64, const float *rx, const float *ry,
                                const float *rz, double tx, double ty, double tz, double focal, int B, int K,
                                const float *partials, int T, const double *gmu2d, const double *gsigma2d,
-                               float *dmus, double *dsigma, float *drot, cudaStream_t st);
+                               float *dmus, double *dsigma, float *drot, cudaStream_t st, int nviews = 1);
 cudaError_t launch_conic_fwd(const void *mu2d, const void *sigma2d, int f64, int N, float *params, cudaStream_t st);
 cudaError_t launch_conic_bwd(const void *mu2d, const void *sigma2d, int f64, int B, int K, const float *partials,
                              int T, double *dmu2d, double *dsigma2d, cudaStream_t st);

@@ -231,18 +231,21 @@ __device__ __forceinline__ void load_sigma(const void *sigma, int is_f64, size_t
 __global__ void __launch_bounds__(128) project_fwd_kernel(
     const float *__restrict__ mus, const void *__restrict__ sigma, int sigma_is_f64,
     const float *__restrict__ rotx, const float *__restrict__ roty, const float *__restrict__ rotz,
-    double tx, double ty, double tz, double focal, int B, int K,
+    double tx, double ty, double tz, double focal, int B, int K, int Bg,
     double *__restrict__ mu2d, double *__restrict__ sigma2d, float *__restrict__ params) {
+  // B rendered images over Bg <= B sets of Gaussians: image b uses set b % Bg (multi-view: V = B / Bg cameras per set,
+  // view-major; Bg == B is the ordinary one camera per set)
   pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * K) return;
   int b = idx / K;
+  const size_t gidx = (size_t)(b % Bg) * K + (idx - b * K);
   // issue every global load before the first use (one round trip instead of two)
   const float rxd = __ldg(rotx + b), ryd = __ldg(roty + b), rzd = __ldg(rotz + b);
   Proj p;
-  load_sigma(sigma, sigma_is_f64, idx, p.S);
+  load_sigma(sigma, sigma_is_f64, gidx, p.S);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) p.mu[i] = (double)__ldg(mus + (size_t)idx * 3 + i);
+  for (int i = 0; i < 3; ++i) p.mu[i] = (double)__ldg(mus + gidx * 3 + i);
   Cam cam;
   make_cam(rxd, ryd, rzd, cam);
   const double t[3] = {tx, ty, tz};
@@ -264,17 +267,22 @@ __global__ void __launch_bounds__(128) project_fwd_kernel(
 __global__ void __launch_bounds__(128) project_bwd_kernel(
     const float *__restrict__ mus, const void *__restrict__ sigma, int sigma_is_f64,
     const float *__restrict__ rotx, const float *__restrict__ roty, const float *__restrict__ rotz,
-    double tx, double ty, double tz, double focal, int B, int K,
+    double tx, double ty, double tz, double focal, int B, int K, int Bg,
     const float *__restrict__ partials, int T, const double *__restrict__ gmu2d_in,
     const double *__restrict__ gsigma2d_in, float *__restrict__ dmus, double *__restrict__ dsigma,
     float *__restrict__ drot) {
   __shared__ double red[3][128];
   __shared__ double Tm_s[128 * GG_MOMENTS];
-  const int b = blockIdx.x;
+  // One CTA per SET of Gaussians; its V = B / Bg views (images bset, bset + Bg, ...) are handled one after the other:
+  // d mus / d Sigma accumulate over the views (the Gaussians are shared), d rot is per view.
+  const int bset = blockIdx.x;
+  const int nviews = B / Bg;
   pdl_enter();   // programmatic dependent launch: see gg_common.cuh
-  const float rxd = __ldg(rotx + b), ryd = __ldg(roty + b), rzd = __ldg(rotz + b);
   const double t[3] = {tx, ty, tz};
   const double f = (double)(float)focal;
+  for (int view = 0; view < nviews; ++view) {
+  const int b = view * Bg + bset;
+  const float rxd = __ldg(rotx + b), ryd = __ldg(roty + b), rzd = __ldg(rotz + b);
   double Rbar[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   Cam cam;
   bool have_cam = false;
@@ -283,11 +291,12 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     const int kn = min(128, K - kb);
     const int k = kb + (int)threadIdx.x;
     const bool active = (int)threadIdx.x < kn;
-    const size_t idx = (size_t)b * K + (active ? k : kb);
+    const size_t idx = (size_t)b * K + (active ? k : kb);             // per-image quantities (partials, gmu2d, gsigma2d)
+    const size_t gidx = (size_t)bset * K + (active ? k : kb);         // the Gaussian itself and its gradients
     Proj p;
-    load_sigma(sigma, sigma_is_f64, idx, p.S);                     // in flight during the column sums
+    load_sigma(sigma, sigma_is_f64, gidx, p.S);                    // in flight during the column sums
 #pragma unroll
-    for (int i = 0; i < 3; ++i) p.mu[i] = (double)__ldg(mus + idx * 3 + i);
+    for (int i = 0; i < 3; ++i) p.mu[i] = (double)__ldg(mus + gidx * 3 + i);
     double gmu[2] = {0, 0}, gsg[4] = {0, 0, 0, 0};
     if (gmu2d_in) { gmu[0] = gmu2d_in[idx * 2]; gmu[1] = gmu2d_in[idx * 2 + 1]; }
     if (gsigma2d_in) {
@@ -377,14 +386,18 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     double Sbar[9];
     mat3_mul_at(cam.R, Spbar, tmp);
     mat3_mul(tmp, cam.R, Sbar);                                // R^T Sigma'bar R
+    // the same thread owns this Gaussian in every view: plain read-modify-write, fixed view order
     if (dsigma) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) dsigma[idx * 9 + i] = Sbar[i];
+      for (int i = 0; i < 9; ++i) dsigma[gidx * 9 + i] = view == 0 ? Sbar[i] : dsigma[gidx * 9 + i] + Sbar[i];
     }
     if (dmus) {
+      // float32, like the sum of the V per-view float32 gradients autograd would form
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-        dmus[idx * 3 + i] = (float)(cam.R[0 * 3 + i] * mbar[0] + cam.R[1 * 3 + i] * mbar[1] + cam.R[2 * 3 + i] * mbar[2]);
+      for (int i = 0; i < 3; ++i) {
+        const float g = (float)(cam.R[0 * 3 + i] * mbar[0] + cam.R[1 * 3 + i] * mbar[1] + cam.R[2 * 3 + i] * mbar[2]);
+        dmus[gidx * 3 + i] = view == 0 ? g : dmus[gidx * 3 + i] + g;
+      }
     }
     // Rbar += Sigma'bar R Sigma^T + Sigma'bar^T R Sigma + mbar mu^T
     double RS[9], RSt[9];
@@ -425,6 +438,8 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
     // degrees -> radians was (deg * pi32) / 180 in float32
     drot[(size_t)b * 3 + threadIdx.x] = (float)(acc * (double)3.14159274101257324219f / 180.0);
   }
+  __syncthreads();   // red[] is reused by the next view
+  }   // views
 }
 
 __global__ void __launch_bounds__(128) conic_fwd_kernel(const void *__restrict__ mu2d,
@@ -487,20 +502,22 @@ __global__ void __launch_bounds__(128) conic_bwd_kernel(const void *__restrict__
 // ------------------------------------------------------------------------------ host launchers
 cudaError_t launch_project_fwd(const float *mus, const void *sigma, int f64, const float *rx, const float *ry,
                                const float *rz, double tx, double ty, double tz, double focal, int B, int K,
-                               double *mu2d, double *sigma2d, float *params, cudaStream_t st) {
+                               double *mu2d, double *sigma2d, float *params, cudaStream_t st, int nviews) {
   int N = B * K;
-  launch_pdl(project_fwd_kernel, dim3((N + 127) / 128), dim3(128), 0, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B, K, mu2d,
-                                                      sigma2d, params);
+  // small launches: 32 threads per CTA spread the Gaussians over more SMs (every thread is one dependent chain)
+  const int threads = N <= 148 * 32 ? 32 : 128;
+  launch_pdl(project_fwd_kernel, dim3((N + threads - 1) / threads), dim3(threads), 0, st, mus, sigma, f64, rx, ry, rz, tx,
+             ty, tz, focal, B, K, B / nviews, mu2d, sigma2d, params);
   return cudaGetLastError();
 }
 
 cudaError_t launch_project_bwd(const float *mus, const void *sigma, int f64, const float *rx, const float *ry,
                                const float *rz, double tx, double ty, double tz, double focal, int B, int K,
                                const float *partials, int T, const double *gmu2d, const double *gsigma2d,
-                               float *dmus, double *dsigma, float *drot, cudaStream_t st) {
+                               float *dmus, double *dsigma, float *drot, cudaStream_t st, int nviews) {
   const int threads = 128;
-  launch_pdl(project_bwd_kernel, dim3(B), dim3(threads), 0, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B, K, partials, T,
-                                            gmu2d, gsigma2d, dmus, dsigma, drot);
+  launch_pdl(project_bwd_kernel, dim3(B / nviews), dim3(threads), 0, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B,
+             K, B / nviews, partials, T, gmu2d, gsigma2d, dmus, dsigma, drot);
   return cudaGetLastError();
 }
 

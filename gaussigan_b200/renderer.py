@@ -35,6 +35,7 @@ class _Spec(NamedTuple):
     want_masks: Tuple[bool, ...]
     layout: int
     want_proj: bool
+    views: int = 1          # cameras per set of Gaussians (rot* hold views * B angles, view-major)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -110,17 +111,18 @@ class _Render(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mus, sigma, rotx, roty, rotz, spec: _Spec):
         dev = mus.device
-        B, K = mus.shape[0], mus.shape[1]
+        Bg, K, V = mus.shape[0], mus.shape[1], spec.views
+        B = Bg * V                                   # rendered images: view-major, image v * Bg + b = set b, camera v
         params = torch.empty((B, K, GG_PARAM_STRIDE), dtype=torch.float32, device=dev)
         mu2d = sigma2d = None
         if spec.want_proj:
             mu2d = torch.empty((B, K, 2), dtype=torch.float64, device=dev)
             sigma2d = torch.empty((B, K, 2, 2), dtype=torch.float64, device=dev)
-        check(lib.gg_project_fwd(mus.data_ptr(), sigma.data_ptr(), int(sigma.dtype == torch.float64),
-                                 rotx.data_ptr(), roty.data_ptr(), rotz.data_ptr(),
-                                 spec.tx, spec.ty, spec.tz, spec.focal, B, K,
-                                 _ptr(mu2d), _ptr(sigma2d), params.data_ptr(), dev.index, _stream(dev)),
-              "gg_project_fwd")
+        check(lib.gg_project_fwd_views(mus.data_ptr(), sigma.data_ptr(), int(sigma.dtype == torch.float64),
+                                       rotx.data_ptr(), roty.data_ptr(), rotz.data_ptr(),
+                                       spec.tx, spec.ty, spec.tz, spec.focal, Bg, V, K,
+                                       _ptr(mu2d), _ptr(sigma2d), params.data_ptr(), dev.index, _stream(dev)),
+              "gg_project_fwd_views")
         maps, masks = ([], [])
         if any(spec.want_maps) or any(spec.want_masks):
             maps, masks = _splat_forward(params, B, K, spec)
@@ -139,7 +141,8 @@ class _Render(torch.autograd.Function):
         mus, sigma, rotx, roty, rotz, params = ctx.saved_tensors
         spec: _Spec = ctx.spec
         dev = mus.device
-        B, K = mus.shape[0], mus.shape[1]
+        Bg, K, V = mus.shape[0], mus.shape[1], spec.views
+        B = Bg * V
         it = iter(grads)
         gmu2d = gsig2d = None
         if spec.want_proj:
@@ -152,15 +155,15 @@ class _Render(torch.autograd.Function):
         if partials is None and gmu2d is None and gsig2d is None:
             return None, None, None, None, None, None
         need = ctx.needs_input_grad
-        dmus = torch.empty((B, K, 3), dtype=torch.float32, device=dev) if need[0] else None
-        dsigma = torch.empty((B, K, 3, 3), dtype=torch.float64, device=dev) if need[1] else None
+        dmus = torch.empty((Bg, K, 3), dtype=torch.float32, device=dev) if need[0] else None
+        dsigma = torch.empty((Bg, K, 3, 3), dtype=torch.float64, device=dev) if need[1] else None
         drot = torch.empty((B, 3), dtype=torch.float32, device=dev) if any(need[2:5]) else None
-        check(lib.gg_project_bwd(mus.data_ptr(), sigma.data_ptr(), int(sigma.dtype == torch.float64),
-                                 rotx.data_ptr(), roty.data_ptr(), rotz.data_ptr(),
-                                 spec.tx, spec.ty, spec.tz, spec.focal, B, K,
-                                 _ptr(partials), T, _ptr(gmu2d), _ptr(gsig2d),
-                                 _ptr(dmus), _ptr(dsigma), _ptr(drot), dev.index, _stream(dev)),
-              "gg_project_bwd")
+        check(lib.gg_project_bwd_views(mus.data_ptr(), sigma.data_ptr(), int(sigma.dtype == torch.float64),
+                                       rotx.data_ptr(), roty.data_ptr(), rotz.data_ptr(),
+                                       spec.tx, spec.ty, spec.tz, spec.focal, Bg, V, K,
+                                       _ptr(partials), T, _ptr(gmu2d), _ptr(gsig2d),
+                                       _ptr(dmus), _ptr(dsigma), _ptr(drot), dev.index, _stream(dev)),
+              "gg_project_bwd_views")
         if dsigma is not None and sigma.dtype != torch.float64:
             dsigma = dsigma.to(sigma.dtype)
         return (dmus, dsigma,
@@ -320,6 +323,45 @@ def get_landmarks(mus, sigma, rotx, roty, rotz, tx, ty, tz, focal=1., *, K: Opti
                      (False,) * len(chunk), _layout_code(layout), False)
         out += list(_Render.apply(mus3, sig, rots[0], rots[1], rots[2], spec))
     return out
+
+
+def get_landmarks_views(mus, sigma, rotx, roty, rotz, tx, ty, tz, focal=1., *, K: Optional[int] = None,
+                        sizes: Sequence[int] = REFERENCE_SIZES, layout: str = "nhwc",
+                        with_mask: bool = False):
+    """V cameras on the same Gaussians in ONE projection launch and ONE splat launch per direction.
+
+    The reference calls ``get_landmarks`` three times per training step on the same ``(mus, sigmas)`` -- pose,
+    pose + random yaw, canonical (mask/mask_gen_dynamic.py:707-709); at its batch size of 3 every call is
+    launch-bound.  ``rotx, roty, rotz``: ``[V,B,1]`` (or ``[V,B]``) float32 degrees.  Returns a list over the V views of
+    what ``get_landmarks`` returns for that view (a list of ``[B,n,n,K]`` maps, views of one ``[V*B,n,n,K]`` tensor per
+    scale); with ``with_mask=True`` each entry is ``(maps_list, mask [B,n_last,n_last,1])`` as from
+    ``get_landmarks_with_mask``.  Gradients of ``mus`` / ``sigma`` are accumulated over the views inside the projection
+    adjoint; each view's angles get their own."""
+    assert mus is not None and sigma is not None
+    if sigma.dim() != 4 or sigma.shape[-2:] != (3, 3):
+        raise ValueError("sigma must be [B,K,3,3]")
+    B = sigma.shape[0]
+    rx = torch.as_tensor(rotx)
+    if rx.dim() < 2 or rx.numel() % B != 0:
+        raise ValueError("rotx/roty/rotz must be [V,B,1] or [V,B]")
+    V = rx.numel() // B
+    flat = [torch.as_tensor(r).reshape(V * B) for r in (rotx, roty, rotz)]
+    dev, _, Kk, mus3, sig, _ = _prep_inputs(mus, sigma, flat[0][:B], flat[1][:B], flat[2][:B], K)
+    rots = [r.float().contiguous() for r in flat]
+    _require_cuda(*rots)
+    sizes = tuple(int(s) for s in sizes)
+    if len(sizes) > _lib.GG_MAX_SCALES:
+        raise ValueError("at most %d scales" % _lib.GG_MAX_SCALES)
+    wk = tuple(with_mask and i == len(sizes) - 1 for i in range(len(sizes)))
+    spec = _Spec(float(tx), float(ty), float(tz), float(focal), sizes, (True,) * len(sizes), wk, _layout_code(layout),
+                 False, V)
+    outs = _Render.apply(mus3, sig, rots[0], rots[1], rots[2], spec)
+    maps = outs[:len(sizes)]
+    res = []
+    for v in range(V):
+        mv = [m[v * B:(v + 1) * B] for m in maps]
+        res.append((mv, outs[-1][v * B:(v + 1) * B].unsqueeze(-1)) if with_mask else mv)
+    return res
 
 
 def get_landmarks_into(bufs: Sequence[torch.Tensor], offsets: Sequence[int], mus, sigma, rotx, roty, rotz, tx, ty, tz,

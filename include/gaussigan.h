@@ -96,6 +96,23 @@ GG_API int gg_project_bwd(const float *mus, const void *sigma, int sigma_is_f64,
                    const float *partials, int T, const double *gmu2d, const double *gsigma2d,
                    float *dmus, double *dsigma, float *drot, int device, void *stream);
 
+/* ---- several cameras per set of Gaussians --------------------------------------------------------
+ * The reference renders the SAME (mus, sigmas) three times per training step -- pose, pose + random yaw, canonical
+ * (mask/mask_gen_dynamic.py:707-709) -- as three get_landmarks calls.  Here V views of Bg sets are one launch:
+ * mus [Bg,K,3], sigma [Bg,K,3,3]; rot* [V*Bg] view-major (image v*Bg + b = set b seen by camera v); params, mu2d,
+ * sigma2d and every splat output are indexed by the V*Bg images (pass B = V*Bg to gg_splat_fwd / gg_splat_bwd: views
+ * are consecutive slices of the batch dimension).  The backward accumulates dmus [Bg,K,3] and dsigma [Bg,K,3,3] over
+ * the views (fixed view order, no atomics); drot [V*Bg,3] is per view.  V = 1 is gg_project_fwd / gg_project_bwd. */
+GG_API int gg_project_fwd_views(const float *mus, const void *sigma, int sigma_is_f64,
+                   const float *rotx, const float *roty, const float *rotz,
+                   double tx, double ty, double tz, double focal, int Bg, int V, int K,
+                   double *mu2d, double *sigma2d, float *params, int device, void *stream);
+GG_API int gg_project_bwd_views(const float *mus, const void *sigma, int sigma_is_f64,
+                   const float *rotx, const float *roty, const float *rotz,
+                   double tx, double ty, double tz, double focal, int Bg, int V, int K,
+                   const float *partials, int T, const double *gmu2d, const double *gsigma2d,
+                   float *dmus, double *dsigma, float *drot, int device, void *stream);
+
 /* ---- conic staging for callers that already hold mu2d / sigma2d -------------------------------
  * Replaces `invsigma = tf.linalg.inv(sigma)` of get_gaussian_maps_2d (mask/mask_gen_dynamic.py:131):
  * mu2d [B,K,2], sigma2d [B,K,2,2] (both f32 or both f64) -> params. */

@@ -246,3 +246,50 @@ def test_concat_direct_forward_and_backward_vs_oracle(gg, cuda_device, K, cx, si
                              sizes=sizes)
     for o, d_ in zip(outs, dense):
         assert_close_norm(o[..., cx:cx + K], d_, 1e-6, "concat-direct vs dense")
+
+
+# ------------------------------------------------------------------------------------- several cameras per set
+@pytest.mark.parametrize("B,K,V,sizes", [(3, 6, 3, (32, 64, 128, 256)), (3, 12, 3, (32, 64)), (2, 16, 2, (64,)), (5, 5, 4, (24,)),
+                                         (1, 130, 2, (16,))])
+def test_multi_view_render_vs_separate_oracle_calls(gg, cuda_device, B, K, V, sizes):
+    """get_landmarks_views: V cameras on the same Gaussians in one projection + one splat launch (the reference's pose /
+    pose + random yaw / canonical renders, mask/mask_gen_dynamic.py:707-709, at its own batch 3 and K = 6 / 12) against V
+    separate oracle calls; d mus / d Sigma are the sums over the views, every view's angles get their own gradient."""
+    inp = rp.synth_inputs(B, K, seed=900 + K)
+    g = torch.Generator().manual_seed(B * K + V)
+    rots = [((torch.rand(V, B, 1, generator=g) - 0.5) * a).float() for a in (30.0, 300.0, 30.0)]
+    rots[1][V - 1] = 0.0                                                   # the canonical view: yaw 0
+    ws = [[torch.randn(B, n, n, K, generator=g) for n in sizes] for _ in range(V)]
+    wm = [torch.randn(B, sizes[-1], sizes[-1], 1, generator=g) for _ in range(V)]
+    lv = {k: inp[k].clone().requires_grad_(True) for k in ("mus", "sigma")}
+    lr = [r.clone().requires_grad_(True) for r in rots]
+    total = 0
+    ref = []
+    for v in range(V):
+        maps = rp.get_landmarks(lv["mus"], lv["sigma"], lr[0][v], lr[1][v], lr[2][v], 0, 0, -2., sizes=sizes)
+        ref.append(maps)
+        total = total + sum((m * w).sum() for m, w in zip(maps, ws[v])) + (maps[-1].sum(-1, keepdim=True) * wm[v]).sum()
+    total.backward()
+    dv = {k: inp[k].clone().to(cuda_device).requires_grad_(True) for k in ("mus", "sigma")}
+    dr = [r.clone().to(cuda_device).requires_grad_(True) for r in rots]
+    out = gg.get_landmarks_views(dv["mus"], dv["sigma"], dr[0], dr[1], dr[2], 0, 0, -2., sizes=sizes, with_mask=True)
+    assert len(out) == V
+    tot = 0
+    for v in range(V):
+        maps, mask = out[v]
+        for m, r in zip(maps, ref[v]):
+            assert_close_norm(m, r, FWD_RTOL, f"view {v} maps n={r.shape[1]}")
+        assert_close_norm(mask, ref[v][-1].detach().sum(-1, keepdim=True), FWD_RTOL, f"view {v} silhouette")
+        tot = tot + sum((m * w.to(cuda_device)).sum() for m, w in zip(maps, ws[v])) + (mask * wm[v].to(cuda_device)).sum()
+    tot.backward()
+    for k in ("mus", "sigma"):
+        assert_close_norm(dv[k].grad, lv[k].grad, GRAD_RTOL, f"multi-view grad {k}")
+    for i, nm in enumerate(("rotx", "roty", "rotz")):
+        assert_close_norm(dr[i].grad, lr[i].grad, GRAD_RTOL, f"multi-view grad {nm}")
+    # one view through the same entry equals the ordinary call bit for bit
+    one = gg.get_landmarks_views(dv["mus"].detach(), dv["sigma"].detach(), dr[0][:1].detach(), dr[1][:1].detach(),
+                                 dr[2][:1].detach(), 0, 0, -2., sizes=sizes)[0]
+    plain = gg.get_landmarks(dv["mus"].detach(), dv["sigma"].detach(), dr[0][0].detach(), dr[1][0].detach(), dr[2][0].detach(),
+                             0, 0, -2., sizes=sizes)
+    for a, b_ in zip(one, plain):
+        assert torch.equal(a, b_)

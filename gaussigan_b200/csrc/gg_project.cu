@@ -8,6 +8,7 @@
 //   M = v v^T - s Q,  sign-flip of the z row/column,  2x2 minors and det(M)  ->  mu2d, sigma2d.
 // The reverse pass is the hand-derived adjoint of exactly those steps, so d Sigma is the raw
 // (non-symmetric) gradient TF's autodiff produces.  B*K threads of O(300) flops: launch-latency bound.
+#include <cstdlib>
 #include "gg_common.cuh"
 
 namespace gg {
@@ -275,9 +276,17 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
   __shared__ double Tm_s[128 * GG_MOMENTS];
   // One CTA per SET of Gaussians; its V = B / Bg views (images bset, bset + Bg, ...) are handled one after the other:
   // d mus / d Sigma accumulate over the views (the Gaussians are shared), d rot is per view.
+  //
+  // Programmatic dependent launch: the Gaussians' own inputs (mus, sigma, rot*) are never written by the kernel that
+  // precedes this one in a stream (that is a splat / fused-loss kernel; they were last written at least two launches
+  // back), so warp 0 loads them and recomputes the whole forward projection BEFORE griddepcontrol.wait, i.e. while the
+  // splat backward is still draining; only the partial sums and the adjoint proper run after it.  The other warps go
+  // straight to the wait and then sum the partials' columns.
   const int bset = blockIdx.x;
   const int nviews = B / Bg;
-  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
+  const bool colwarp = threadIdx.x >= 32;
+  const int ncol = (int)blockDim.x - 32;           // threads that sum columns
+  bool waited = false;
   const double t[3] = {tx, ty, tz};
   const double f = (double)(float)focal;
   for (int view = 0; view < nviews; ++view) {
@@ -289,41 +298,44 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
 
   for (int kb = 0; kb < K; kb += 128) {
     const int kn = min(128, K - kb);
-    const int k = kb + (int)threadIdx.x;
     const bool active = (int)threadIdx.x < kn;
+    // Gaussians of this chunk: thread i takes Gaussian kb + i, in rounds of blockDim.x when the CTA is smaller than
+    // the chunk (never the case for the launch shapes used: 64 threads for K <= 32, 128 otherwise)
+    const int k = kb + (int)threadIdx.x;
     const size_t idx = (size_t)b * K + (active ? k : kb);             // per-image quantities (partials, gmu2d, gsigma2d)
     const size_t gidx = (size_t)bset * K + (active ? k : kb);         // the Gaussian itself and its gradients
     Proj p;
-    load_sigma(sigma, sigma_is_f64, gidx, p.S);                    // in flight during the column sums
+    load_sigma(sigma, sigma_is_f64, gidx, p.S);
 #pragma unroll
     for (int i = 0; i < 3; ++i) p.mu[i] = (double)__ldg(mus + gidx * 3 + i);
+    const bool have_partials = partials && T > 0;
+    if (colwarp) {
+      if (!waited) { pdl_enter(); waited = true; }
+      if (have_partials) {
+        const float *base = partials + ((size_t)b * T * K + kb) * GG_MOMENTS;
+        const size_t tile_stride = (size_t)K * GG_MOMENTS;
+        for (int c = (int)threadIdx.x - 32; c < kn * GG_MOMENTS; c += ncol) {
+          double acc = 0.0;
+          for (int t0 = 0; t0 < T; t0 += 16) {     // 16 independent loads in flight: one round trip for T <= 16
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (t0 + u < T) ? __ldg(base + (size_t)(t0 + u) * tile_stride + c) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc += (double)v[u];
+          }
+          Tm_s[c] = acc;
+        }
+      }
+    }
+    if (!have_cam) { make_cam(rxd, ryd, rzd, cam); have_cam = true; }
+    if (active) project_one(cam, t, f, p);
+    if (!waited) { pdl_enter(); waited = true; }
     double gmu[2] = {0, 0}, gsg[4] = {0, 0, 0, 0};
     if (gmu2d_in) { gmu[0] = gmu2d_in[idx * 2]; gmu[1] = gmu2d_in[idx * 2 + 1]; }
     if (gsigma2d_in) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) gsg[i] = gsigma2d_in[idx * 4 + i];
     }
-    const bool have_partials = partials && T > 0;
-    if (have_partials) {
-      const float *base = partials + ((size_t)b * T * K + kb) * GG_MOMENTS;
-      const size_t tile_stride = (size_t)K * GG_MOMENTS;
-      // warps 1-3 take the columns, so that warp 0 (the Gaussians of a K <= 32 model) is already running the
-      // projection below when the sums land
-      for (int c = (int)threadIdx.x - 32; c < kn * GG_MOMENTS; c += 96) {
-        if (c < 0) break;
-        double acc = 0.0;
-        for (int t0 = 0; t0 < T; t0 += 8) {
-          float v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = (t0 + u < T) ? __ldg(base + (size_t)(t0 + u) * tile_stride + c) : 0.f;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc += (double)v[u];
-        }
-        Tm_s[c] = acc;
-      }
-    }
-    if (!have_cam) { make_cam(rxd, ryd, rzd, cam); have_cam = true; }
-    if (active) project_one(cam, t, f, p);
     __syncthreads();
     if (active) {
     if (have_partials) {
@@ -505,7 +517,8 @@ cudaError_t launch_project_fwd(const float *mus, const void *sigma, int f64, con
                                double *mu2d, double *sigma2d, float *params, cudaStream_t st, int nviews) {
   int N = B * K;
   // small launches: 32 threads per CTA spread the Gaussians over more SMs (every thread is one dependent chain)
-  const int threads = N <= 148 * 32 ? 32 : 128;
+  static const int env_threads = [] { const char *e = std::getenv("GG_PROJ_FWD_THREADS"); return e ? std::atoi(e) : 0; }();
+  const int threads = env_threads > 0 ? env_threads : (N <= 148 * 32 ? 32 : 128);
   launch_pdl(project_fwd_kernel, dim3((N + threads - 1) / threads), dim3(threads), 0, st, mus, sigma, f64, rx, ry, rz, tx,
              ty, tz, focal, B, K, B / nviews, mu2d, sigma2d, params);
   return cudaGetLastError();
@@ -515,7 +528,10 @@ cudaError_t launch_project_bwd(const float *mus, const void *sigma, int f64, con
                                const float *rz, double tx, double ty, double tz, double focal, int B, int K,
                                const float *partials, int T, const double *gmu2d, const double *gsigma2d,
                                float *dmus, double *dsigma, float *drot, cudaStream_t st, int nviews) {
-  const int threads = 128;
+  // 128 threads: warp 0 holds the Gaussians of a K <= 32 model, the other three sum the partials' columns in one round
+  // of loads (measured on the C2 step chain, tools/time_step.py: 128 threads 44.1 us/step, 64 threads 46.2)
+  static const int env_threads = [] { const char *e = std::getenv("GG_PROJ_BWD_THREADS"); return e ? std::atoi(e) : 0; }();
+  const int threads = env_threads > 0 ? env_threads : 128;
   launch_pdl(project_bwd_kernel, dim3(B / nviews), dim3(threads), 0, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B,
              K, B / nviews, partials, T, gmu2d, gsigma2d, dmus, dsigma, drot);
   return cudaGetLastError();

@@ -89,7 +89,10 @@ GG_API int gg_project_fwd(const float *mus, const void *sigma, int sigma_is_f64,
  * when T == 0); gmu2d / gsigma2d (float64, may be NULL) are upstream gradients w.r.t. the mu2d /
  * sigma2d outputs themselves.  Outputs: dmus [B,K,3] f32, dsigma [B,K,3,3] f64 (the raw, generally
  * non-symmetric gradient the reference's autodiff yields), drot [B,3] f32 (d/d rotx,roty,rotz, per
- * degree).  The forward is recomputed in registers; nothing is saved between passes. */
+ * degree).  The forward is recomputed in registers; nothing is saved between passes.  Under programmatic dependent
+ * launch that recompute runs BEFORE the kernel waits for its predecessor in the stream, so mus / sigma / rot* must not
+ * be outputs of the kernel launched immediately before this one (partials, gmu2d and gsigma2d may be); they never
+ * are in the sequences of this library (the predecessor is a splat or fused-loss kernel). */
 GG_API int gg_project_bwd(const float *mus, const void *sigma, int sigma_is_f64,
                    const float *rotx, const float *roty, const float *rotz,
                    double tx, double ty, double tz, double focal, int B, int K,

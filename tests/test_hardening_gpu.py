@@ -293,3 +293,110 @@ def test_multi_view_render_vs_separate_oracle_calls(gg, cuda_device, B, K, V, si
                              0, 0, -2., sizes=sizes)
     for a, b_ in zip(one, plain):
         assert torch.equal(a, b_)
+
+
+# ----------------------------------------------------------------------------------------------- red zones
+def _zoned(shape, dtype, dev, fill):
+    """A tensor of `shape` carved out of the middle of a larger allocation whose margins hold a sentinel."""
+    n = int(np.prod(shape))
+    pad = 4096                                                     # elements on either side
+    pad -= pad % 64
+    big = torch.full((n + 2 * pad,), fill, dtype=dtype, device=dev)
+    return big, big[pad:pad + n].view(shape), pad
+
+
+def _margins_intact(big, pad, fill):
+    lo, hi = big[:pad], big[-pad:]
+    if isinstance(fill, float) and math.isnan(fill):
+        return bool(torch.isnan(lo).all() and torch.isnan(hi).all())
+    return bool((lo == fill).all() and (hi == fill).all())
+
+
+@pytest.mark.parametrize("B,K,sizes", [(3, 16, (32, 64, 128, 256)), (2, 6, (24, 40)), (1, 5, (17,)), (2, 64, (72,)), (2, 12, (48, 8))])
+def test_no_entry_point_writes_outside_its_buffers(gg, cuda_device, restore_modes, B, K, sizes):
+    """compute-sanitizer is closed on this pool (profiles/r2_sanitizer_unavailable.txt), so the out-of-bounds check is
+    done with red zones: every output of every launch entry (projection, maps and masks of the forward in both
+    layouts and both arithmetic modes, partials of the backward through the bulk-copy, quad, strip and fused kernels,
+    loss partials, gradients) sits in the middle of a larger allocation filled with NaN, and the margins must still
+    be NaN afterwards; inputs get the same treatment so that a read past their end would poison the results, which are
+    checked to be finite."""
+    from gaussigan_b200._lib import GG_MOMENTS, GG_PARAM_STRIDE, LAYOUT_NCHW, LAYOUT_NHWC, check, int_array, lib, ptr_array
+    dev, nan = cuda_device, float("nan")
+    st = torch.cuda.current_stream(dev).cuda_stream
+    inp = rp.synth_inputs(B, K, seed=B * 31 + K)
+    zoned_in = {}
+    for k, shape, dt in (("mus", (B, K, 3), torch.float32), ("sigma", (B, K, 3, 3), torch.float64), ("rotx", (B,), torch.float32),
+                         ("roty", (B,), torch.float32), ("rotz", (B,), torch.float32)):
+        big, view, pad = _zoned(shape, dt, dev, nan)
+        view.copy_(inp[k].reshape(shape).to(dev))
+        zoned_in[k] = (big, view, pad)
+    I = {k: v[1] for k, v in zoned_in.items()}
+    outs = []
+
+    def zone(shape, dtype=torch.float32):
+        big, view, pad = _zoned(shape, dtype, dev, nan)
+        outs.append((big, view, pad))
+        return view
+
+    params = zone((B, K, GG_PARAM_STRIDE))
+    mu2d, sg2d = zone((B, K, 2), torch.float64), zone((B, K, 2, 2), torch.float64)
+    check(lib.gg_project_fwd(I["mus"].data_ptr(), I["sigma"].data_ptr(), 1, I["rotx"].data_ptr(), I["roty"].data_ptr(),
+                             I["rotz"].data_ptr(), 0., 0., -2., 1., B, K, mu2d.data_ptr(), sg2d.data_ptr(), params.data_ptr(),
+                             dev.index, st), "project_fwd")
+    sz = int_array(sizes)
+    ns = len(sizes)
+    for fast in (True, False):
+        gg.set_fast_mask(fast)
+        for layout in (LAYOUT_NHWC, LAYOUT_NCHW):
+            maps = [zone((B, n, n, K) if layout == LAYOUT_NHWC else (B, K, n, n)) for n in sizes]
+            masks = [zone((B, n, n)) for n in sizes]
+            check(lib.gg_splat_fwd(params.data_ptr(), B, K, ns, sz, ptr_array([m.data_ptr() for m in maps]),
+                                   ptr_array([m.data_ptr() for m in masks]), layout, dev.index, st), "splat_fwd")
+            only_masks = [zone((B, n, n)) for n in sizes]
+            check(lib.gg_splat_fwd(params.data_ptr(), B, K, ns, sz, ptr_array([None] * ns),
+                                   ptr_array([m.data_ptr() for m in only_masks]), layout, dev.index, st), "splat_fwd(mask)")
+            for m in maps + masks + only_masks:
+                assert torch.isfinite(m).all()
+            # backward: gradients of maps + masks, of maps only, of masks only
+            for hm, hk in (((1,) * ns, (1,) * ns), ((1,) * ns, (0,) * ns), ((0,) * ns, (1,) * ns)):
+                T = check(lib.gg_splat_bwd_tiles(K, ns, sz, int_array(hm), int_array(hk), layout), "tiles")
+                part = zone((B, T, K, GG_MOMENTS))
+                gm = [_zoned(tuple(m.shape), torch.float32, dev, nan) for m in maps]
+                gk = [_zoned(tuple(m.shape), torch.float32, dev, nan) for m in masks]
+                for _, v, _ in gm + gk:
+                    v.normal_()
+                check(lib.gg_splat_bwd(params.data_ptr(), B, K, ns, sz,
+                                       ptr_array([g[1].data_ptr() if h else None for g, h in zip(gm, hm)]),
+                                       ptr_array([g[1].data_ptr() if h else None for g, h in zip(gk, hk)]), layout,
+                                       part.data_ptr(), T, dev.index, st), "splat_bwd")
+                assert torch.isfinite(part).all(), (fast, layout, hm, hk)        # a read past an input would be NaN
+                dmus, dsig, drot = zone((B, K, 3)), zone((B, K, 3, 3), torch.float64), zone((B, 3))
+                check(lib.gg_project_bwd(I["mus"].data_ptr(), I["sigma"].data_ptr(), 1, I["rotx"].data_ptr(), I["roty"].data_ptr(),
+                                         I["rotz"].data_ptr(), 0., 0., -2., 1., B, K, part.data_ptr(), T, None, None,
+                                         dmus.data_ptr(), dsig.data_ptr(), drot.data_ptr(), dev.index, st), "project_bwd")
+                assert torch.isfinite(dmus).all() and torch.isfinite(dsig).all() and torch.isfinite(drot).all()
+        # fused silhouette loss (K <= 64), uint8 and float targets
+        if K <= 64:
+            n = sizes[-1]
+            T = check(lib.gg_splat_bwd_tiles(K, 1, int_array([n]), int_array([0]), int_array([1]), LAYOUT_NHWC), "tiles")
+            for dt, kind in ((torch.uint8, 0), (torch.float32, 1)):
+                tb, tv, tp = _zoned((B, n, n), dt, dev, 255 if dt == torch.uint8 else nan)
+                tv.copy_((torch.rand(B, n, n, device=dev) * (255 if dt == torch.uint8 else 1)).to(dt))
+                part, lp, mo = zone((B, T, K, GG_MOMENTS)), zone((B * T,)), zone((B, n, n))
+                check(lib.gg_silhouette_loss_fused(params.data_ptr(), tv.data_ptr(), kind, B, K, n, mo.data_ptr(), part.data_ptr(),
+                                                   T, lp.data_ptr(), dev.index, st), "fused")
+                assert torch.isfinite(part).all() and torch.isfinite(lp).all() and torch.isfinite(mo).all()
+    # cycle loss and colourise
+    n = sizes[0]
+    Tc, nl = lib.gg_cycle_tiles(n), lib.gg_cycle_loss_count(B, K, n)
+    qa, qb, lp = zone((B, Tc, K, GG_MOMENTS)), zone((B, Tc, K, GG_MOMENTS)), zone((nl,))
+    check(lib.gg_cycle_l1_fused(params.data_ptr(), params.data_ptr(), B, K, n, qa.data_ptr(), qb.data_ptr(), Tc, lp.data_ptr(),
+                                dev.index, st), "cycle")
+    cols = torch.rand(K, 3, device=dev)
+    rgb = zone((B, n, n, 3))
+    check(lib.gg_colorize(params.data_ptr(), None, cols.data_ptr(), B, K, n, rgb.data_ptr(), 0, dev.index, st), "colorize")
+    torch.cuda.synchronize()
+    for big, view, pad in outs:
+        assert _margins_intact(big, pad, nan), f"write outside a buffer of shape {tuple(view.shape)}"
+    for k, (big, view, pad) in zoned_in.items():
+        assert _margins_intact(big, pad, nan), f"input {k} was written"

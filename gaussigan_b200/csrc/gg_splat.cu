@@ -510,61 +510,6 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_pair_kernel(const __grid_c
   }
 }
 
-// ============================================================== forward, 128-bit vectors, K = 4 m + 2
-// Dense NHWC maps for K = 2 (mod 4) -- the reference's K = 6 -- on an even n: two pixels are K / 2 whole 128-bit
-// vectors, so thread = (pixel pair, vector v of the pair), one 16-byte store, consecutive threads -> consecutive
-// 16-byte chunks.  The four elements of vector v are (pixel offset, Gaussian) = ((4 v + e) / K, (4 v + e) % K); a
-// thread keeps them for the whole launch, with their constants in registers -- the pair kernel's arithmetic at twice
-// the bytes per store instruction.
-__global__ void __launch_bounds__(kThreads) splat_fwd_vec2_kernel(const __grid_constant__ SplatArgs a, int P) {
-  pdl_enter();   // programmatic dependent launch: see gg_common.cuh
-  const int b = blockIdx.x / a.T;
-  const int tile = blockIdx.x - b * a.T;
-  const ScaleDesc &s = a.sc[find_scale(a, tile)];
-  const int K = a.K, n = s.n;
-  const int ppp = kThreads / P;                     // pixel pairs per pass
-  const int c0 = threadIdx.x / P, v = threadIdx.x - c0 * P;
-  if (c0 >= ppp) return;
-
-  float mux[4], muy[4], nA[4], nr[4], nE[4];
-  int dp[4];
-  {
-    const float4 *gp = reinterpret_cast<const float4 *>(a.params + (size_t)b * K * GG_PARAM_STRIDE);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int f = 4 * v + e;
-      dp[e] = f >= K ? 1 : 0;
-      const int k = f - dp[e] * K;
-      float4 lo = __ldg(gp + 2 * k), hi = __ldg(gp + 2 * k + 1);
-      mux[e] = lo.x; muy[e] = lo.y; nA[e] = lo.z; nr[e] = lo.w; nE[e] = hi.x;
-    }
-  }
-  const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
-  const int row_end = min(n, row_begin + s.rows_per_tile);
-  const int pairs = n >> 1;
-  for (int row = row_begin; row < row_end; ++row) {
-    const float y = grid_coord(row, s.step);
-    float sh[4], ee[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float dy = y - muy[e];
-      sh[e] = fmaf(nr[e], dy, mux[e]);
-      ee[e] = (nE[e] * dy) * dy;
-    }
-    float *mrow = s.maps + ((size_t)b * n + row) * n * K + 4 * v;
-    for (int pr = c0; pr < pairs; pr += ppp) {
-      const float x0 = grid_coord(2 * pr, s.step), x1 = grid_coord(2 * pr + 1, s.step);
-      float g[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float t = (dp[e] ? x1 : x0) - sh[e];
-        g[e] = ex2_approx(fmaf(nA[e] * t, t, ee[e]));
-      }
-      st_f4(mrow + (size_t)pr * 2 * K, g[0], g[1], g[2], g[3]);
-    }
-  }
-}
-
 // ================================================================================= forward, flat
 // NHWC maps for ANY K with n K % 4 == 0 (the reference's own K = 6 and 12 among them).  A row of the output is n K
 // consecutive floats; thread = 4 of them = one 128-bit store, whichever (pixel, Gaussian) pairs they belong to.
@@ -1029,13 +974,10 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
       launch_pdl(splat_fwd_quadg_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 2);
       err = cudaGetLastError();
     } else if (pl.maps_kind == MAPS_FLAT && (K & 1) == 0 && (K >> 1) <= kThreads) {
-      bool even_n = !pl.strided;
-      for (int i = 0; i < a.nscales; ++i) even_n = even_n && (a.sc[i].n & 1) == 0;
-      static const bool use_vec2 = env_int("GG_FWD_VEC2", 1) != 0;
-      if (even_n && use_vec2)     // dense, every n even: 128-bit stores over pixel pairs
-        launch_pdl(splat_fwd_vec2_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 1);
-      else
-        launch_pdl(splat_fwd_pair_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 1);
+      // (a variant with 128-bit stores over pixel PAIRS -- K / 2 whole vectors per two pixels -- was measured in round 2
+      // and is slower than these 64-bit stores: K = 6: 4.41 vs 4.55 TB/s, K = 10: 5.33 vs 5.76, K = 14: 5.70 vs 6.28 at
+      // B = 64; at this size the launch ramp, not the store width, is what separates K = 6 from the copy bandwidth)
+      launch_pdl(splat_fwd_pair_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 1);
       err = cudaGetLastError();
     } else if (pl.maps_kind == MAPS_FLAT) {
       int max_rows = 1;

@@ -15,7 +15,8 @@ Numbers on the JSON line
             K-step pass is repeated until the timed region is >= 0.5 s, every repetition device-timed, and the
             MEDIAN repetition is reported (max over ranks per repetition).
   e2e       same metric through the public host-buffer call (gaussigan_b200.host.HostSilhouetteStep):
-            pinned-host inputs copied H2D and loss+gradients copied D2H inside the timed region, every step.
+            pinned-host inputs copied H2D and loss+gradients copied D2H inside the timed region, every step; the 8-bit
+            target masks in the library's lossless strip packing (e2e_raw_uint8: the raw image instead).
   roofline  dominant kernel (backward splat): algorithmic issue slots / measured duration vs the FP32 issue
             peak; plus the HBM view of the same launch.  SURVEY.md 8d defines the algorithmic counts.
   cpu_baseline  the oracle (float64 torch restatement of the reference) timed on this box's host cores on a
@@ -445,8 +446,8 @@ def run_gpu(args):
         allreduce = bench_allreduce(args, sets, R, B, K, world, dev, capture, timed_passes, make_pass, KSTEPS)
 
     # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
-    def e2e_leg(target_bits):
-        host = HostSilhouetteStep(B, K, n, dev, depth=6, target_bits=target_bits)
+    def e2e_leg(target_bits=False, target_strips=False):
+        host = HostSilhouetteStep(B, K, n, dev, depth=6, target_bits=target_bits, target_strips=target_strips)
         hsets = [host.make_host_inputs(s[2], s[3]) for s in sets[:min(R, 4)]]
         # the first transfers out of freshly pinned buffers run at a fraction of the steady PCIe rate on this pool's
         # hosts (measured: 390 us per 4 MiB for the first ~100 copies, ~110 us after): warm the path up properly
@@ -478,12 +479,9 @@ def run_gpu(args):
                              "steps_timed": nsub, "timed_region_s": ems * 1e-3,
                              "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes}
 
-    e2e = None
-    try:
-        host, hsets, e2e = e2e_leg(False)
-        # raw pinned-host -> device bandwidth for the target masks of one step, issued the way the e2e path issues them
-        # (one copy per slot stream): what bounds the e2e number
-        hb = hsets[0].target
+    def h2d_alone(host, hb):
+        """raw pinned-host -> device bandwidth for one step's target buffer, issued the way the e2e path issues it (one
+        copy per slot stream, all ranks at once): what bounds the host path"""
         dbs = [torch.empty(hb.shape, dtype=hb.dtype, device=dev) for _ in range(host.depth)]
         cur = torch.cuda.current_stream(dev)
 
@@ -503,24 +501,52 @@ def run_gpu(args):
         copies(400)
         c1.record()
         barrier()
-        h2d_us = max_over_ranks([c0.elapsed_time(c1) / 400 * 1e3])[0]
-        e2e.update({"h2d_copy_alone_us": h2d_us,
-                    "h2d_copy_alone_gbs": hb.numel() * hb.element_size() / (h2d_us * 1e-6) / 1e9,
-                    "bound": "PCIe host->device copy of the uint8 target masks (4.19 MB/step): compare ms_per_step with "
-                             "h2d_copy_alone_us (the same copies alone, one per slot stream, all ranks at once, no kernels)",
+        us = max_over_ranks([c0.elapsed_time(c1) / 400 * 1e3])[0]
+        return us, hb.numel() * hb.element_size() / (us * 1e-6) / 1e9
+
+    # ---- e2e (headline): host buffers in, loss + gradients out, every copy inside the timed region.  The 8-bit target
+    # masks cross the host link in the library's LOSSLESS strip packing (GG_TARGET_STRIPS: two header bits per flat
+    # 8-pixel strip, 8 raw bytes otherwise; bit-identical results to the raw image, tests/test_hardening_gpu.py); the
+    # packing is done once per mask by the data loader (gaussigan_b200.host.encode_target_strips) and is timed
+    # separately below.  `e2e_raw_uint8` is the same step with the raw [B,256,256] uint8 image copied instead.
+    e2e = None
+    try:
+        host, hsets, e2e = e2e_leg(target_strips=True)
+        raw_img = ((sets[0][3].reshape(B, n, n) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+        from gaussigan_b200.host import encode_target_strips
+        t0 = time.perf_counter()
+        for _ in range(5):
+            encode_target_strips(raw_img, pin=False)
+        enc_ms = (time.perf_counter() - t0) / 5 * 1e3
+        h2d_us, h2d_gbs = h2d_alone(host, hsets[0].target)
+        e2e.update({"target_format": "GG_TARGET_STRIPS: lossless strip packing of the uint8 masks "
+                                     f"({hsets[0].target.numel()} bytes instead of {B * n * n} for this batch of synthetic discs)",
+                    "encode": {"ms_per_batch_one_host_thread": enc_ms, "where": "data loader, once per mask, outside the timed region",
+                               "api": "gaussigan_b200.host.encode_target_strips -> gg_encode_target_strips"},
+                    "h2d_copy_alone_us": h2d_us, "h2d_copy_alone_gbs": h2d_gbs,
                     "api": "gaussigan_b200.host.HostSilhouetteStep.submit (pinned host buffers) -> gg_silhouette_step_host",
                     "launches_per_step": host.LAUNCHES_PER_STEP, "host_numa": numa})
-        del host, hsets, dbs
+        del host, hsets
     except Exception as exc:                      # pragma: no cover - reported, never hidden
         e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
 
-    # ---- the same host-buffer step with the (binary) synthetic targets packed 1 bit per pixel (GG_TARGET_BITS): shows
-    # what the host path does once the PCIe copy of the masks is out of the way.  Secondary: the reference's masks are
-    # 8-bit images, so the headline e2e above stays on uint8 targets.
+    e2e_raw = None
+    try:
+        host, hsets, e2e_raw = e2e_leg()
+        h2d_us, h2d_gbs = h2d_alone(host, hsets[0].target)
+        e2e_raw.update({"target_format": "raw uint8 image [B,256,256] (the round-1 headline e2e)",
+                        "h2d_copy_alone_us": h2d_us, "h2d_copy_alone_gbs": h2d_gbs,
+                        "bound": "PCIe host->device copy of the uint8 target masks (4.19 MB/step): compare ms_per_step with "
+                                 "h2d_copy_alone_us (the same copies alone, one per slot stream, all ranks at once, no kernels)"})
+        del host, hsets
+    except Exception as exc:                      # pragma: no cover
+        e2e_raw = {"value": None, "unit": UNIT, "error": repr(exc)}
+
+    # ---- the same host-buffer step with the (binary) synthetic targets packed 1 bit per pixel (GG_TARGET_BITS)
     e2e_bits = None
     try:
-        _, _, e2e_bits = e2e_leg(True)
-        e2e_bits["note"] = "binary target masks packed 1 bit/pixel (lossless for the synthetic discs; not the reference's format)"
+        _, _, e2e_bits = e2e_leg(target_bits=True)
+        e2e_bits["note"] = "binary target masks packed 1 bit/pixel (lossless for two-level masks only)"
     except Exception as exc:                      # pragma: no cover
         e2e_bits = {"value": None, "error": repr(exc)}
 
@@ -544,7 +570,8 @@ def run_gpu(args):
                                  f"{min(KSTEPS, CHAIN_MAX)} steps (programmatic-dependent-launch edges, also across step "
                                  f"boundaries); {hl['reps']} passes back to back = {hl['timed_region_s']:.2f} s timed region, each "
                                  "pass timed with CUDA events; value = median pass, max over ranks per pass"},
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "e2e_binary_targets": e2e_bits,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "e2e_raw_uint8": e2e_raw,
+            "e2e_binary_targets": e2e_bits,
             "fused_loss": fused, "two_chains": two_chains, "maps_mode": maps_mode,
             "allreduce": allreduce, "configs": configs,
             "gpu_launches": hl["reps"] * KSTEPS * SilhouetteStep.LAUNCHES_PER_STEP,

@@ -72,6 +72,8 @@ SIGNATURES = {
     "gg_cycle_loss_count": (_i, [_i, _i, _i]),
     "gg_cycle_l1_fused": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "gg_colorize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    "gg_target_strips_bound": (C.c_size_t, [_i, _i]),
+    "gg_encode_target_strips": (C.c_longlong, [_vp, _i, _i, _vp, C.c_size_t]),
     "gg_silhouette_step_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "gg_silhouette_step_loss_count": (_i, [_i, _i, _i]),
     "gg_silhouette_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _d, _d, _d, _i, _i, _i,

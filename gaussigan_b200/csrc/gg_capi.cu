@@ -297,13 +297,16 @@ int gg_silhouette_loss_fused(const float *params, const void *target, int target
   const int sizes[1] = {n};
   if (int r = check_scales(K, 1, sizes)) return r;
   if (K > 64) return fail(GG_E_SHAPE, "gg_silhouette_loss_fused: K=%d > 64 (use the unfused entry points)", K);
-  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32 && target_kind != GG_TARGET_BITS)
+  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32 && target_kind != GG_TARGET_BITS &&
+      target_kind != GG_TARGET_STRIPS)
     return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
-  if (target_kind == GG_TARGET_BITS && !gg::fast_mask())
-    return fail(GG_E_SHAPE, "GG_TARGET_BITS needs the forward-differenced kernels (gg_set_fast_mask(1))");
+  if ((target_kind == GG_TARGET_BITS || target_kind == GG_TARGET_STRIPS) && !gg::fast_mask())
+    return fail(GG_E_SHAPE, "GG_TARGET_BITS / GG_TARGET_STRIPS need the forward-differenced kernels (gg_set_fast_mask(1))");
+  if (target_kind == GG_TARGET_STRIPS && (reinterpret_cast<uintptr_t>(target) & 7))
+    return fail(GG_E_ALIGN, "gg_silhouette_loss_fused: a GG_TARGET_STRIPS buffer must be 8-byte aligned");
   if (B == 0) return GG_OK;
   if (!params || !target || !partials || !loss_partials) return fail(GG_E_NULL, "gg_silhouette_loss_fused: NULL pointer");
-  if (!aligned16(params) || (mask_out && !aligned16(mask_out)) || (target_kind != GG_TARGET_BITS && !aligned16(target)))
+  if (!aligned16(params) || (mask_out && !aligned16(mask_out)) || (target_kind != GG_TARGET_BITS && target_kind != GG_TARGET_STRIPS && !aligned16(target)))
     return fail(GG_E_ALIGN, "gg_silhouette_loss_fused: params/target/mask_out must be 16-byte aligned");
   if (T != gg::fused_loss_tiles(K, n)) return fail(GG_E_WORKSPACE, "gg_silhouette_loss_fused: T=%d, expected %d", T, gg::fused_loss_tiles(K, n));
   DeviceGuard guard(device);

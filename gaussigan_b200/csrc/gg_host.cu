@@ -16,7 +16,16 @@ struct StepLayout {
 
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
+constexpr unsigned kStripsMagic = 0x54534747u;   // "GGST"
+
+static size_t strips_payload_offset(int B, int n) { return (16 + (size_t)B * n * 4 + 7) & ~size_t(7); }
+static size_t strips_bound(int B, int n) {
+  const size_t strips = (size_t)(n + 7) / 8, W = (strips + 31) / 32;
+  return strips_payload_offset(B, n) + (size_t)B * n * (8 * W + 8 * strips);
+}
+
 static size_t target_bytes(int B, int n, int target_kind) {
+  if (target_kind == GG_TARGET_STRIPS) return strips_bound(B, n);        // capacity; the bytes in use are in the header
   if (target_kind == GG_TARGET_BITS) return (size_t)B * n * ((n + 7) / 8);
   return (size_t)B * n * n * (target_kind == GG_TARGET_U8 ? 1 : 4);
 }
@@ -78,6 +87,50 @@ using gg::zero_copy_enabled;
 
 extern "C" {
 
+size_t gg_target_strips_bound(int B, int n) {
+  if (B <= 0 || n < 1) return 0;
+  return gg::strips_bound(B, n);
+}
+
+long long gg_encode_target_strips(const unsigned char *image_host, int B, int n, void *out_host, size_t capacity) {
+  if (B <= 0 || n < 1 || n > 16384) return fail(GG_E_SHAPE, "gg_encode_target_strips: bad B=%d n=%d", B, n);
+  if (!image_host || !out_host) return fail(GG_E_NULL, "gg_encode_target_strips: NULL pointer");
+  if (reinterpret_cast<uintptr_t>(out_host) & 7) return fail(GG_E_ALIGN, "gg_encode_target_strips: out must be 8-byte aligned");
+  const int strips = (n + 7) / 8, W = (strips + 31) / 32;
+  const size_t pay0 = gg::strips_payload_offset(B, n);
+  if (capacity < pay0) return fail(GG_E_WORKSPACE, "gg_encode_target_strips: capacity %zu too small", capacity);
+  unsigned char *out = reinterpret_cast<unsigned char *>(out_host);
+  unsigned *hdr = reinterpret_cast<unsigned *>(out);
+  unsigned *offs = hdr + 4;
+  size_t used = 0;                                      // bytes of payload written
+  for (size_t r = 0; r < (size_t)B * n; ++r) {
+    const unsigned char *src = image_host + r * n;
+    if (pay0 + used + 8 * (size_t)W + 8 * (size_t)strips > capacity)
+      return fail(GG_E_WORKSPACE, "gg_encode_target_strips: capacity %zu too small (use gg_target_strips_bound)", capacity);
+    unsigned char *rec = out + pay0 + used;
+    unsigned *M = reinterpret_cast<unsigned *>(rec), *V = M + W;
+    for (int w = 0; w < W; ++w) M[w] = V[w] = 0u;
+    unsigned char *lit = rec + 8 * W;
+    int nlit = 0;
+    for (int s_ = 0; s_ < strips; ++s_) {
+      const int c0 = s_ * 8, cnt = n - c0 < 8 ? n - c0 : 8;
+      unsigned long long x = 0;
+      std::memcpy(&x, src + c0, (size_t)cnt);
+      const unsigned long long ones = cnt == 8 ? ~0ull : ((1ull << (8 * cnt)) - 1ull);
+      if (x == 0ull) continue;                            // flat 0: M = 0, V = 0
+      if (x == ones) { V[s_ >> 5] |= 1u << (s_ & 31); continue; }   // flat 255
+      M[s_ >> 5] |= 1u << (s_ & 31);
+      std::memcpy(lit + 8 * (size_t)nlit, &x, 8);
+      ++nlit;
+    }
+    offs[r] = (unsigned)used;
+    used += 8 * (size_t)W + 8 * (size_t)nlit;
+    if (used > 0xffffffffull) return fail(GG_E_SHAPE, "gg_encode_target_strips: payload exceeds 4 GiB");
+  }
+  hdr[0] = gg::kStripsMagic; hdr[1] = (unsigned)n; hdr[2] = (unsigned)B; hdr[3] = (unsigned)(pay0 + used);
+  return (long long)(pay0 + used);
+}
+
 size_t gg_silhouette_step_workspace_bytes(int B, int K, int n, int target_kind) {
   if (B <= 0 || K <= 0 || n < 1) return 0;
   return gg::step_layout(B, K, n, target_kind).total;
@@ -98,10 +151,11 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
   const int sizes[1] = {n};
   if (int r = check_scales(K, 1, sizes)) return r;
   if (B == 0) return GG_OK;
-  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32 && target_kind != GG_TARGET_BITS)
+  if (target_kind != GG_TARGET_U8 && target_kind != GG_TARGET_F32 && target_kind != GG_TARGET_BITS &&
+      target_kind != GG_TARGET_STRIPS)
     return fail(GG_E_SHAPE, "unknown target_kind %d", target_kind);
-  if (target_kind == GG_TARGET_BITS && (K > 64 || !gg::fast_mask()))
-    return fail(GG_E_SHAPE, "GG_TARGET_BITS: K <= 64 and the forward-differenced kernels only");
+  if ((target_kind == GG_TARGET_BITS || target_kind == GG_TARGET_STRIPS) && (K > 64 || !gg::fast_mask()))
+    return fail(GG_E_SHAPE, "GG_TARGET_BITS / GG_TARGET_STRIPS: K <= 64 and the forward-differenced kernels only");
   if (!mus_host || !sigma_host || !rotx_host || !roty_host || !rotz_host || !target_host || !loss_partials_host ||
       !dmus_host || !dsigma_host || !drot_host || !workspace)
     return fail(GG_E_NULL, "gg_silhouette_step_host: NULL pointer");
@@ -158,9 +212,17 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
     static const bool zc_target = [] { const char *v = std::getenv("GG_ZEROCOPY_TARGET"); return v && v[0] == '1'; }();
     const void *m = zc_target ? mapped_or_null(target_host, gg::target_bytes(B, n, target_kind)) : nullptr;
     if (m) k_target = m;
-    else
-      GG_TRY(cudaMemcpyAsync(d_target, target_host, gg::target_bytes(B, n, target_kind), cudaMemcpyHostToDevice,
-                             st), "H2D target");
+    else {
+      size_t tbytes = gg::target_bytes(B, n, target_kind);
+      if (target_kind == GG_TARGET_STRIPS) {       // the packed size is data dependent: read it from the buffer's header
+        const unsigned *h = reinterpret_cast<const unsigned *>(target_host);
+        if ((reinterpret_cast<uintptr_t>(target_host) & 7) || h[0] != gg::kStripsMagic || h[1] != (unsigned)n ||
+            h[2] != (unsigned)B || h[3] > tbytes)
+          return fail(GG_E_SHAPE, "gg_silhouette_step_host: target_host is not a GG_TARGET_STRIPS buffer for B=%d n=%d", B, n);
+        tbytes = h[3];
+      }
+      GG_TRY(cudaMemcpyAsync(d_target, target_host, tbytes, cudaMemcpyHostToDevice, st), "H2D target");
+    }
   }
   GG_TRY(gg::launch_project_fwd(k_mus, k_sigma, 1, k_rx, k_ry, k_rz, tx, ty, tz, focal, B, K,
                                 nullptr, nullptr, d_params, st), "project_fwd");

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
     }
   }
   stage_fast_consts(a.params + ((size_t)b * K + k0) * GG_PARAM_STRIDE, kn, h, x_lo, x_hi, y_lo, y_hi, sc);
-  if (FUSED && a.target_kind == GG_TARGET_U8) {
+  if (FUSED && (a.target_kind == GG_TARGET_U8 || a.target_kind == GG_TARGET_STRIPS)) {
     // 0.5 * ((raw / 127.5 - 1) + 1), op by op in float32 as the reference (:672, :787): one division per
     // thread instead of one per pixel
     for (int i = threadIdx.x; i < 256; i += NW * 32)
@@ -284,6 +284,30 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) tg[j] = (pos.colA + j < n) ? lut[__ldg(tp + pos.colA + j)] : 0.f;
+        }
+      } else if (a.target_kind == GG_TARGET_STRIPS) {
+        // lossless strip packing (include/gaussigan.h): two header bits per flat strip, 8 raw bytes otherwise
+        const unsigned char *base = reinterpret_cast<const unsigned char *>(a.target);
+        const unsigned *offs = reinterpret_cast<const unsigned *>(base + 16);
+        const size_t payload = (16 + (size_t)a.B * n * 4 + 7) & ~(size_t)7;
+        const int W = (((n + 7) >> 3) + 31) >> 5;
+        const unsigned char *rec = base + payload + __ldg(offs + (size_t)b * n + row[r]);
+        const unsigned *hdr = reinterpret_cast<const unsigned *>(rec);
+        const int strip = pos.colA >> 3, word = strip >> 5, bit = strip & 31;
+        const unsigned M = __ldg(hdr + word);
+        if ((M >> bit) & 1u) {
+          int idx = __popc(M & ((1u << bit) - 1u));
+          for (int w = 0; w < word; ++w) idx += __popc(__ldg(hdr + w));
+          const uint2 u = __ldg(reinterpret_cast<const uint2 *>(rec + 8 * W) + idx);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            tg[j] = lut[(u.x >> (8 * j)) & 0xffu];
+            tg[j + 4] = lut[(u.y >> (8 * j)) & 0xffu];
+          }
+        } else {
+          const float v = ((__ldg(hdr + W + word) >> bit) & 1u) ? lut[255] : lut[0];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tg[j] = v;
         }
       } else if (a.target_kind == GG_TARGET_BITS) {
         // one byte = this thread's 8 pixels (strips start at multiples of 8); bit set -> 0.5 * (1 + 1) = 1

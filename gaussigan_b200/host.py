@@ -16,8 +16,28 @@ import torch
 
 from ._lib import check, lib
 
-GG_TARGET_U8, GG_TARGET_F32, GG_TARGET_BITS = 0, 1, 2
+GG_TARGET_U8, GG_TARGET_F32, GG_TARGET_BITS, GG_TARGET_STRIPS = 0, 1, 2, 3
 GG_LOSS_PARTIALS = 296
+
+
+def encode_target_strips(image_u8: torch.Tensor, pin: bool = True) -> torch.Tensor:
+    """Pack 8-bit target masks ``[B,n,n]`` uint8 (host tensor) losslessly by 8-pixel strips (``GG_TARGET_STRIPS``,
+    include/gaussigan.h): a strip whose pixels are all 0 or all 255 costs two header bits, any other strip its 8 raw
+    bytes.  Silhouette masks are mostly flat, so the result is several times smaller than the image -- it is what
+    crosses the host link.  Returns a 1-D uint8 host tensor (pinned by default) holding exactly the bytes in use; the
+    step's results are bit-identical to those on the raw image.  One pass at memory speed: meant to be called by the
+    data loader when it produces the mask."""
+    assert image_u8.dtype == torch.uint8 and image_u8.dim() == 3 and image_u8.shape[1] == image_u8.shape[2]
+    assert not image_u8.is_cuda, "encode_target_strips packs HOST images"
+    img = image_u8.contiguous()
+    B, n = int(img.shape[0]), int(img.shape[1])
+    cap = int(lib.gg_target_strips_bound(B, n))
+    scratch = torch.empty(cap // 8 + 1, dtype=torch.int64)
+    used = int(lib.gg_encode_target_strips(img.data_ptr(), B, n, scratch.data_ptr(), cap))
+    check(used, "gg_encode_target_strips")
+    out = torch.empty((used + 7) // 8, dtype=torch.int64, pin_memory=pin)
+    out.copy_(scratch[:out.numel()])
+    return out.view(torch.uint8)[:used]
 
 
 def _parse_cpulist(text: str):
@@ -109,7 +129,8 @@ class HostSilhouetteStep:
 
     def __init__(self, B: int, K: int, size: int = 256, device="cuda", depth: int = 2,
                  tx: float = 0.0, ty: float = 0.0, tz: float = -2.0, focal: float = 1.0,
-                 target_dtype: torch.dtype = torch.uint8, want_mask: bool = False, target_bits: bool = False):
+                 target_dtype: torch.dtype = torch.uint8, want_mask: bool = False, target_bits: bool = False,
+                 target_strips: bool = False):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("gaussigan_b200 runs on CUDA (sm_100a) only; there is no CPU path")
@@ -126,6 +147,10 @@ class HostSilhouetteStep:
             if target_dtype != torch.uint8 or K > 64:
                 raise ValueError("target_bits needs uint8 storage and K <= 64")
             self.kind = GG_TARGET_BITS
+        if target_strips:        # any 8-bit mask, losslessly packed by strips (GG_TARGET_STRIPS): ~7x fewer bytes over PCIe
+            if target_dtype != torch.uint8 or K > 64 or target_bits:
+                raise ValueError("target_strips needs uint8 masks and K <= 64 (and excludes target_bits)")
+            self.kind = GG_TARGET_STRIPS
         self.ws_bytes = int(lib.gg_silhouette_step_workspace_bytes(self.B, self.K, self.n, self.kind))
         if self.ws_bytes <= 0:
             raise ValueError("bad B/K/size")
@@ -138,7 +163,9 @@ class HostSilhouetteStep:
         self._next = 0
         self.target_numel = B * size * ((size + 7) // 8) if self.kind == GG_TARGET_BITS else B * size * size
         tb = 4 if self.kind == GG_TARGET_F32 else 1
-        self.h2d_bytes = B * K * 3 * 4 + B * K * 9 * 8 + 3 * B * 4 + self.target_numel * tb
+        self.small_h2d_bytes = B * K * 3 * 4 + B * K * 9 * 8 + 3 * B * 4
+        #: bytes copied host -> device per step (strips: the size of the LAST submitted target; it is data dependent)
+        self.h2d_bytes = self.small_h2d_bytes + self.target_numel * tb
         self.d2h_bytes = (self.nloss * 4 + B * K * 3 * 4 + B * K * 9 * 8 + B * 3 * 4
                           + (B * size * size * 4 if want_mask else 0))
 
@@ -146,7 +173,10 @@ class HostSilhouetteStep:
         """Pack oracle-style inputs (mus [B,K,1,3], sigma, rot [B,1], target [B,n,n,1] in {-1,+1}) into pinned buffers."""
         B, K, n = self.B, self.K, self.n
         t = target_pm1.reshape(B, n, n)
-        if self.kind == GG_TARGET_BITS:
+        if self.kind == GG_TARGET_STRIPS:
+            raw = ((t + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+            t = encode_target_strips(raw)
+        elif self.kind == GG_TARGET_BITS:
             assert bool(((t == 1) | (t == -1)).all()), "target_bits: the masks must be two-level (-1 / +1)"
             t = torch.from_numpy(np.packbits((t > 0).numpy(), axis=-1, bitorder="little"))      # [B,n,ceil(n/8)]
         elif self.kind == GG_TARGET_U8:
@@ -158,14 +188,18 @@ class HostSilhouetteStep:
                           inp["rotx"].reshape(B).float().contiguous().pin_memory(),
                           inp["roty"].reshape(B).float().contiguous().pin_memory(),
                           inp["rotz"].reshape(B).float().contiguous().pin_memory(),
-                          t.contiguous().pin_memory())
+                          t if t.is_pinned() else t.contiguous().pin_memory())
 
     def submit(self, h: HostInputs) -> StepResult:
         """Enqueue one whole step on the next slot; returns that slot's (asynchronously filled) result."""
         B, K, n = self.B, self.K, self.n
         assert h.mus.dtype == torch.float32 and h.mus.numel() == B * K * 3 and h.mus.is_contiguous()
         assert h.sigma.dtype == torch.float64 and h.sigma.numel() == B * K * 9 and h.sigma.is_contiguous()
-        assert h.target.dtype == self.target_dtype and h.target.numel() == self.target_numel and h.target.is_contiguous()
+        if self.kind == GG_TARGET_STRIPS:
+            assert h.target.dtype == torch.uint8 and h.target.is_contiguous() and h.target.data_ptr() % 8 == 0
+            self.h2d_bytes = self.small_h2d_bytes + h.target.numel()
+        else:
+            assert h.target.dtype == self.target_dtype and h.target.numel() == self.target_numel and h.target.is_contiguous()
         for r in (h.rotx, h.roty, h.rotz):
             assert r.dtype == torch.float32 and r.numel() == B and r.is_contiguous()
         assert not h.mus.is_cuda and not h.target.is_cuda, "HostSilhouetteStep takes HOST tensors"

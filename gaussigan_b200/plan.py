@@ -136,11 +136,15 @@ class SilhouetteLossStep(SilhouetteStep):
         self.loss_partials = torch.empty(self.B * self.T, dtype=torch.float32, device=self.dev)
         self.want_mask = want_mask
 
-    def loss_backward(self, target: torch.Tensor, bits: bool = False):
+    def loss_backward(self, target: torch.Tensor, bits: bool = False, strips: bool = False):
         """``target`` [B,n,n] uint8 (raw 0..255) or float32 in [-1,1]; with ``bits=True`` a two-level mask packed one
-        bit per pixel, uint8 [B,n,ceil(n/8)] (``numpy.packbits(mask > 0, axis=-1, bitorder="little")``)."""
+        bit per pixel, uint8 [B,n,ceil(n/8)] (``numpy.packbits(mask > 0, axis=-1, bitorder="little")``); with
+        ``strips=True`` the device copy of a ``gaussigan_b200.host.encode_target_strips`` buffer (any 8-bit mask, lossless)."""
         assert target.is_cuda and target.is_contiguous()
-        if bits:
+        if strips:
+            assert target.dtype == torch.uint8 and target.data_ptr() % 8 == 0
+            kind = 3
+        elif bits:
             assert target.dtype == torch.uint8 and target.numel() == self.B * self.n * ((self.n + 7) // 8)
             kind = 2
         else:

@@ -61,6 +61,11 @@ extern "C" {
                                      bit 0 = mask -1.  Lossless only for two-level masks; 8x fewer bytes than GG_TARGET_U8
                                      on the host link.  gg_silhouette_loss_fused (forward-differenced kernels) and
                                      gg_silhouette_step_host with K <= 64 only. */
+#define GG_TARGET_STRIPS 3        /* ANY 8-bit target mask, losslessly packed by 8-pixel strips (gg_encode_target_strips): a
+                                     strip whose pixels are all 0 or all 255 costs two header bits, any other strip its 8 raw
+                                     bytes.  Silhouette masks are mostly flat, so the buffer is ~7x smaller than the raw image
+                                     on the host link; results are bit-identical to GG_TARGET_U8 on the same image.  Same
+                                     entry points and restrictions as GG_TARGET_BITS. */
 #define GG_LOSS_PARTIALS 296      /* per-CTA partial sums of |residual| written by gg_mask_l1_loss_bwd */
 
 #define GG_OK 0
@@ -296,6 +301,18 @@ GG_API int gg_shared_grad_allreduce_p2p(const float *dmus, const double *dsigma,
  * mus/sigma/rot at the END of the chain and writes the gradients directly into the host buffers, so every host
  * buffer -- inputs and outputs -- must stay untouched until the stream has passed the whole call (record an event
  * after it), not merely until the leading copies are done. */
+/* GG_TARGET_STRIPS buffer (host or device memory, 8-byte aligned):
+ *   bytes 0..15   uint32 magic 0x54534747 ("GGST"), n, B, total_bytes
+ *   then          uint32 row_offset[B*n]: byte offset of row (b, r)'s record from the start of the payload
+ *   then (8-byte aligned) payload; record of one row, W = ceil(ceil(n/8) / 32):
+ *                 uint32 M[W] (bit s set: strip s is stored raw), uint32 V[W] (bit s: a flat strip's value, 1 = 255),
+ *                 then 8 bytes per raw strip in strip order (pixels past the row's end are zero).
+ * gg_target_strips_bound: bytes that always suffice.  gg_encode_target_strips (host function, no CUDA): image
+ * [B,n,n] uint8 -> buffer; returns the bytes used (also stored in the header) or < 0.  One pass over the image at
+ * memory speed; a data loader calls it when it produces the mask. */
+GG_API size_t gg_target_strips_bound(int B, int n);
+GG_API long long gg_encode_target_strips(const unsigned char *image_host, int B, int n, void *out_host, size_t capacity);
+
 GG_API size_t gg_silhouette_step_workspace_bytes(int B, int K, int n, int target_kind);
 GG_API int gg_silhouette_step_loss_count(int B, int K, int n);
 GG_API int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, const float *rotx_host,

@@ -171,3 +171,51 @@ def test_mode_switches_are_safe_to_flip_from_threads():
     fake = C.c_void_p(1 << 20)
     rc = lib.gg_splat_bwd(fake, 2, 16, 1, ia([256]), None, _lib.ptr_array([1 << 20]), 0, fake, t_fast + 1, 0, None)
     assert rc == -5
+
+
+def test_strip_packing_is_lossless_on_the_host():
+    """gg_encode_target_strips (host function, no CUDA): decode the buffer in numpy and compare with the image -- two-level,
+    anti-aliased and noise masks, n that is not a multiple of 8 and n > 256 (several header words per row)."""
+    import numpy as np
+    from gaussigan_b200 import _lib
+    lib = _lib.lib
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 8, 37, 100, 256, 300, 520):
+        for kind in range(3):
+            B = 2
+            if kind == 0:
+                img = (rng.random((B, n, n)) < 0.5).astype(np.uint8) * 255
+                img[:, : n // 2] = 0
+                img[:, n // 2:, : n // 3] = 255
+            elif kind == 1:
+                img = np.clip(rng.normal(128, 200, (B, n, n)), 0, 255).astype(np.uint8)
+            else:
+                img = rng.integers(0, 256, (B, n, n), dtype=np.uint8)
+            cap = lib.gg_target_strips_bound(B, n)
+            buf = np.zeros(cap // 8 + 1, np.uint64)
+            used = lib.gg_encode_target_strips(img.ctypes.data, B, n, buf.ctypes.data, cap)
+            assert 0 < used <= cap
+            raw = buf.view(np.uint8)[:used]
+            hdr = raw[:16].view(np.uint32)
+            assert hdr[0] == 0x54534747 and hdr[1] == n and hdr[2] == B and hdr[3] == used
+            offs = raw[16:16 + 4 * B * n].view(np.uint32)
+            pay0 = (16 + 4 * B * n + 7) & ~7
+            strips = (n + 7) // 8
+            W = (strips + 31) // 32
+            dec = np.zeros((B * n, strips * 8), np.uint8)
+            for r in range(B * n):
+                rec = raw[pay0 + offs[r]:]
+                M = rec[:4 * W].view(np.uint32)
+                V = rec[4 * W:8 * W].view(np.uint32)
+                k = 0
+                for s in range(strips):
+                    if (M[s >> 5] >> (s & 31)) & 1:
+                        dec[r, 8 * s:8 * s + 8] = rec[8 * W + 8 * k:8 * W + 8 * k + 8]
+                        k += 1
+                    elif (V[s >> 5] >> (s & 31)) & 1:
+                        dec[r, 8 * s:8 * s + 8] = 255
+            assert np.array_equal(dec[:, :n].reshape(B, n, n), img), (n, kind)
+    # too small a buffer is refused
+    img = np.zeros((1, 64, 64), np.uint8)
+    small = np.zeros(8, np.uint64)
+    assert lib.gg_encode_target_strips(img.ctypes.data, 1, 64, small.ctypes.data, 64) == -5

@@ -400,3 +400,56 @@ def test_no_entry_point_writes_outside_its_buffers(gg, cuda_device, restore_mode
         assert _margins_intact(big, pad, nan), f"write outside a buffer of shape {tuple(view.shape)}"
     for k, (big, view, pad) in zoned_in.items():
         assert _margins_intact(big, pad, nan), f"input {k} was written"
+
+
+# --------------------------------------------------------------------------------- lossless strip-packed targets
+def _mask_images(B, n, kind, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "discs":                                   # two-level
+        return ((rp.synth_target_masks(B, n, seed=seed).reshape(B, n, n) + 1.0) * 127.5).round().to(torch.uint8)
+    if kind == "antialiased":                             # flat inside / outside, intermediate values on the edge
+        ax = torch.linspace(-1, 1, n)
+        yy, xx = torch.meshgrid(ax, ax, indexing="ij")
+        c = torch.rand(B, 2, generator=g) - 0.5
+        r = torch.rand(B, 1, 1, generator=g) * 0.4 + 0.2
+        d = ((xx[None] - c[:, 0, None, None]) ** 2 + (yy[None] - c[:, 1, None, None]) ** 2).sqrt()
+        return (255.0 * torch.clamp((r - d) / (3.0 / n) + 0.5, 0, 1)).round().to(torch.uint8)
+    return torch.randint(0, 256, (B, n, n), generator=g, dtype=torch.uint8)       # noise: every strip raw
+
+
+@pytest.mark.parametrize("n", [256, 100, 37, 8, 5, 520])
+@pytest.mark.parametrize("kind", ["discs", "antialiased", "noise"])
+def test_strip_packed_targets_equal_uint8_targets(gg, cuda_device, n, kind):
+    """GG_TARGET_STRIPS (any 8-bit mask, two header bits per flat 8-pixel strip, 8 raw bytes otherwise) gives bit for bit
+    the loss and gradients of the same image as raw uint8, through the planned fused step and the host-buffer step;
+    the packed buffer is several times smaller for silhouette-like masks and never more than 7 % larger."""
+    from gaussigan_b200.host import HostSilhouetteStep, encode_target_strips
+    from gaussigan_b200.plan import SilhouetteLossStep
+    B, K = 3, 16
+    inp = rp.synth_inputs(B, K, seed=9 + n)
+    raw = _mask_images(B, n, kind, seed=n)
+    packed = encode_target_strips(raw, pin=False)
+    if kind != "noise" and n >= 100:
+        assert packed.numel() * 4 < raw.numel(), (packed.numel(), raw.numel())
+    assert packed.numel() <= raw.numel() * 1.07 + 16 + 4 * B * n + 16 * B * n
+    step = SilhouetteLossStep(B, K, n, cuda_device)
+    step.bind(inp["mus"].reshape(B, K, 3).contiguous().to(cuda_device), inp["sigma"].to(cuda_device),
+              *(inp[k].reshape(B).contiguous().to(cuda_device) for k in ("rotx", "roty", "rotz")))
+    ref = [t.clone() for t in step.loss_backward(raw.to(cuda_device))] + [step.loss_partials.clone()]
+    dev_packed = torch.empty((packed.numel() + 7) // 8, dtype=torch.int64, device=cuda_device).view(torch.uint8)
+    dev_packed[:packed.numel()] = packed.to(cuda_device)
+    out = [t.clone() for t in step.loss_backward(dev_packed, strips=True)] + [step.loss_partials.clone()]
+    for a, b_ in zip(out, ref):
+        assert torch.equal(a, b_)
+    # the host-buffer step
+    tgt_pm1 = (raw.float() / 127.5 - 1.0).reshape(B, n, n, 1)
+    res = []
+    for strips in (False, True):
+        host = HostSilhouetteStep(B, K, n, cuda_device, depth=2, target_strips=strips)
+        h = host.make_host_inputs(inp, tgt_pm1)
+        r = host.submit(h).wait()
+        res.append([r.loss_partials.clone(), r.dmus.clone(), r.dsigma.clone(), r.drot.clone()])
+        if strips and kind != "noise" and n >= 100:
+            assert host.h2d_bytes < 0.4 * (host.small_h2d_bytes + B * n * n)
+    for a, b_ in zip(res[0], res[1]):
+        assert torch.equal(a, b_)

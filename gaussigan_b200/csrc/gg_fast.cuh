@@ -12,9 +12,24 @@ namespace gg {
 #ifndef GG_MAX_SHARPNESS
 #define GG_MAX_SHARPNESS 512.0f
 #endif
-constexpr float kMaxSlope = 13.0f;     // largest |d(exponent)/d(pixel)| the recurrence is trusted with (range safety)
+#ifndef GG_MAX_SLOPE
+#define GG_MAX_SLOPE 10.0f
+#endif
+// largest |d(exponent)/d(pixel)| the strip forms are trusted with (range safety): the backward's Horner sums run in
+// units of the strip's first pixel, so they reach 2^(7 * 10) times the upstream gradient -- finite up to |Gbar| = 2^55
+constexpr float kMaxSlope = GG_MAX_SLOPE;
 constexpr float kMaxVisibleSlope = GG_MAX_VISIBLE_SLOPE;   // ... and where the Gaussian is visible (accuracy)
 constexpr float kMaxSharpness = GG_MAX_SHARPNESS;    // largest |nA| = a log2(e): bounds the error of stepping by exactly h
+
+__device__ __forceinline__ float exp2_small_f32(float delta) {   // exp2(delta), |delta| <= 0.125, ~half an ulp
+  const float z = delta * 0.693147180559945f;
+  float q = fmaf(z, 1.0f / 6.0f, 1.0f);
+  q = fmaf(z * 0.2f, q, 1.0f);
+  q = fmaf(z * 0.25f, q, 1.0f);
+  q = fmaf(z * (1.0f / 3.0f), q, 1.0f);
+  q = fmaf(z * 0.5f, q, 1.0f);
+  return fmaf(z, q, 1.0f);
+}
 
 // Per-Gaussian constants of the recurrence at grid step h:
 //   c0 = mu_x, mu_y, nA, -nr      c1 = nE, 2 nA h, nA h^2, c = exp2(2 nA h^2)      steep: evaluate directly instead
@@ -32,13 +47,7 @@ __device__ __forceinline__ void fast_consts_one(const float4 *__restrict__ gp, i
   const float delta = 2.0f * nAhh;
   float c;
   if (fabsf(delta) <= 0.125f) {
-    const float z = delta * 0.693147180559945f;
-    float q = fmaf(z, 1.0f / 6.0f, 1.0f);
-    q = fmaf(z * 0.2f, q, 1.0f);
-    q = fmaf(z * 0.25f, q, 1.0f);
-    q = fmaf(z * (1.0f / 3.0f), q, 1.0f);
-    q = fmaf(z * 0.5f, q, 1.0f);
-    c = fmaf(z, q, 1.0f);
+    c = exp2_small_f32(delta);
   } else {
     c = (float)exp2(2.0 * (double)lo.z * (double)h * (double)h);
   }
@@ -61,17 +70,31 @@ __device__ __forceinline__ void fast_consts_one(const float4 *__restrict__ gp, i
   c1 = make_float4(nE, 2.0f * nAh, nAhh, c);
 }
 
-// One CTA's Gaussians, 3 x float4 each in shared memory: c0, c1, (steep flag 0/1, 0, 0, 0)
+// One CTA's Gaussians in shared memory, float4 records:
+//   [0] c0 = mu_x, mu_y, nA, -nr
+//   [1] nE, 2 nA h, nA h^2, c            forward  (g_{j+1} = g_j r_j, r_0 = exp2(2 nA h t_0 + nA h^2), r_{j+1} = r_j c)
+//   [.] nE, 2 nA h, 13 nA h^2, 1/c       backward (Horner form, ratios from the far end of the strip:
+//                                                  r_6 = exp2(2 nA h t_0 + 13 nA h^2), r_{j-1} = r_j / c)
+// The last word is 0 for a guarded Gaussian (c and 1/c are positive otherwise): evaluate directly.
+// WHICH = 1: forward record only (2 float4 per Gaussian), 2: backward only (2), 3: both (3: c0, forward, backward).
+template <int WHICH>
 __device__ __forceinline__ void stage_fast_consts(const float *__restrict__ gparams, int kn, float h, float x_lo,
                                                   float x_hi, float y_lo, float y_hi, float4 *sc) {
+  constexpr int REC = WHICH == 3 ? 3 : 2;
   const float4 *gp = reinterpret_cast<const float4 *>(gparams);
   for (int k = threadIdx.x; k < kn; k += blockDim.x) {
     float4 c0, c1;
     bool steep;
     fast_consts_one(gp, k, h, x_lo, x_hi, y_lo, y_hi, c0, c1, steep);
-    sc[3 * k + 0] = c0;
-    sc[3 * k + 1] = c1;
-    sc[3 * k + 2] = make_float4(steep ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    sc[REC * k] = c0;
+    if (WHICH & 1) sc[REC * k + 1] = make_float4(c1.x, c1.y, c1.z, steep ? 0.f : c1.w);
+    if (WHICH & 2) {
+      const float delta = -2.0f * c1.z;
+      float ci = 0.f;
+      if (!steep)
+        ci = fabsf(delta) <= 0.125f ? exp2_small_f32(delta) : (float)exp2(-2.0 * (double)c0.z * (double)h * (double)h);
+      sc[REC * k + (WHICH == 3 ? 2 : 1)] = make_float4(c1.x, c1.y, __fmul_rn(13.0f, c1.z), ci);
+    }
   }
 }
 

@@ -42,30 +42,39 @@ namespace {
 #define GG_BWD_KUNROLL 1      // Gaussians processed per main-loop iteration of the backward (ILP vs registers)
 #endif
 #ifndef GG_BWD_MINBLOCKS
-#define GG_BWD_MINBLOCKS 4    // resident 256-thread CTAs per SM the backward is compiled for
+#define GG_BWD_MINBLOCKS 3    // resident 256-thread CTAs per SM the backward is compiled for
 #endif
 #ifndef GG_FWD_KUNROLL
 #define GG_FWD_KUNROLL 0      // 0 = leave it to the compiler
 #endif
 constexpr int kBwdKUnroll = GG_BWD_KUNROLL;
 
-// One Gaussian on one strip of a ROW PAIR: lanes of every f32x2 are the two rows, G[j] is pixel j of the strip.
+// One Gaussian on one strip of a ROW PAIR: lanes of every f32x2 are the two rows.
 //   dy = y - mu_y;  t0 = (x_0 - mu_x) - nr dy;  e = nE dy^2   (per lane)
+// Guarded (narrow or very distant) Gaussian: one exponential per pixel on the reference's own float32 grid coordinates
+// (not x_0 + j h: at this sharpness the 1e-7 non-uniformity of the grid matters), exactly as gg_splat.cu does.
+__device__ __forceinline__ void eval_strip_direct(const float4 &c0, f32x2 e, f32x2 dy, int col0, float h, f32x2 (&G)[8]) {
+  const f32x2 nA = bc(c0.z);
+  const f32x2 sh = fma2(bc(-c0.w), dy, bc(c0.x));          // mu_x + nr dy
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const f32x2 t = sub2(bc(grid_coord(col0 + j, h)), sh);
+    G[j] = ex2_2(fma2(nA, mul2(t, t), e));
+  }
+}
+
+// Forward: the 8 values of a strip by the recurrence g_{j+1} = g_j r_j, r_{j+1} = r_j c: 2 exponentials and 13 multiplies.
+// (The closed form g_j = g_0 rho^j Q_j with per-Gaussian tables Q_j = exp2(nA (j h)^2) needs 7 multiplies and 7
+// multiply-adds into the accumulators but two more 128-bit shared-memory loads per Gaussian: measured 12.66 us against
+// 12.99 us at B = 64, K = 16, 256 x 256 -- not kept, the fused-loss kernel has no shared memory left for the tables and
+// its silhouette has to equal this kernel's bit for bit.)
 __device__ __forceinline__ void eval_strip(const float4 &c0, const float4 &c1, bool steep, f32x2 t0, f32x2 e, f32x2 dy,
                                            int col0, float h, f32x2 (&G)[8]) {
-  const f32x2 nA = bc(c0.z);
   if (steep) {
-    // narrow or very distant Gaussian: one exponential per pixel on the reference's own float32 grid coordinates
-    // (not x_0 + j h: at this sharpness the 1e-7 non-uniformity of the grid matters), exactly as gg_splat.cu does
-    const f32x2 sh = fma2(bc(-c0.w), dy, bc(c0.x));          // mu_x + nr dy
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const f32x2 t = sub2(bc(grid_coord(col0 + j, h)), sh);
-      G[j] = ex2_2(fma2(nA, mul2(t, t), e));
-    }
+    eval_strip_direct(c0, e, dy, col0, h, G);
     return;
   }
-  f32x2 g = ex2_2(fma2(mul2(nA, t0), t0, e));
+  f32x2 g = ex2_2(fma2(mul2(bc(c0.z), t0), t0, e));
   f32x2 r = ex2_2(fma2(bc(c1.y), t0, bc(c1.z)));
   const f32x2 c = bc(c1.w);
 #pragma unroll
@@ -74,6 +83,33 @@ __device__ __forceinline__ void eval_strip(const float4 &c0, const float4 &c1, b
     if (j < 7) g = mul2(g, r);
     if (j < 6) r = mul2(r, c);
   }
+}
+
+// Backward: the three strip sums  S0 = sum W_j g_j,  S1 = sum xi_j W_j g_j,  S2 = sum xi_j^2 W_j g_j  (W = upstream
+// gradient, xi_j = x_j - x_0 on the reference's float32 grid) as three Horner evaluations in the ratios r_j = g_{j+1}/g_j:
+//   S = g_0 (C_0 + r_0 (C_1 + r_1 (C_2 + ... r_6 C_7)))      with C_j = W_j, xi_j W_j, xi_j^2 W_j
+// The coefficients do not depend on the Gaussian: they are formed once per thread.  Per pixel and Gaussian this is one
+// multiply for the ratio and three multiply-adds (the term-by-term form needs g_j, u_j = g_j W_j and three sums: six).
+__device__ __forceinline__ void horner_strip(const float4 &c0, const float4 &c1, f32x2 t0, f32x2 e,
+                                             const f32x2 (&W)[8], const f32x2 (&A)[8], const f32x2 (&Bc)[8],
+                                             f32x2 &S0, f32x2 &S1, f32x2 &S2) {
+  const f32x2 g0 = ex2_2(fma2(mul2(bc(c0.z), t0), t0, e));
+  f32x2 r = ex2_2(fma2(bc(c1.y), t0, bc(c1.z)));        // r_6
+  const f32x2 ci = bc(c1.w);
+  f32x2 T = W[7], U = A[7], V = Bc[7];
+#pragma unroll
+  for (int m = 6; m >= 1; --m) {
+    T = fma2(r, T, W[m]);
+    U = fma2(r, U, A[m]);
+    V = fma2(r, V, Bc[m]);
+    r = mul2(r, ci);
+  }
+  T = fma2(r, T, W[0]);
+  U = mul2(r, U);         // xi_0 = 0
+  V = mul2(r, V);
+  S0 = mul2(g0, T);
+  S1 = mul2(g0, U);
+  S2 = mul2(g0, V);
 }
 
 __device__ __forceinline__ void store8c(float *rowp, int col0, int n, const float *f) {
@@ -116,7 +152,7 @@ __device__ __forceinline__ void tile_extent(const ScaleDesc &s, int tile_local, 
 // NP = row pairs per thread (rows per thread = 2 NP, spaced s.rpp apart)
 template <int NP, int NW>
 __global__ void __launch_bounds__(NW * 32) splat_fwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
-  extern __shared__ float4 sc[];   // [K][3]
+  extern __shared__ float4 sc[];   // [K][2]: c0, forward record
   const int b = blockIdx.x / a.T;
   const int tile = blockIdx.x - b * a.T;
   const ScaleDesc &s = a.sc[find_scale(a, tile)];
@@ -136,7 +172,7 @@ __global__ void __launch_bounds__(NW * 32) splat_fwd_mask_fast_kernel(const __gr
     unpack2(y[NP - 1], ya, yb);
     pdl_enter_after(pos.colA, pos.row0, x0 + x_hi, ya + yb + y_lo);
   }
-  stage_fast_consts(a.params + (size_t)b * K * GG_PARAM_STRIDE, K, h, x_lo, x_hi, y_lo, y_hi, sc);
+  stage_fast_consts<1>(a.params + (size_t)b * K * GG_PARAM_STRIDE, K, h, x_lo, x_hi, y_lo, y_hi, sc);
   __syncthreads();
   if (!pos.valid) return;
 
@@ -147,8 +183,8 @@ __global__ void __launch_bounds__(NW * 32) splat_fwd_mask_fast_kernel(const __gr
     for (int j = 0; j < 8; ++j) acc[p][j] = pack2(0.f, 0.f);
 
   for (int k = 0; k < K; ++k) {
-    const float4 c0 = sc[3 * k], c1 = sc[3 * k + 1];
-    const bool steep = sc[3 * k + 2].x != 0.f;
+    const float4 c0 = sc[2 * k], c1 = sc[2 * k + 1];
+    const bool steep = c1.w == 0.f;
     const float xm = x0 - c0.x;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -182,10 +218,12 @@ __global__ void __launch_bounds__(NW * 32) splat_fwd_mask_fast_kernel(const __gr
 //         pixels, where a guarded Gaussian can be far sub-pixel; costs 4 % of the kernel, so not at the large scales)
 template <int NP, bool FUSED, int NW, bool CENTRE>
 __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW : 1) splat_bwd_mask_fast_kernel(const __grid_constant__ SplatArgs a) {
-  __shared__ float4 sc[kKBlock * 3];
+  constexpr int REC = FUSED ? 3 : 2;   // c0, [forward record,] backward record
+  __shared__ float4 sc[kKBlock * REC];
   __shared__ __align__(16) float stage[NW][kStageCols][kStagePad];
   __shared__ float warpsum[NW][kKBlock * GG_MOMENTS];
-  __shared__ float lut[FUSED ? 256 : 1];
+  float *lut = &stage[0][0][0];   // FUSED: byte -> target value table; dead before the transpose buffer is first written
+  static_assert(NW * kStageCols * kStagePad >= 256, "lut");
 
   const int b = blockIdx.x / a.T;
   const int tile = blockIdx.x - b * a.T;
@@ -226,7 +264,7 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
       if (rv[r]) load8c(s.mask + ((size_t)b * n + row[r]) * n, pos.colA, n, gm[r]);
     }
   }
-  stage_fast_consts(a.params + ((size_t)b * K + k0) * GG_PARAM_STRIDE, kn, h, x_lo, x_hi, y_lo, y_hi, sc);
+  stage_fast_consts<FUSED ? 3 : 2>(a.params + ((size_t)b * K + k0) * GG_PARAM_STRIDE, kn, h, x_lo, x_hi, y_lo, y_hi, sc);
   if (FUSED && (a.target_kind == GG_TARGET_U8 || a.target_kind == GG_TARGET_STRIPS)) {
     // 0.5 * ((raw / 127.5 - 1) + 1), op by op in float32 as the reference (:672, :787): one division per
     // thread instead of one per pixel
@@ -244,7 +282,7 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
       for (int j = 0; j < 8; ++j) acc[p][j] = pack2(0.f, 0.f);
     for (int kk = 0; kk < kn; ++kk) {
       const float4 c0 = sc[3 * kk], c1 = sc[3 * kk + 1];
-      const bool steep = sc[3 * kk + 2].x != 0.f;
+      const bool steep = c1.w == 0.f;
       const float xm = x0 - c0.x;
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
@@ -342,23 +380,25 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
     }
     __syncthreads();
   }
-  // the upstream gradient of a pixel is shared by all Gaussians: packed once per row pair
-  f32x2 W0[NP][8];
-  float xi1[8], xi2[8];
+  // the upstream gradient of a pixel is shared by all Gaussians, and so are its products with the pixel's offset from
+  // the strip origin on the reference's float32 grid (j h to ~1e-7): the Horner coefficients, packed once per row pair
+  f32x2 W0[NP][8], W1[NP][8], W2[NP][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {   // offsets of the strip's pixels on the reference's float32 grid (j h to ~1e-7)
-    xi1[j] = pin(grid_coord(pos.colA + j, h) - x0);
-    xi2[j] = pin(xi1[j] * xi1[j]);
+  for (int j = 0; j < 8; ++j) {
+    const float xi1 = grid_coord(pos.colA + j, h) - x0;
+    const float xi2 = xi1 * xi1;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      W0[p][j] = pack2(gm[2 * p][j], gm[2 * p + 1][j]);
+      W1[p][j] = mul2(W0[p][j], bc(xi1));
+      W2[p][j] = mul2(W0[p][j], bc(xi2));
+    }
   }
-#pragma unroll
-  for (int p = 0; p < NP; ++p)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) W0[p][j] = pack2(gm[2 * p][j], gm[2 * p + 1][j]);
 
 #pragma unroll kBwdKUnroll
   for (int kk = 0; kk < kn; ++kk) {
-    const float4 c0 = sc[3 * kk], c1 = sc[3 * kk + 1];
-    const bool steep = sc[3 * kk + 2].x != 0.f;
+    const float4 c0 = sc[REC * kk], c1 = sc[REC * kk + REC - 1];
+    const bool steep = c1.w == 0.f;
     const float xm = x0 - c0.x;
     f32x2 P20 = pack2(0.f, 0.f), P11 = P20, P02 = P20, P10 = P20, P01 = P20;
 #pragma unroll
@@ -366,40 +406,46 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
       const f32x2 dy = sub2(y[p], bc(c0.y));
       const f32x2 t0 = fma2(bc(c0.w), dy, bc(xm));
       const f32x2 e = mul2(mul2(bc(c1.x), dy), dy);
-      f32x2 G[8];
-      eval_strip(c0, c1, steep, t0, e, dy, pos.colA, h, G);
-      f32x2 S0 = mul2(G[0], W0[p][0]), m1, m2;
-      if (!(CENTRE && steep)) {
-        f32x2 u1 = mul2(G[1], W0[p][1]);
-        f32x2 S1 = mul2(u1, bc(xi1[1])), S2 = mul2(u1, bc(xi2[1]));
-        S0 = add2(S0, u1);
-#pragma unroll
-        for (int j = 2; j < 8; ++j) {
-          const f32x2 u = mul2(G[j], W0[p][j]);
-          S0 = add2(S0, u);
-          S1 = fma2(u, bc(xi1[j]), S1);
-          S2 = fma2(u, bc(xi2[j]), S2);
-        }
+      f32x2 S0, m1, m2;
+      if (!steep) {
+        f32x2 S1, S2;
+        horner_strip(c0, c1, t0, e, W0[p], W1[p], W2[p], S0, S1, S2);
         // strip-local moments (about x_0) -> moments of t = t0 + xi
         m1 = fma2(t0, S0, S1);
         m2 = fma2(t0, add2(S1, m1), S2);
       } else {
-        // CENTRE kernels, guarded Gaussian (a needle much narrower than the strip): sums about its own centre line,
-        // with the t of the direct evaluation -- re-centring from x_0 cancels (strip length / sigma)^2 of the second
-        // moment, which only matters on coarse grids, where such Gaussians are sub-pixel
-        const f32x2 sh = fma2(bc(-c0.w), dy, bc(c0.x));
-        f32x2 tj = sub2(bc(x0), sh);
-        f32x2 v = mul2(S0, tj);
-        m1 = v;
-        m2 = mul2(v, tj);
+        f32x2 G[8];
+        eval_strip_direct(c0, e, dy, pos.colA, h, G);
+        if (!CENTRE) {
+          S0 = mul2(G[0], W0[p][0]);
+          f32x2 S1 = mul2(G[1], W1[p][1]), S2 = mul2(G[1], W2[p][1]);
 #pragma unroll
-        for (int j = 1; j < 8; ++j) {
-          const f32x2 u = mul2(G[j], W0[p][j]);
-          tj = sub2(bc(grid_coord(pos.colA + j, h)), sh);
-          v = mul2(u, tj);
-          S0 = add2(S0, u);
-          m1 = add2(m1, v);
-          m2 = fma2(v, tj, m2);
+          for (int j = 1; j < 8; ++j) {
+            S0 = fma2(G[j], W0[p][j], S0);
+            if (j > 1) {
+              S1 = fma2(G[j], W1[p][j], S1);
+              S2 = fma2(G[j], W2[p][j], S2);
+            }
+          }
+          m1 = fma2(t0, S0, S1);
+          m2 = fma2(t0, add2(S1, m1), S2);
+        } else {
+          // CENTRE kernels, guarded Gaussian (a needle much narrower than the strip): sums about its own centre line,
+          // with the t of the direct evaluation -- re-centring from x_0 cancels (strip length / sigma)^2 of the second
+          // moment, which only matters on coarse grids, where such Gaussians are sub-pixel
+          const f32x2 sh = fma2(bc(-c0.w), dy, bc(c0.x));
+          S0 = pack2(0.f, 0.f);
+          m1 = S0;
+          m2 = S0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const f32x2 u = mul2(G[j], W0[p][j]);
+            const f32x2 tj = sub2(bc(grid_coord(pos.colA + j, h)), sh);
+            const f32x2 v = mul2(u, tj);
+            S0 = add2(S0, u);
+            m1 = add2(m1, v);
+            m2 = fma2(v, tj, m2);
+          }
         }
       }
       // ... then the row weights
@@ -446,7 +492,7 @@ __global__ void __launch_bounds__(NW * 32, NP == 1 ? (GG_BWD_MINBLOCKS * 8) / NW
 
 // ====================================================================================== launchers
 // rpt = rows per thread of the plan (2 or 4); the CTA size comes from the plan's geometry (sc[0].cta)
-// K * 48 bytes of staged constants exceed the 48 KB default above K = 1024 (the C ABI accepts K <= 1536): opt in
+// K * 32 bytes of staged constants exceed the 48 KB default above K = 1536 (the C ABI's limit): kept for safety (the C ABI accepts K <= 1536): opt in
 template <typename Kern>
 static cudaError_t launch_fwd_fast_one(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const SplatArgs &a) {
   if (smem > 48 * 1024) {
@@ -459,7 +505,7 @@ static cudaError_t launch_fwd_fast_one(Kern kern, dim3 grid, dim3 block, size_t 
 
 cudaError_t launch_fwd_mask_fast(const SplatArgs &a, int B, int rpt, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)B * a.T));
-  size_t smem = (size_t)a.K * 3 * sizeof(float4);
+  size_t smem = (size_t)a.K * 2 * sizeof(float4);
   const int cta = a.sc[0].cta;
   if (rpt == 4) return launch_fwd_fast_one(splat_fwd_mask_fast_kernel<2, 8>, grid, dim3(256), smem, st, a);
   if (cta == 128) return launch_fwd_fast_one(splat_fwd_mask_fast_kernel<1, 4>, grid, dim3(128), smem, st, a);

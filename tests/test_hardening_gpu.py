@@ -64,7 +64,7 @@ def test_pointwise_allclose_statistics_at_config2(gg, cuda_device, restore_modes
 def _guard_case(n, nA_abs, tmax_pixels, shear, B=1):
     """2-D Gaussians (mu2d, sigma2d) with a prescribed sharpness |nA| = a log2(e) and centre offset, one per batch
     element, placed so that the strip recurrence's three criteria (gg_fast.cuh: |nA| <= 512, visible slope
-    2 h sqrt(14 |nA|) <= 3, range slope |2 nA h| (tmax + 8 h) <= 13) sit just inside / just outside."""
+    2 h sqrt(14 |nA|) <= 3, range slope |2 nA h| (tmax + 8 h) <= 10) sit just inside / just outside."""
     h = 2.0 / (n - 1)
     a = nA_abs / LOG2E                       # conic entry P00
     c = a * 0.05 + 0.3                       # a broad axis along y
@@ -114,16 +114,16 @@ def test_guard_boundary_visible_slope(gg, cuda_device, n, eps):
 @pytest.mark.parametrize("n", [256, 128, 64, 24, 16, 13])
 @pytest.mark.parametrize("eps", [-1e-2, 1e-2])
 def test_guard_boundary_range_slope(gg, cuda_device, n, eps):
-    """|2 nA h| (tmax + 8 h) = 13 (1 +- eps): criterion (i), range safety, with the centre far off the tile."""
+    """|2 nA h| (tmax + 8 h) = 10 (1 +- eps): criterion (i), range safety, with the centre far off the tile."""
     h = 2.0 / (n - 1)
     nA = min(0.5 * ((3.0 / (2 * h)) ** 2 / 14.0), 400.0)              # comfortably inside (ii) and (iii)
-    tmax = 13.0 * (1 + eps) / abs(2 * nA * h) - 8 * h                  # distance of the far tile corner from the centre
+    tmax = 10.0 * (1 + eps) / abs(2 * nA * h) - 8 * h                  # distance of the far tile corner from the centre
     # centre to the LEFT of the frame so that the far (right) edge is tmax away: mu_x = 1 - tmax (may be off-screen)
     a = nA / LOG2E
     P = torch.tensor([[a, 0.0], [0.0, 0.4]], dtype=torch.float64)
     sg = torch.linalg.inv(P).reshape(1, 1, 2, 2)
     mu = torch.tensor([[[1.0 - tmax, -0.2]]], dtype=torch.float64)
-    _check_2d(gg, cuda_device, mu, sg, n, f"range slope 13(1{eps:+g}) n={n}")
+    _check_2d(gg, cuda_device, mu, sg, n, f"range slope 10(1{eps:+g}) n={n}")
 
 
 @pytest.mark.parametrize("n", list(range(13, 25)))

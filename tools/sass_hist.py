@@ -3,7 +3,7 @@ backward-branch loop that contains MUFU.EX2), from the shipped library with cuob
     python tools/sass_hist.py > profiles/r2_sass_hot_kernels.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "gaussigan_b200", "lib", "libgaussigan_sm100.so")
+LIB = os.environ.get("GAUSSIGAN_LIB") or os.path.join(ROOT, "gaussigan_b200", "lib", "libgaussigan_sm100.so")
 WANT = [("splat_bwd_mask_fast_kernel<1,false,8,false>", "_ZN2gg26splat_bwd_mask_fast_kernelILi1ELb0ELi8ELb0EEEvNS_9SplatArgsE"),
         ("splat_fwd_mask_fast_kernel<1,8>", "_ZN2gg26splat_fwd_mask_fast_kernelILi1ELi8EEEvNS_9SplatArgsE"),
         ("splat_bwd_mask_fast_kernel<1,true,8,false> (fused loss)", "_ZN2gg26splat_bwd_mask_fast_kernelILi1ELb1ELi8ELb0EEEvNS_9SplatArgsE")]

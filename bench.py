@@ -358,12 +358,12 @@ def run_gpu(args):
         with open(tpath) as fh:
             traffic = json.load(fh).get("splat_bwd_mask_dram_bytes_per_launch")
     # executed FP32-pipe work of the forward-differenced kernels, counted in their SASS hot loops
-    # (profiles/r2_sass_hot_kernels.txt, tools/sass_hist.py): backward 54 packed + 8 scalar FP32-pipe instructions per
-    # (Gaussian, 2 rows x 8 px) = 7.25 lane-ops per (pixel, Gaussian); forward 28 packed + 1 scalar = 3.56.  The pipe
-    # retires 128 lane-ops/clk/SM.
-    EXEC_BWD, EXEC_FWD = 7.25, 3.56
+    # (profiles/r2_sass_hot_kernels.txt, tools/sass_hist.py): backward (Horner strip sums) 43 packed + 6 scalar
+    # FP32-pipe instructions per (Gaussian, 2 rows x 8 px) = 5.75 lane-ops per (pixel, Gaussian); forward 28 packed +
+    # 1 scalar = 3.56.  The pipe retires 128 lane-ops/clk/SM.
+    EXEC_BWD, EXEC_FWD = 5.75, 3.56
     roofline = {
-        "kernel": "gg::splat_bwd_mask_fast_kernel (mask gradient -> per-Gaussian moments, forward-differenced strips)",
+        "kernel": "gg::splat_bwd_mask_fast_kernel (mask gradient -> per-Gaussian moments, Horner sums over forward-differenced strips)",
         "bound": "fp32_pipe",
         "achieved": ach / 1e12, "peak": issue_peak / 1e12,
         "unit": "T lane-slots/s (17 algorithmic issue slots per pixel-Gaussian, SURVEY.md 8d)",
@@ -371,8 +371,9 @@ def run_gpu(args):
         "us_per_launch_note": "average over a CUDA graph of 64 back-to-back launches on rotating buffers, chained by "
                               "programmatic dependent launch (the next launch's prologue overlaps this one's tail)",
         "peak_source": f"148 SMs x 128 FP32 lanes x sm_max_mhz ({peaks['source']} MEASURED_PEAKS.json); no tensor cores: not a contraction",
-        "note": "frac > 1 is expected: the kernel forward-differences the Gaussians along each strip, so it executes "
-                "7.25 FP32 lane-ops + 0.25 MUFU.EX2 per pixel-Gaussian instead of the 17 slots of the algorithmic count",
+        "note": "frac > 1 is expected: the kernel forward-differences the Gaussians along each strip and sums them in "
+                "Horner form, so it executes 5.75 FP32 lane-ops + 0.25 MUFU.EX2 per pixel-Gaussian instead of the 17 "
+                "slots of the algorithmic count",
         "executed": {"fp32_lane_ops_per_pixel_gaussian": EXEC_BWD,
                      "frac_of_fp32_pipe_peak": EXEC_BWD * pxk / (us_bwd * 1e-6) / issue_peak,
                      "forward_fp32_lane_ops_per_pixel_gaussian": EXEC_FWD,

@@ -7,7 +7,7 @@
 //     a_j = nA t_j^2 + e,   t_j = t_0 + j h          (log2 of the Gaussian at pixel j of the strip)
 //     g_{j+1} = g_j r_j,    r_j = exp2(nA h (2 t_j + h)),    r_{j+1} = r_j c,    c = exp2(2 nA h^2)
 // a strip of 8 pixels needs TWO exponentials (g_0, r_0) instead of eight; c is computed once per
-// (CTA, Gaussian) in float64.  MUFU work drops 4x and the kernels become FP32-pipe bound.
+// (CTA, Gaussian) to half an ulp (gg_fast.cuh).  MUFU work drops 4x and the kernels become FP32-pipe bound.
 //
 // Lanes.  A thread owns one 8-pixel strip of TWO rows (row, row + rpp).  Every FP32x2 register holds the
 // same quantity for the two rows, so the whole per-(Gaussian,row) set-up (dy, t0, the two exponents), the
@@ -16,19 +16,28 @@
 // Accuracy (tests/studies/recurrence_accuracy.py, float32 emulation against the float64 oracle, reference
 // activation ranges): silhouette max|err|/max = 8e-7 (direct form: 1e-7; tolerance 1e-5).
 //
-// Guard.  The recurrence is only used where the per-pixel change of the exponent is small,
-// |nA h (2 t + h)| <= 13 over the whole tile: then nothing can overflow and a strip whose first pixel
-// underflows (g_0 < 2^-126) stays below 2^-35 everywhere; and <= 3 wherever the Gaussian is visible (the rounding
+// Guard.  The strip forms are only used where the per-pixel change of the exponent is small,
+// |nA h (2 t + h)| <= 10 over the whole tile: then nothing can overflow and a strip whose first pixel
+// underflows (g_0 < 2^-126) stays below 2^-56 everywhere; and <= 3 wherever the Gaussian is visible (the rounding
 // error of the ratio grows with its exponent; the reference's range stays below 0.8); and only for |nA| <= 512,
 // because the recurrence steps by exactly h while the reference's float32 pixel grid deviates from uniform by up to
 // 1.8e-7, an error that grows like sqrt(|nA|) (the reference's range ends near 210).  The test is made once per
 // (CTA, Gaussian) from the tile's corners (t is linear in the pixel position); Gaussians that fail it (narrower than
 // ~2 pixels, or very distant) are evaluated directly, one exponential per pixel on the true grid, by the whole CTA.
 //
-// Backward.  Strip sums are taken about the strip's first pixel, u = g Gbar; S0 += u; S1 += u xi; S2 += u xi^2 with
-// xi_j = x_j - x_0 on the reference's grid (four packed instructions per pixel pair, only Gbar in registers), and
-// re-centred to the sheared coordinate t = t0 + xi per row (CENTRE kernels, used for launches with a scale below 64
-// pixels: guarded Gaussians are summed about their own centre line instead, see the kernel).
+// Backward.  Per strip and Gaussian three sums about the strip's first pixel are needed,
+//     S0 = sum_j W_j g_j,   S1 = sum_j xi_j W_j g_j,   S2 = sum_j xi_j^2 W_j g_j       (W = dL/dmask, xi_j = x_j - x_0
+// on the reference's float32 grid), re-centred afterwards to the sheared coordinate t = t0 + xi per row.  Term by term
+// that is g_j (2 multiplies for the two recurrences), u_j = g_j W_j and three multiply-adds: 6 lane-ops per pixel and
+// Gaussian (round 1).  Round 2 evaluates each sum in HORNER form in the ratios r_j = g_{j+1} / g_j,
+//     S = g_0 (C_0 + r_0 (C_1 + r_1 (C_2 + ... + r_6 C_7)))         C_j = W_j,  xi_j W_j,  xi_j^2 W_j
+// whose coefficients do not depend on the Gaussian and are formed once per thread: one multiply for the ratio
+// (r_{j-1} = r_j / c, started from r_6 = exp2(2 nA h t_0 + 13 nA h^2)) and three multiply-adds, 4 lane-ops.  The 24
+// coefficient pairs cost registers: 80 per thread, 3 CTAs per SM instead of 4 at 64.  Measured at B = 64, K = 16,
+// 256 x 256: 24.3 -> 22.4 us per launch; SASS 54 -> 43 packed FP32x2 instructions per (Gaussian, 2 rows x 8 pixels).
+// The Horner sums run in units of g_0, so they reach 2^(7 x 10) times the upstream gradient: finite for |W| < 2^55.
+// Guarded Gaussians are summed term by term from the direct values (CENTRE kernels, used for launches with a scale
+// below 64 pixels: about their own centre line instead of the strip origin, see the kernel).
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
 #include "gg_fast.cuh"

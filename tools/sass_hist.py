@@ -63,6 +63,22 @@ for name, fn in WANT:
                 y = next((z for z in range(x - 1, -1, -1) if re.search(r"@!?P\d\s+BRA\s+0x", body[z][1])), None)
                 if y is not None and sum("MUFU.EX2" in q for _, q in body[y:x]) >= 8:
                     drop.update(b[0] for b in body[y + 1:x + 1])
+        # second layout (Horner backward): `@!P BRA T` jumps forward to the direct block at T, which sits behind the
+        # unguarded block; that one ends with `BRA J` right before T, and the direct block is [T, J)
+        baddr = {a: x for x, (a, _) in enumerate(body)}
+        for x, (a, t) in enumerate(body):
+            m = re.search(r"@!?P\d\s+BRA\s+0x([0-9a-f]+)", t)
+            if not m:
+                continue
+            T = int(m.group(1), 16)
+            if T not in baddr or baddr[T] <= x or baddr[T] == 0:
+                continue
+            m2 = re.match(r"BRA\s+0x([0-9a-f]+)", body[baddr[T] - 1][1])
+            if not m2 or int(m2.group(1), 16) not in baddr:
+                continue
+            J = baddr[int(m2.group(1), 16)]
+            if J > baddr[T] and sum("MUFU.EX2" in q for _, q in body[baddr[T]:J]) >= 8:
+                drop.update(b[0] for b in body[baddr[T]:J])
         path = [b for b in body if b[0] not in drop]
         ngauss = len(guards)
         flush_lo = next((a for a, t in path if t.startswith("BSSY")), None)

@@ -71,19 +71,23 @@ static T *mapped_or_null(T *host, size_t bytes) {
   return reinterpret_cast<T *>(const_cast<void *>(static_cast<const void *>(at.devicePointer)));
 }
 
-static bool zero_copy_enabled() {
-  static const bool on = [] {
-    const char *v = std::getenv("GG_ZEROCOPY");
-    return !(v && v[0] == '0');
-  }();
-  return on;
+// GG_ZEROCOPY: which of the small arrays the projection kernels access in place in pinned host memory --
+// "out" the gradients (default), "in" the Gaussians and the camera, "1" both, "0" none.  Measured at batch 64, K = 16,
+// 256 x 256, six steps in flight (tools/e2e_host_cost.py): out 34.8 us per step, none 35.1, in 42.0, both 44.0 -- reads
+// over PCIe sit on the projection's dependent chain, posted writes do not.
+static int zero_copy_mode() {   // read on every call (a getenv): tests and callers may switch it between steps
+  const char *v = std::getenv("GG_ZEROCOPY");
+  if (!v || v[0] == 'o') return 2;
+  if (v[0] == '0') return 0;
+  if (v[0] == 'i') return 1;
+  return 3;
 }
 
 }  // namespace gg
 
 using namespace gg::api;
 using gg::mapped_or_null;
-using gg::zero_copy_enabled;
+using gg::zero_copy_mode;
 
 extern "C" {
 
@@ -188,16 +192,20 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
     if (e__ != cudaSuccess) return cuda_fail(e__, what);    \
   } while (0)
   const size_t px = (size_t)B * n * n;
-  // The Gaussians, the camera and the gradients are ~90 KB per step in nine arrays: when the caller's buffers are
-  // pinned (cudaHostAlloc / cudaHostRegister, device-accessible through UVA) the two projection kernels read and
-  // write them in place over PCIe and the nine small copies disappear from the copy-engine queues; only the target
-  // mask (the bulk of the bytes) goes through the DMA engine.  Pageable buffers take the copy path.
+  // The Gaussians, the camera and the gradients are ~90 KB per step in nine arrays.  Pinned buffers (cudaHostAlloc /
+  // cudaHostRegister, device-accessible through UVA) can be accessed by the two projection kernels in place over PCIe
+  // (zero_copy_mode above); everything else, and every pageable buffer, takes the copy path.
   const size_t nbk = (size_t)B * K;
-  const float *k_mus = mapped_or_null(mus_host, nbk * 3 * 4);
-  const double *k_sigma = mapped_or_null(sigma_host, nbk * 9 * 8);
-  const float *k_rx = mapped_or_null(rotx_host, (size_t)B * 4), *k_ry = mapped_or_null(roty_host, (size_t)B * 4),
-              *k_rz = mapped_or_null(rotz_host, (size_t)B * 4);
-  const bool in_place_in = zero_copy_enabled() && k_mus && k_sigma && k_rx && k_ry && k_rz;
+  const float *k_mus = nullptr, *k_rx = nullptr, *k_ry = nullptr, *k_rz = nullptr;
+  const double *k_sigma = nullptr;
+  if (zero_copy_mode() & 1) {
+    k_mus = mapped_or_null(mus_host, nbk * 3 * 4);
+    k_sigma = mapped_or_null(sigma_host, nbk * 9 * 8);
+    k_rx = mapped_or_null(rotx_host, (size_t)B * 4);
+    k_ry = mapped_or_null(roty_host, (size_t)B * 4);
+    k_rz = mapped_or_null(rotz_host, (size_t)B * 4);
+  }
+  const bool in_place_in = k_mus && k_sigma && k_rx && k_ry && k_rz;
   if (!in_place_in) {
     GG_TRY(cudaMemcpyAsync(d_mus, mus_host, (size_t)B * K * 3 * 4, cudaMemcpyHostToDevice, st), "H2D mus");
     GG_TRY(cudaMemcpyAsync(d_sigma, sigma_host, (size_t)B * K * 9 * 8, cudaMemcpyHostToDevice, st), "H2D sigma");
@@ -237,9 +245,14 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
     const float *gmasks[1] = {d_gmask};
     GG_TRY(gg::launch_splat_bwd(d_params, B, K, 1, sizes, nullptr, gmasks, GG_LAYOUT_NHWC, d_part, L.T, st), "splat_bwd");
   }
-  float *k_dmus = mapped_or_null(dmus_host, nbk * 3 * 4), *k_drot = mapped_or_null(drot_host, (size_t)B * 3 * 4);
-  double *k_dsig = mapped_or_null(dsigma_host, nbk * 9 * 8);
-  const bool in_place_out = zero_copy_enabled() && k_dmus && k_dsig && k_drot;
+  float *k_dmus = nullptr, *k_drot = nullptr;
+  double *k_dsig = nullptr;
+  if (zero_copy_mode() & 2) {
+    k_dmus = mapped_or_null(dmus_host, nbk * 3 * 4);
+    k_drot = mapped_or_null(drot_host, (size_t)B * 3 * 4);
+    k_dsig = mapped_or_null(dsigma_host, nbk * 9 * 8);
+  }
+  const bool in_place_out = k_dmus && k_dsig && k_drot;
   GG_TRY(gg::launch_project_bwd(k_mus, k_sigma, 1, k_rx, k_ry, k_rz, tx, ty, tz, focal, B, K, d_part, L.T, nullptr,
                                 nullptr, in_place_out ? k_dmus : d_dmus, in_place_out ? k_dsig : d_dsig,
                                 in_place_out ? k_drot : d_drot, st), "project_bwd");

@@ -383,7 +383,9 @@ __host__ __device__ inline size_t fast_wsum_bytes(int K) {
 }
 
 // NP = lane pairs per thread (2: a quad of Gaussians, K % 4 == 0; 1: a pair); KU = units per pixel (<= 32)
-template <int NP, bool WITH_GMASK>
+// KODD (pair units only): K is odd -- decided at compile time, the even-K pair kernel (the reference's K = 6) carries no
+// predicated-off copies of the odd-K loads
+template <int NP, bool WITH_GMASK, bool KODD>
 __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const __grid_constant__ SplatArgs a, int KU,
                                                                           int nwork) {
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
   const int slice_bytes = SPT * spw * 32 * K;   // a strip is 8 pixels x K floats
   const bool flip = NP == 2 && pow2 && KU <= 4 && (sl & 1);     // odd strips run from pixel 7 down to pixel 0
   const int dir = flip ? -1 : 1;
-  const bool kodd = (K & 1) != 0;
+  constexpr bool kodd = KODD;
   const f32x2 vm = pack2(1.0f, kbase + 1 < K ? 1.0f : 0.0f);
   float *sc_base = reinterpret_cast<float *>(dyn);
   float *wsum = reinterpret_cast<float *>(dyn + fast_consts_bytes(K));
@@ -657,10 +659,11 @@ cudaError_t launch_splat_bwd_nhwc_fast(const SplatArgs &a, int B, bool any_mask,
   if (sms == 0) {   // first launch on this device
     const int max_smem = (int)(fast_consts_bytes(128) + fast_wsum_bytes(128) + (size_t)kWarps * kFastStages * kFastStageBytes);
     cudaError_t e = cudaSuccess;
-#define GG_SET_SMEM(NP, GM)                                                                                           \
+#define GG_SET_SMEM(NP, GM, KO)                                                                                       \
   if (e == cudaSuccess)                                                                                               \
-    e = cudaFuncSetAttribute(splat_bwd_nhwc_fast_kernel<NP, GM>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
-    GG_SET_SMEM(1, false); GG_SET_SMEM(1, true); GG_SET_SMEM(2, false); GG_SET_SMEM(2, true);
+    e = cudaFuncSetAttribute(splat_bwd_nhwc_fast_kernel<NP, GM, KO>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
+    GG_SET_SMEM(1, false, false); GG_SET_SMEM(1, true, false); GG_SET_SMEM(1, false, true); GG_SET_SMEM(1, true, true);
+    GG_SET_SMEM(2, false, false); GG_SET_SMEM(2, true, false);
 #undef GG_SET_SMEM
     int count = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
@@ -675,13 +678,17 @@ cudaError_t launch_splat_bwd_nhwc_fast(const SplatArgs &a, int B, bool any_mask,
   const bool quads = (a.K & 3) == 0;
   // persistent: 2 CTAs per SM (registers and shared memory both allow exactly two)
   const unsigned grid = (unsigned)(nwork < (size_t)2 * sms ? nwork : (size_t)2 * sms);
+  const bool kodd = (a.K & 1) != 0;
+#define GG_LAUNCH_FAST(NP, GM, KO) \
+  launch_pdl(splat_bwd_nhwc_fast_kernel<NP, GM, KO>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork)
   if (quads) {
-    if (any_mask) launch_pdl(splat_bwd_nhwc_fast_kernel<2, true>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork);
-    else launch_pdl(splat_bwd_nhwc_fast_kernel<2, false>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork);
+    if (any_mask) GG_LAUNCH_FAST(2, true, false); else GG_LAUNCH_FAST(2, false, false);
+  } else if (kodd) {
+    if (any_mask) GG_LAUNCH_FAST(1, true, true); else GG_LAUNCH_FAST(1, false, true);
   } else {
-    if (any_mask) launch_pdl(splat_bwd_nhwc_fast_kernel<1, true>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork);
-    else launch_pdl(splat_bwd_nhwc_fast_kernel<1, false>, dim3(grid), dim3(kThreads), smem, st, a, KU, (int)nwork);
+    if (any_mask) GG_LAUNCH_FAST(1, true, false); else GG_LAUNCH_FAST(1, false, false);
   }
+#undef GG_LAUNCH_FAST
   return cudaGetLastError();
 }
 

@@ -376,13 +376,25 @@ def test_host_buffer_step_matches_oracle(gg, cuda_device):
 
 
 def test_randomised_host_step_equals_device_step(gg, cuda_device):
-    """Seeded sweep: the host-buffer step (pinned host arrays in, gradients out; zero-copy for the small arrays,
-    uint8 / float32 / bit-packed targets; K <= 64 fused, K > 64 five launches) returns exactly what the same kernels
-    return when driven from device tensors."""
+    """Seeded sweep: the host-buffer step (pinned host arrays in, gradients out; every GG_ZEROCOPY mode -- gradients
+    written in place (default), inputs read in place, both, neither; uint8 / float32 / bit-packed targets; K <= 64
+    fused, K > 64 five launches) returns exactly what the same kernels return when driven from device tensors."""
     from gaussigan_b200.host import HostSilhouetteStep
     from gaussigan_b200.plan import SilhouetteLossStep
     rng = torch.Generator().manual_seed(9)
+    saved = os.environ.get("GG_ZEROCOPY")
+    try:
+        _host_step_sweep(gg, cuda_device, rng, HostSilhouetteStep, SilhouetteLossStep)
+    finally:
+        if saved is None:
+            os.environ.pop("GG_ZEROCOPY", None)
+        else:
+            os.environ["GG_ZEROCOPY"] = saved
+
+
+def _host_step_sweep(gg, cuda_device, rng, HostSilhouetteStep, SilhouetteLossStep):
     for case in range(int(os.environ.get("GG_SWEEP_CASES", "100"))):
+        os.environ["GG_ZEROCOPY"] = ("out", "in", "1", "0")[case % 4]      # read by the library on every call
         B = int(torch.randint(1, 6, (1,), generator=rng))
         K = int(torch.randint(1, 65, (1,), generator=rng))
         n = int(torch.randint(1, 130, (1,), generator=rng))

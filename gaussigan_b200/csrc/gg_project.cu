@@ -189,14 +189,22 @@ __device__ __forceinline__ void sum_partials(const float *partials, int T, size_
   }
 }
 
-// summed moments (shear coordinates t = dx + r dy) -> d mu2d, d sigma2d (accumulated into gmu, gsg)
-__device__ void conic_adjoint(const double mu[2], const double sg[4], const double Tm[GG_MOMENTS], double gmu[2],
-                              double gsg[4]) {
+// summed moments (shear coordinates t = dx + r dy) -> d mu2d, d sigma2d (accumulated into gmu, gsg), in two parts: what
+// depends on the Gaussian alone (P = inv(sigma2d) and the float32-rounded shear the pixel kernel used) ...
+struct ConicConsts {
+  double P[4], a, b, c, r;
+};
+__device__ __forceinline__ void conic_consts(const double sg[4], ConicConsts &cc) {
   double det2 = sg[0] * sg[3] - sg[1] * sg[2];
   double idet = 1.0 / det2;
-  double P[4] = {sg[3] * idet, -sg[1] * idet, -sg[2] * idet, sg[0] * idet};
-  double a = P[0], b = 0.5 * (P[1] + P[2]), c = P[3];
-  double r = -(double)((float)(-(b / a)));          // the float32-rounded shear the pixel kernel used
+  cc.P[0] = sg[3] * idet; cc.P[1] = -sg[1] * idet; cc.P[2] = -sg[2] * idet; cc.P[3] = sg[0] * idet;
+  cc.a = cc.P[0]; cc.b = 0.5 * (cc.P[1] + cc.P[2]); cc.c = cc.P[3];
+  cc.r = -(double)((float)(-(cc.b / cc.a)));          // the float32-rounded shear the pixel kernel used
+}
+// ... and the map from the moments to the gradients
+__device__ __forceinline__ void conic_apply(const ConicConsts &cc, const double Tm[GG_MOMENTS], double gmu[2], double gsg[4]) {
+  const double *P = cc.P;
+  const double a = cc.a, b = cc.b, c = cc.c, r = cc.r;
   double M20 = Tm[0] - 2.0 * r * Tm[1] + r * r * Tm[2];
   double M11 = Tm[1] - r * Tm[2];
   double M02 = Tm[2];
@@ -214,6 +222,12 @@ __device__ void conic_adjoint(const double mu[2], const double sg[4], const doub
   gsg[2] -= PtPb[2] * P[0] + PtPb[3] * P[1];
   gsg[3] -= PtPb[2] * P[2] + PtPb[3] * P[3];
 }
+__device__ void conic_adjoint(const double mu[2], const double sg[4], const double Tm[GG_MOMENTS], double gmu[2],
+                              double gsg[4]) {
+  ConicConsts cc;
+  conic_consts(sg, cc);
+  conic_apply(cc, Tm, gmu, gsg);
+}
 
 __device__ __forceinline__ void load_sigma(const void *sigma, int is_f64, size_t idx, double *S) {
   if (is_f64) {
@@ -225,6 +239,95 @@ __device__ __forceinline__ void load_sigma(const void *sigma, int is_f64, size_t
 #pragma unroll
     for (int i = 0; i < 9; ++i) S[i] = (double)p[i];
   }
+}
+
+// Adjoint of project_one for ONE Gaussian: (d mu2d, d sigma2d) -> d Sigma (raw, non-symmetric), d m (camera frame)
+// and this Gaussian's contribution to d R.  Linear in (gmu, gsg).
+__device__ __forceinline__ void project_adjoint_one(const Cam &cam, const Proj &p, double f, const double gmu[2],
+                                                    const double gsg[4], double Sbar[9], double mbar[3],
+                                                    double Rbar_add[9]) {
+  // ---- adjoint of: sigma2d = q * adj(M33), q = -dM / d33^2; mu2d = f (d31, -d23) / d33
+  const double *M = p.M;
+  double Mb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double i33 = 1.0 / p.d33;
+  double q = -p.dM * i33 * i33;
+  double qbar = gsg[0] * M[4] - gsg[1] * M[1] - gsg[2] * M[3] + gsg[3] * M[0];
+  Mb[4] += q * gsg[0]; Mb[1] -= q * gsg[1]; Mb[3] -= q * gsg[2]; Mb[0] += q * gsg[3];
+  double dMbar = -qbar * i33 * i33;
+  double d33bar = 2.0 * p.dM * i33 * i33 * i33 * qbar;
+  double d31bar = f * gmu[0] * i33;
+  double d23bar = -f * gmu[1] * i33;
+  d33bar += -f * p.d31 * gmu[0] * i33 * i33 + f * p.d23 * gmu[1] * i33 * i33;
+  Mb[0] += d33bar * M[4]; Mb[4] += d33bar * M[0]; Mb[1] -= d33bar * M[3]; Mb[3] -= d33bar * M[1];
+  Mb[1] += d31bar * M[5]; Mb[5] += d31bar * M[1]; Mb[2] -= d31bar * M[4]; Mb[4] -= d31bar * M[2];
+  Mb[0] += d23bar * M[7]; Mb[7] += d23bar * M[0]; Mb[1] -= d23bar * M[6]; Mb[6] -= d23bar * M[1];
+  double Cm[9];
+  cofactors(M, Cm);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Mb[i] += dMbar * Cm[i];
+  // undo the sign flip
+  Mb[2] = -Mb[2]; Mb[5] = -Mb[5]; Mb[6] = -Mb[6]; Mb[7] = -Mb[7];
+  // ---- M = v v^T - s Q
+  double vbar[3], Qbar[9], sbar = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    vbar[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      vbar[i] += (Mb[i * 3 + j] + Mb[j * 3 + i]) * p.v[j];
+      sbar -= Mb[i * 3 + j] * p.Q[i * 3 + j];
+      Qbar[i * 3 + j] = -p.s * Mb[i * 3 + j];
+    }
+  }
+  // ---- s = m Q m^T - 1 ;  v = Q m^T
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    mbar[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      mbar[i] += sbar * (p.Q[i * 3 + j] + p.Q[j * 3 + i]) * p.m[j] + p.Q[j * 3 + i] * vbar[j];
+      Qbar[i * 3 + j] += sbar * p.m[i] * p.m[j] + vbar[i] * p.m[j];
+    }
+  }
+  // ---- Q = inv(Sigma')  =>  Sigma'bar = -Q^T Qbar Q^T
+  double tmp[9], Spbar[9];
+  mat3_mul_at(p.Q, Qbar, tmp);
+  mat3_mul_bt(tmp, p.Q, Spbar);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Spbar[i] = -Spbar[i];
+  // ---- Sigma' = R Sigma R^T ;  m = R mu + t
+  mat3_mul_at(cam.R, Spbar, tmp);
+  mat3_mul(tmp, cam.R, Sbar);                                // R^T Sigma'bar R
+  // d R += Sigma'bar R Sigma^T + Sigma'bar^T R Sigma + mbar mu^T
+  double RS[9], RSt[9];
+  mat3_mul(cam.R, p.S, RS);
+  mat3_mul_bt(cam.R, p.S, RSt);
+  double t1[9], t2[9];
+  mat3_mul(Spbar, RSt, t1);
+  mat3_mul_at(Spbar, RS, t2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rbar_add[i * 3 + j] = t1[i * 3 + j] + t2[i * 3 + j] + mbar[i] * p.mu[j];
+}
+
+// Adjoint of R = RX RY RZ (float32 in the forward; evaluated in float64 on the same float32 values): d R -> d angles
+// (radians).  Linear in Rbar.
+__device__ __forceinline__ void rotation_adjoint(const Cam &cam, const double Rbar[9], double &gx, double &gy, double &gz) {
+  double RXd[9], RYd[9], RZd[9], RXYd[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { RXd[i] = cam.RX[i]; RYd[i] = cam.RY[i]; RZd[i] = cam.RZ[i]; RXYd[i] = cam.RXY[i]; }
+  double RYZ[9], RXbar[9], RYbar[9], RZbar[9], tmp[9];
+  mat3_mul(RYd, RZd, RYZ);
+  mat3_mul_bt(Rbar, RYZ, RXbar);            // Rbar (RY RZ)^T
+  mat3_mul_at(RXd, Rbar, tmp);
+  mat3_mul_bt(tmp, RZd, RYbar);             // RX^T Rbar RZ^T
+  mat3_mul_at(RXYd, Rbar, RZbar);           // (RX RY)^T Rbar
+  const double cx = cam.c[0], sx = cam.s[0], cy = cam.c[1], sy = cam.s[1], cz = cam.c[2], sz = cam.s[2];
+  // dRX/da = [[0,0,0],[0,-s,c],[0,-c,-s]], dRY/da = [[-s,0,-c],[0,0,0],[c,0,-s]], dRZ/da = [[-s,c,0],[-c,-s,0],[0,0,0]]
+  gx = -sx * RXbar[4] + cx * RXbar[5] - cx * RXbar[7] - sx * RXbar[8];
+  gy = -sy * RYbar[0] - cy * RYbar[2] + cy * RYbar[6] - sy * RYbar[8];
+  gz = -sz * RZbar[0] + cz * RZbar[1] - cz * RZbar[3] - sz * RZbar[4];
 }
 
 }  // namespace
@@ -345,59 +448,8 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
       conic_adjoint(p.mu2d, p.sig2d, Tm, gmu, gsg);
     }
 
-    // ---- adjoint of: sigma2d = q * adj(M33), q = -dM / d33^2; mu2d = f (d31, -d23) / d33
-    const double *M = p.M;
-    double Mb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double i33 = 1.0 / p.d33;
-    double q = -p.dM * i33 * i33;
-    double qbar = gsg[0] * M[4] - gsg[1] * M[1] - gsg[2] * M[3] + gsg[3] * M[0];
-    Mb[4] += q * gsg[0]; Mb[1] -= q * gsg[1]; Mb[3] -= q * gsg[2]; Mb[0] += q * gsg[3];
-    double dMbar = -qbar * i33 * i33;
-    double d33bar = 2.0 * p.dM * i33 * i33 * i33 * qbar;
-    double d31bar = f * gmu[0] * i33;
-    double d23bar = -f * gmu[1] * i33;
-    d33bar += -f * p.d31 * gmu[0] * i33 * i33 + f * p.d23 * gmu[1] * i33 * i33;
-    Mb[0] += d33bar * M[4]; Mb[4] += d33bar * M[0]; Mb[1] -= d33bar * M[3]; Mb[3] -= d33bar * M[1];
-    Mb[1] += d31bar * M[5]; Mb[5] += d31bar * M[1]; Mb[2] -= d31bar * M[4]; Mb[4] -= d31bar * M[2];
-    Mb[0] += d23bar * M[7]; Mb[7] += d23bar * M[0]; Mb[1] -= d23bar * M[6]; Mb[6] -= d23bar * M[1];
-    double Cm[9];
-    cofactors(M, Cm);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Mb[i] += dMbar * Cm[i];
-    // undo the sign flip
-    Mb[2] = -Mb[2]; Mb[5] = -Mb[5]; Mb[6] = -Mb[6]; Mb[7] = -Mb[7];
-    // ---- M = v v^T - s Q
-    double vbar[3], Qbar[9], sbar = 0.0, mbar[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      vbar[i] = 0.0;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        vbar[i] += (Mb[i * 3 + j] + Mb[j * 3 + i]) * p.v[j];
-        sbar -= Mb[i * 3 + j] * p.Q[i * 3 + j];
-        Qbar[i * 3 + j] = -p.s * Mb[i * 3 + j];
-      }
-    }
-    // ---- s = m Q m^T - 1 ;  v = Q m^T
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      mbar[i] = 0.0;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        mbar[i] += sbar * (p.Q[i * 3 + j] + p.Q[j * 3 + i]) * p.m[j] + p.Q[j * 3 + i] * vbar[j];
-        Qbar[i * 3 + j] += sbar * p.m[i] * p.m[j] + vbar[i] * p.m[j];
-      }
-    }
-    // ---- Q = inv(Sigma')  =>  Sigma'bar = -Q^T Qbar Q^T
-    double tmp[9], Spbar[9];
-    mat3_mul_at(p.Q, Qbar, tmp);
-    mat3_mul_bt(tmp, p.Q, Spbar);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Spbar[i] = -Spbar[i];
-    // ---- Sigma' = R Sigma R^T ;  m = R mu + t
-    double Sbar[9];
-    mat3_mul_at(cam.R, Spbar, tmp);
-    mat3_mul(tmp, cam.R, Sbar);                                // R^T Sigma'bar R
+    double Sbar[9], mbar[3], Radd[9];
+    project_adjoint_one(cam, p, f, gmu, gsg, Sbar, mbar, Radd);
     // the same thread owns this Gaussian in every view: plain read-modify-write, fixed view order
     if (dsigma) {
 #pragma unroll
@@ -411,36 +463,14 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
         dmus[gidx * 3 + i] = view == 0 ? g : dmus[gidx * 3 + i] + g;
       }
     }
-    // Rbar += Sigma'bar R Sigma^T + Sigma'bar^T R Sigma + mbar mu^T
-    double RS[9], RSt[9];
-    mat3_mul(cam.R, p.S, RS);
-    mat3_mul_bt(cam.R, p.S, RSt);
-    double t1[9], t2[9];
-    mat3_mul(Spbar, RSt, t1);
-    mat3_mul_at(Spbar, RS, t2);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) Rbar[i * 3 + j] += t1[i * 3 + j] + t2[i * 3 + j] + mbar[i] * p.mu[j];
+    for (int i = 0; i < 9; ++i) Rbar[i] += Radd[i];
     }   // active
     __syncthreads();   // Tm_s is rewritten by the next chunk
   }
 
-  // ---- R = RX RY RZ (float32 in the forward; adjoint evaluated in float64 on the same float32 values)
-  double RXd[9], RYd[9], RZd[9], RXYd[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) { RXd[i] = cam.RX[i]; RYd[i] = cam.RY[i]; RZd[i] = cam.RZ[i]; RXYd[i] = cam.RXY[i]; }
-  double RYZ[9], RXbar[9], RYbar[9], RZbar[9], tmp[9];
-  mat3_mul(RYd, RZd, RYZ);
-  mat3_mul_bt(Rbar, RYZ, RXbar);            // Rbar (RY RZ)^T
-  mat3_mul_at(RXd, Rbar, tmp);
-  mat3_mul_bt(tmp, RZd, RYbar);             // RX^T Rbar RZ^T
-  mat3_mul_at(RXYd, Rbar, RZbar);           // (RX RY)^T Rbar
-  const double cx = cam.c[0], sx = cam.s[0], cy = cam.c[1], sy = cam.s[1], cz = cam.c[2], sz = cam.s[2];
-  // dRX/da = [[0,0,0],[0,-s,c],[0,-c,-s]], dRY/da = [[-s,0,-c],[0,0,0],[c,0,-s]], dRZ/da = [[-s,c,0],[-c,-s,0],[0,0,0]]
-  double gx = -sx * RXbar[4] + cx * RXbar[5] - cx * RXbar[7] - sx * RXbar[8];
-  double gy = -sy * RYbar[0] - cy * RYbar[2] + cy * RYbar[6] - sy * RYbar[8];
-  double gz = -sz * RZbar[0] + cz * RZbar[1] - cz * RZbar[3] - sz * RZbar[4];
+  double gx, gy, gz;
+  rotation_adjoint(cam, Rbar, gx, gy, gz);
   red[0][threadIdx.x] = gx; red[1][threadIdx.x] = gy; red[2][threadIdx.x] = gz;
   __syncthreads();
   if (threadIdx.x < 3 && drot) {
@@ -452,6 +482,122 @@ __global__ void __launch_bounds__(128) project_bwd_kernel(
   }
   __syncthreads();   // red[] is reused by the next view
   }   // views
+}
+
+// The same adjoint for the common shape -- one camera per set of Gaussians and 6 K <= 128 -- with the dependent float64
+// chain taken OFF the critical path.  The adjoint is linear in its six inputs (d mu2d [2], d sigma2d [4]), and those are
+// the only quantities that depend on the splat backward's partial sums.  So thread (seed i, Gaussian k) recomputes the
+// forward projection of k and runs the whole adjoint for the unit input e_i BEFORE griddepcontrol.wait -- under the
+// tail of the splat backward, where the chain measured 2.8 us of free time beyond the forward recompute
+// (tools/chain_parts.py and the pre-wait spin experiment in DESIGN.md) -- leaving the 6 x 15 Jacobian block of k in
+// shared memory (9 d Sigma, 3 d mu, 3 d angle).  After the wait: the T partial sums per column (one round of loads),
+// the 2 x 2 conic map to the six inputs, and 15 dot products of length 6 per Gaussian.  Same inputs contract as
+// project_bwd_kernel (mus / sigma / rot* at least two launches old).
+constexpr int kLinOut = 15;
+__global__ void __launch_bounds__(128) project_bwd_lin_kernel(
+    const float *__restrict__ mus, const void *__restrict__ sigma, int sigma_is_f64,
+    const float *__restrict__ rotx, const float *__restrict__ roty, const float *__restrict__ rotz,
+    double tx, double ty, double tz, double focal, int B, int K,
+    const float *__restrict__ partials, int T, const double *__restrict__ gmu2d_in,
+    const double *__restrict__ gsigma2d_in, float *__restrict__ dmus, double *__restrict__ dsigma,
+    float *__restrict__ drot) {
+  extern __shared__ double lin_sm[];
+  double *J = lin_sm;                        // [K][6][kLinOut]
+  double *gs = J + (size_t)K * 6 * kLinOut;   // [K][6]   the six inputs of every Gaussian
+  double *Tm_s = gs + (size_t)K * 6;          // [K][5]   summed moments
+  double *red = Tm_s + (size_t)K * GG_MOMENTS;   // [3][K]   d angle per Gaussian
+  const int b = blockIdx.x;
+  const int tid = (int)threadIdx.x;
+  const int seed = tid / K, k = tid - seed * K;
+  const bool active = tid < 6 * K;
+  const size_t gidx = (size_t)b * K + (active ? k : 0);
+  const double t[3] = {tx, ty, tz};
+  const double f = (double)(float)focal;
+
+  // ---- before the wait: forward recompute and the adjoint of one unit input
+  const float rxd = __ldg(rotx + b), ryd = __ldg(roty + b), rzd = __ldg(rotz + b);
+  Proj p;
+  load_sigma(sigma, sigma_is_f64, gidx, p.S);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p.mu[i] = (double)__ldg(mus + gidx * 3 + i);
+  Cam cam;
+  make_cam(rxd, ryd, rzd, cam);
+  ConicConsts cc;
+  if (active) {
+    project_one(cam, t, f, p);
+    conic_consts(p.sig2d, cc);
+    double gmu[2] = {seed == 0 ? 1.0 : 0.0, seed == 1 ? 1.0 : 0.0};
+    double gsg[4] = {seed == 2 ? 1.0 : 0.0, seed == 3 ? 1.0 : 0.0, seed == 4 ? 1.0 : 0.0, seed == 5 ? 1.0 : 0.0};
+    double Sbar[9], mbar[3], Radd[9], gx, gy, gz;
+    project_adjoint_one(cam, p, f, gmu, gsg, Sbar, mbar, Radd);
+    rotation_adjoint(cam, Radd, gx, gy, gz);
+    double *Jk = J + ((size_t)k * 6 + seed) * kLinOut;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Jk[i] = Sbar[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      Jk[9 + i] = cam.R[0 * 3 + i] * mbar[0] + cam.R[1 * 3 + i] * mbar[1] + cam.R[2 * 3 + i] * mbar[2];
+    Jk[12] = gx; Jk[13] = gy; Jk[14] = gz;
+  }
+  pdl_enter();
+
+  // ---- after the wait
+  const bool have_partials = partials && T > 0;
+  if (have_partials) {
+    const float *base = partials + (size_t)b * T * K * GG_MOMENTS;
+    const size_t tile_stride = (size_t)K * GG_MOMENTS;
+    for (int c = tid; c < K * GG_MOMENTS; c += (int)blockDim.x) {
+      double acc = 0.0;
+      for (int t0 = 0; t0 < T; t0 += 16) {     // 16 independent loads in flight: one round trip for T <= 16
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = (t0 + u < T) ? __ldg(base + (size_t)(t0 + u) * tile_stride + c) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc += (double)v[u];
+      }
+      Tm_s[c] = acc;
+    }
+  }
+  double gmu[2] = {0, 0}, gsg[4] = {0, 0, 0, 0};
+  if (tid < K) {
+    if (gmu2d_in) { gmu[0] = gmu2d_in[gidx * 2]; gmu[1] = gmu2d_in[gidx * 2 + 1]; }
+    if (gsigma2d_in) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gsg[i] = gsigma2d_in[gidx * 4 + i];
+    }
+  }
+  __syncthreads();
+  if (tid < K) {
+    if (have_partials) {
+      double Tm[GG_MOMENTS];
+#pragma unroll
+      for (int j = 0; j < GG_MOMENTS; ++j) Tm[j] = Tm_s[tid * GG_MOMENTS + j];
+      conic_apply(cc, Tm, gmu, gsg);
+    }
+    gs[tid * 6 + 0] = gmu[0]; gs[tid * 6 + 1] = gmu[1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gs[tid * 6 + 2 + i] = gsg[i];
+  }
+  __syncthreads();
+  for (int o = tid; o < K * kLinOut; o += (int)blockDim.x) {
+    const int kk = o / kLinOut, j = o - kk * kLinOut;
+    const double *Jk = J + (size_t)kk * 6 * kLinOut + j;
+    const double *g = gs + kk * 6;
+    double acc = Jk[0] * g[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) acc += Jk[i * kLinOut] * g[i];
+    const size_t go = (size_t)b * K + kk;
+    if (j < 9) { if (dsigma) dsigma[go * 9 + j] = acc; }
+    else if (j < 12) { if (dmus) dmus[go * 3 + (j - 9)] = (float)acc; }
+    else red[(j - 12) * K + kk] = acc;
+  }
+  __syncthreads();
+  if (tid < 3 && drot) {
+    double acc = 0.0;
+    for (int i = 0; i < K; ++i) acc += red[tid * K + i];
+    // degrees -> radians was (deg * pi32) / 180 in float32
+    drot[(size_t)b * 3 + tid] = (float)(acc * (double)3.14159274101257324219f / 180.0);
+  }
 }
 
 __global__ void __launch_bounds__(128) conic_fwd_kernel(const void *__restrict__ mu2d,
@@ -531,6 +677,14 @@ cudaError_t launch_project_bwd(const float *mus, const void *sigma, int f64, con
   // 128 threads: warp 0 holds the Gaussians of a K <= 32 model, the other three sum the partials' columns in one round
   // of loads (measured on the C2 step chain, tools/time_step.py: 128 threads 44.1 us/step, 64 threads 46.2)
   static const int env_threads = [] { const char *e = std::getenv("GG_PROJ_BWD_THREADS"); return e ? std::atoi(e) : 0; }();
+  static const bool lin = [] { const char *e = std::getenv("GG_PROJ_BWD_LIN"); return !e || e[0] != '0'; }();
+  if (lin && nviews == 1 && 6 * K <= 128) {
+    // one camera per set, at most 21 Gaussians: the linearised adjoint (Jacobian before the wait)
+    const size_t smem = (size_t)K * (6 * kLinOut + 6 + GG_MOMENTS + 3) * sizeof(double);
+    launch_pdl(project_bwd_lin_kernel, dim3(B), dim3(128), smem, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B, K,
+               partials, T, gmu2d, gsigma2d, dmus, dsigma, drot);
+    return cudaGetLastError();
+  }
   const int threads = env_threads > 0 ? env_threads : 128;
   launch_pdl(project_bwd_kernel, dim3(B / nviews), dim3(threads), 0, st, mus, sigma, f64, rx, ry, rz, tx, ty, tz, focal, B,
              K, B / nviews, partials, T, gmu2d, gsigma2d, dmus, dsigma, drot);

@@ -194,6 +194,8 @@ def run_gpu(args):
     from gaussigan_b200.host import bind_to_gpu_numa_node
     numa = bind_to_gpu_numa_node(local)           # before any pinned allocation: host buffers land next to the GPU
     if world > 1:
+        # NCCL prints its version banner to stdout at some debug levels: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B, K, n = B_PER_GPU, K_GAUSS, SIZE
     peaks = _peaks()

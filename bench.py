@@ -155,7 +155,7 @@ def run_reference(args):
               f"{len(chunks)} chunks of {chunk}; float64 torch-CPU restatement of "
               f"mask/mask_gen_dynamic.py:112-143,233-323,785-787 (TensorFlow 1.12 is not installable); value = mean over "
               f"the {steps} timed steps, best step {B_PER_GPU / min(times):.1f} silhouettes/s")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -166,7 +166,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -194,8 +194,6 @@ def run_gpu(args):
     from gaussigan_b200.host import bind_to_gpu_numa_node
     numa = bind_to_gpu_numa_node(local)           # before any pinned allocation: host buffers land next to the GPU
     if world > 1:
-        # NCCL prints its version banner to stdout at some debug levels: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B, K, n = B_PER_GPU, K_GAUSS, SIZE
     peaks = _peaks()
@@ -581,7 +579,7 @@ def run_gpu(args):
             "allreduce": allreduce, "configs": configs,
             "gpu_launches": hl["reps"] * KSTEPS * SilhouetteStep.LAUNCHES_PER_STEP,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -956,7 +954,27 @@ def bench_configs(world, rank, dev, peaks, capture, timed_passes, max_over_ranks
     return out
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep the process's stdout for the ONE JSON line: duplicate it for our own use and point fd 1 at stderr, so that
+    whatever a library prints to stdout (NCCL's version banner under torchrun, for one) ends up on stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2048)

@@ -677,7 +677,8 @@ cudaError_t launch_project_bwd(const float *mus, const void *sigma, int f64, con
   // 128 threads: warp 0 holds the Gaussians of a K <= 32 model, the other three sum the partials' columns in one round
   // of loads (measured on the C2 step chain, tools/time_step.py: 128 threads 44.1 us/step, 64 threads 46.2)
   static const int env_threads = [] { const char *e = std::getenv("GG_PROJ_BWD_THREADS"); return e ? std::atoi(e) : 0; }();
-  static const bool lin = [] { const char *e = std::getenv("GG_PROJ_BWD_LIN"); return !e || e[0] != '0'; }();
+  const char *lin_env = std::getenv("GG_PROJ_BWD_LIN");      // read per call: the tests compare the two kernels
+  const bool lin = !lin_env || lin_env[0] != '0';
   if (lin && nviews == 1 && 6 * K <= 128) {
     // one camera per set, at most 21 Gaussians: the linearised adjoint (Jacobian before the wait)
     const size_t smem = (size_t)K * (6 * kLinOut + 6 + GG_MOMENTS + 3) * sizeof(double);

@@ -327,6 +327,48 @@ def test_projection_outputs_match_oracle_to_float64_roundoff(gg, cuda_device):
     assert (mu2d.cpu() - rmu).abs().max() < 1e-12 and max_rel(s2d, rs) < 1e-12
 
 
+@pytest.mark.parametrize("B,K,n", [(5, 16, 64), (3, 6, 40), (2, 21, 32), (4, 1, 24), (2, 12, 96)])
+def test_linearised_projection_adjoint_equals_generic_kernel(gg, cuda_device, B, K, n):
+    """project_bwd_lin_kernel (one camera per set, 6 K <= 128: Jacobian block per Gaussian ahead of the dependency wait,
+    dot products after it) against project_bwd_kernel (GG_PROJ_BWD_LIN=0, read per call) on the same partial sums, all
+    three Euler angles, with and without upstream gradients of mu2d / sigma2d on top: float64 round-off apart, and
+    both within the gradient tolerance of the oracle."""
+    inp = rp.synth_inputs(B, K, seed=900 + K, angle=60.0)
+    inp["rotx"] = torch.randn(B, 1, generator=torch.Generator().manual_seed(1)) * 25
+    inp["rotz"] = torch.randn(B, 1, generator=torch.Generator().manual_seed(2)) * 25
+    w = weights_like([(B, n, n, 1)], 41)[0]
+    lv = _leaves(inp)
+    ref = rp.get_landmarks(lv["mus"], lv["sigma"], lv["rotx"], lv["roty"], lv["rotz"], 0.1, -0.2, -2.2, 1.3, sizes=(n,))[0]
+    (ref.sum(-1, keepdim=True) * w).sum().backward()
+    saved = os.environ.get("GG_PROJ_BWD_LIN")
+    grads = {}
+    try:
+        for mode in ("1", "0"):
+            os.environ["GG_PROJ_BWD_LIN"] = mode
+            dv = _leaves(inp, cuda_device)
+            m = gg.render_silhouette(dv["mus"], dv["sigma"], dv["rotx"], dv["roty"], dv["rotz"], 0.1, -0.2, -2.2, 1.3, size=n)
+            (m.reshape(B, n, n, 1) * w.to(cuda_device)).sum().backward()
+            grads[mode] = {k: dv[k].grad.clone() for k in ("mus", "sigma", "rotx", "roty", "rotz")}
+            # the frozen-graph boundary tensors carry their own upstream gradients through the same kernel
+            dv2 = _leaves(inp, cuda_device)
+            mu2d, s2d = gg.project(dv2["mus"], dv2["sigma"], dv2["rotx"], dv2["roty"], dv2["rotz"], 0.1, -0.2, -2.2, 1.3)
+            ((mu2d ** 2).sum() + (s2d * torch.arange(4, device=cuda_device, dtype=s2d.dtype).reshape(2, 2)).sum()).backward()
+            grads[mode + "p"] = {k: dv2[k].grad.clone() for k in ("mus", "sigma", "roty")}
+    finally:
+        if saved is None:
+            os.environ.pop("GG_PROJ_BWD_LIN", None)
+        else:
+            os.environ["GG_PROJ_BWD_LIN"] = saved
+    for k in grads["1"]:
+        assert_close_norm(grads["1"][k], lv[k].grad, GRAD_RTOL, f"K={K} grad {k} (linearised)")
+        assert_close_norm(grads["0"][k], lv[k].grad, GRAD_RTOL, f"K={K} grad {k} (generic)")
+        tol = 1e-6 if grads["1"][k].dtype == torch.float32 else 1e-9        # float32 outputs are rounded once
+        assert_close_norm(grads["1"][k], grads["0"][k], tol, f"K={K} grad {k}: linearised vs generic")
+    for k in grads["1p"]:
+        tol = 1e-6 if grads["1p"][k].dtype == torch.float32 else 1e-9
+        assert_close_norm(grads["1p"][k], grads["0p"][k], tol, f"K={K} projection-only grad {k}: linearised vs generic")
+
+
 # ------------------------------------------------------------------ fused consumers / host-buffer step
 @pytest.mark.parametrize("B,K,n,dtype", [(6, 16, 256, torch.uint8), (3, 6, 64, torch.float32), (2, 5, 100, torch.uint8),
                                          (2, 64, 40, torch.float32)])

@@ -97,7 +97,10 @@ GG_API int gg_project_fwd(const float *mus, const void *sigma, int sigma_is_f64,
  * degree).  The forward is recomputed in registers; nothing is saved between passes.  Under programmatic dependent
  * launch that recompute runs BEFORE the kernel waits for its predecessor in the stream, so mus / sigma / rot* must not
  * be outputs of the kernel launched immediately before this one (partials, gmu2d and gsigma2d may be); they never
- * are in the sequences of this library (the predecessor is a splat or fused-loss kernel). */
+ * are in the sequences of this library (the predecessor is a splat or fused-loss kernel).  For K <= 21 the same window
+ * also takes the adjoint itself: it is linear in d mu2d / d sigma2d, so six threads per Gaussian run it for the six
+ * unit inputs before the wait and only 15 dot products of length 6 per Gaussian remain after it (GG_PROJ_BWD_LIN=0
+ * selects the generic kernel; the two agree to float64 round-off). */
 GG_API int gg_project_bwd(const float *mus, const void *sigma, int sigma_is_f64,
                    const float *rotx, const float *roty, const float *rotz,
                    double tx, double ty, double tz, double focal, int B, int K,

@@ -419,6 +419,8 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quad_kernel(const __grid_c
 // the CTA are used, so that a thread keeps its quad of Gaussians (constants in registers) from pass to pass and
 // consecutive threads still write consecutive 16-byte chunks.  No fused silhouette: the lanes of a pixel do not form
 // an aligned group of a warp; the launcher gives the silhouette to the mask kernel.
+// NC: columns a thread keeps in registers (its whole share of a row: n <= NC * pixels per pass); 0: column loop
+template <int NC>
 __global__ void __launch_bounds__(kThreads) splat_fwd_quadg_kernel(const __grid_constant__ SplatArgs a, int KQ) {
   pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   const int b = blockIdx.x / a.T;
@@ -440,6 +442,46 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quadg_kernel(const __grid_
   }
   const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
   const int row_end = min(n, row_begin + s.rows_per_tile);
+  if (NC > 0) {
+    constexpr int kColsPerThread = NC > 0 ? NC : 1;
+    // A thread owns at most kColsPerThread columns (c0, c0 + cpp, ...: 4 at n = 256, K = 12): their coordinates and
+    // store pointers are formed once, so a row costs its 8 setup operations plus four operations, one exponential
+    // and a quarter of a 128-bit store per value (the column loop below re-derives coordinate and address per
+    // element and ran at 70 % of the issue slots).  Same arithmetic, bit-identical values.
+    float xs[kColsPerThread];
+    float *ptr[kColsPerThread];
+    bool on[kColsPerThread];
+#pragma unroll
+    for (int j = 0; j < kColsPerThread; ++j) {
+      const int col = c0 + j * cpp;
+      on[j] = col < n;
+      xs[j] = grid_coord(on[j] ? col : c0, s.step);
+      ptr[j] = s.maps + ((size_t)b * n + row_begin) * n * s.cstride + 4 * kq + (size_t)(on[j] ? col : c0) * s.cstride;
+    }
+    const size_t row_stride = (size_t)n * s.cstride;
+    for (int row = row_begin; row < row_end; ++row) {
+      const float y = grid_coord(row, s.step);
+      float sh[4], e[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dy = y - muy[i];
+        sh[i] = fmaf(nr[i], dy, mux[i]);
+        e[i] = (nE[i] * dy) * dy;
+      }
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; ++j) {
+        float g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float t = xs[j] - sh[i];
+          g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+        }
+        if (on[j]) st_f4(ptr[j], g[0], g[1], g[2], g[3]);
+        ptr[j] += row_stride;
+      }
+    }
+    return;
+  }
   for (int row = row_begin; row < row_end; ++row) {
     const float y = grid_coord(row, s.step);
     float sh[4], e[4];
@@ -466,6 +508,7 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quadg_kernel(const __grid_
 // ========================================================================== forward, pairs, even K
 // The same for K = 2 KP that is not a multiple of 4 (the reference's K = 6): thread = (pixel, 2 Gaussians), one
 // 64-bit store, consecutive threads -> consecutive 8-byte chunks.
+template <int NC>
 __global__ void __launch_bounds__(kThreads) splat_fwd_pair_kernel(const __grid_constant__ SplatArgs a, int KP) {
   pdl_enter();   // programmatic dependent launch: see gg_common.cuh
   const int b = blockIdx.x / a.T;
@@ -487,6 +530,42 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_pair_kernel(const __grid_c
   }
   const int row_begin = (tile - s.tile_begin) * s.rows_per_tile;
   const int row_end = min(n, row_begin + s.rows_per_tile);
+  if (NC > 0) {      // columns of a thread hoisted out of the row loop: see splat_fwd_quadg_kernel
+    constexpr int kColsPerThread = NC > 0 ? NC : 1;
+    float xs[kColsPerThread];
+    float *ptr[kColsPerThread];
+    bool on[kColsPerThread];
+#pragma unroll
+    for (int j = 0; j < kColsPerThread; ++j) {
+      const int col = c0 + j * cpp;
+      on[j] = col < n;
+      xs[j] = grid_coord(on[j] ? col : c0, s.step);
+      ptr[j] = s.maps + ((size_t)b * n + row_begin) * n * s.cstride + 2 * kp + (size_t)(on[j] ? col : c0) * s.cstride;
+    }
+    const size_t row_stride = (size_t)n * s.cstride;
+    for (int row = row_begin; row < row_end; ++row) {
+      const float y = grid_coord(row, s.step);
+      float sh[2], e[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float dy = y - muy[i];
+        sh[i] = fmaf(nr[i], dy, mux[i]);
+        e[i] = (nE[i] * dy) * dy;
+      }
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; ++j) {
+        float g[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float t = xs[j] - sh[i];
+          g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+        }
+        if (on[j]) *reinterpret_cast<float2 *>(ptr[j]) = make_float2(g[0], g[1]);
+        ptr[j] += row_stride;
+      }
+    }
+    return;
+  }
   for (int row = row_begin; row < row_end; ++row) {
     const float y = grid_coord(row, s.step);
     float sh[2], e[2];
@@ -935,6 +1014,13 @@ static cudaError_t launch_bwd_strip(const SplatArgs &a, int gin_mode, int B, cud
   return cudaGetLastError();
 }
 
+// columns of a row one thread of the quadg / pair forwards writes (cpp = pixels per pass), largest scale of the launch
+static int fwd_cols_per_thread(const SplatArgs &a, int cpp) {
+  int cols = 1;
+  for (int i = 0; i < a.nscales; ++i) cols = max(cols, (a.sc[i].n + cpp - 1) / cpp);
+  return cols;
+}
+
 cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, const int *sizes, float *const *maps,
                              float *const *masks, int layout, cudaStream_t st, const int *cstrides,
                              const int *coffsets) {
@@ -971,13 +1057,21 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
       else launch_pdl(splat_fwd_quad_kernel<false>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
       err = cudaGetLastError();
     } else if (pl.maps_kind == MAPS_FLAT && (K & 3) == 0 && (K >> 2) <= kThreads) {
-      launch_pdl(splat_fwd_quadg_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 2);
+      const int cols = fwd_cols_per_thread(a, kThreads / (K >> 2));
+      const dim3 grid((unsigned)((size_t)B * a.T));
+      if (cols <= 4) launch_pdl(splat_fwd_quadg_kernel<4>, grid, dim3(kThreads), 0, st, a, K >> 2);
+      else if (cols <= 8) launch_pdl(splat_fwd_quadg_kernel<8>, grid, dim3(kThreads), 0, st, a, K >> 2);
+      else launch_pdl(splat_fwd_quadg_kernel<0>, grid, dim3(kThreads), 0, st, a, K >> 2);
       err = cudaGetLastError();
     } else if (pl.maps_kind == MAPS_FLAT && (K & 1) == 0 && (K >> 1) <= kThreads) {
       // (a variant with 128-bit stores over pixel PAIRS -- K / 2 whole vectors per two pixels -- was measured in round 2
       // and is slower than these 64-bit stores: K = 6: 4.41 vs 4.55 TB/s, K = 10: 5.33 vs 5.76, K = 14: 5.70 vs 6.28 at
       // B = 64; at this size the launch ramp, not the store width, is what separates K = 6 from the copy bandwidth)
-      launch_pdl(splat_fwd_pair_kernel, dim3((unsigned)((size_t)B * a.T)), dim3(kThreads), 0, st, a, K >> 1);
+      const int cols = fwd_cols_per_thread(a, kThreads / (K >> 1));
+      const dim3 grid((unsigned)((size_t)B * a.T));
+      if (cols <= 4) launch_pdl(splat_fwd_pair_kernel<4>, grid, dim3(kThreads), 0, st, a, K >> 1);
+      else if (cols <= 8) launch_pdl(splat_fwd_pair_kernel<8>, grid, dim3(kThreads), 0, st, a, K >> 1);
+      else launch_pdl(splat_fwd_pair_kernel<0>, grid, dim3(kThreads), 0, st, a, K >> 1);
       err = cudaGetLastError();
     } else if (pl.maps_kind == MAPS_FLAT) {
       int max_rows = 1;

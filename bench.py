@@ -438,8 +438,44 @@ def run_gpu(args):
                      "hbm_peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"],
                      "note": "the forward only writes: its rate can exceed the measured copy (read+write) bandwidth"}
         del mbufs, mpart
+        # the K values the reference's own models use (mask/train_giraffe.sh:1, mask/train_manuel.sh:1): general-K kernels
+        from gaussigan_b200 import synth as _synth
+        for Kr in (6, 12):
+            inp_r = _synth.synth_inputs(B, Kr, seed=56, device=dev)
+            par_r = torch.empty(B, Kr, 8, device=dev)
+            # (the device copies are kept in variables until the projection has run: a temporary would hand its memory
+            # back to the allocator before the kernel reads it)
+            d_mus = inp_r["mus"].reshape(B, Kr, 3).contiguous().to(dev)
+            d_sig = inp_r["sigma"].contiguous().to(dev)
+            d_rot = [inp_r[k_].reshape(B).contiguous().to(dev) for k_ in ("rotx", "roty", "rotz")]
+            check(lib.gg_project_fwd(d_mus.data_ptr(), d_sig.data_ptr(), 1, d_rot[0].data_ptr(), d_rot[1].data_ptr(),
+                                     d_rot[2].data_ptr(), 0.0, 0.0, -2.0, 1.0, B, Kr, None, None, par_r.data_ptr(),
+                                     dev.index, st()), "gg_project_fwd")
+            torch.cuda.synchronize(dev)
+            del d_mus, d_sig, d_rot
+            rb = [torch.randn((B, n, n, Kr), device=dev) for _ in range(3)]       # 3 x 101 / 201 MB > L2
+            rp_ = [ptr_array([m.data_ptr()]) for m in rb]
+            rT = check(lib.gg_splat_bwd_tiles(Kr, 1, msz, int_array((1,)), int_array((0,)), LAYOUT_NHWC), "tiles")
+            rpart = torch.empty((B, rT, Kr, 5), device=dev)
+
+            def r_bwd(i):
+                check(lib.gg_splat_bwd(par_r.data_ptr(), B, Kr, 1, msz, rp_[i % 3], mnull, LAYOUT_NHWC, rpart.data_ptr(),
+                                       rT, dev.index, st()), "gg_splat_bwd(maps)")
+
+            def r_fwd(i):
+                check(lib.gg_splat_fwd(par_r.data_ptr(), B, Kr, 1, msz, rp_[i % 3], mnull, LAYOUT_NHWC, dev.index, st()),
+                      "gg_splat_fwd(maps)")
+
+            us_b, us_f = kernel_us(r_bwd, 18), kernel_us(r_fwd, 18)
+            rbytes = B * n * n * Kr * 4
+            maps_mode[f"k{Kr}"] = {"workload": f"NHWC maps [{B},{n},{n},{Kr}] float32, {rbytes / 1e6:.0f} MB per launch",
+                                   "bwd_us": us_b, "bwd_gbs": rbytes / us_b / 1e3,
+                                   "bwd_frac_of_hbm": rbytes / us_b / 1e3 / peaks["hbm_gbs"],
+                                   "fwd_us": us_f, "fwd_gbs": rbytes / us_f / 1e3,
+                                   "fwd_frac_of_hbm": rbytes / us_f / 1e3 / peaks["hbm_gbs"]}
+            del rb, rpart
     except Exception as exc:                      # pragma: no cover
-        maps_mode = {"error": repr(exc)}
+        maps_mode = {"error": repr(exc)} if maps_mode is None else {**maps_mode, "error_reference_k": repr(exc)}
 
     # ---- training-time exchange: the shared (canonical-Gaussian) gradients summed over batch and ranks after every step.
     # (a) gaussigan_b200.dist.P2PSharedGradReducer: peer-memory kernels over NVLink captured in the same graph as the

@@ -10,6 +10,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--B', type=int, default=64); ap.add_argument('--K', type=int, default=16)
 ap.add_argument('--sizes', type=str, default='256'); ap.add_argument('--reps', type=int, default=20)
 ap.add_argument('--sets', type=int, default=2, help='rotating gradient sets (> L2 in total)')
+ap.add_argument('--graph', type=int, default=0, help='time a CUDA graph of this many back-to-back launches instead of eager launches')
 a = ap.parse_args()
 dev = torch.device('cuda:0')
 B, K = a.B, a.K
@@ -33,17 +34,30 @@ def run(i): check(lib.gg_splat_bwd(params.data_ptr(), B, K, ns, sz, gps[i % a.se
 for i in range(3): run(i)
 torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-e0.record()
-for i in range(a.reps): run(i)
-e1.record(); torch.cuda.synchronize()
-us = e0.elapsed_time(e1) / a.reps * 1e3
+def timed(fn):
+    if a.graph:
+        side = torch.cuda.Stream(dev); side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(a.graph): fn(i)
+        torch.cuda.current_stream(dev).wait_stream(side); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(a.graph): fn(i)
+        for _ in range(3): g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.reps): g.replay()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (a.reps * a.graph) * 1e3
+    e0.record()
+    for i in range(a.reps): fn(i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / a.reps * 1e3
+us = timed(run)
 print(f"B={B} K={K} sizes={sizes} T={T}: bwd {us:.1f} us = {byts/us*1e6/1e9:.0f} GB/s ({byts/1e6:.0f} MB per launch)")
 # forward into the same buffers
 def runf(i): check(lib.gg_splat_fwd(params.data_ptr(), B, K, ns, sz, gps[i % a.sets], nul, LAYOUT_NHWC, 0, st()), 'f')
 for i in range(3): runf(i)
 torch.cuda.synchronize()
-e0.record()
-for i in range(a.reps): runf(i)
-e1.record(); torch.cuda.synchronize()
-us = e0.elapsed_time(e1) / a.reps * 1e3
+us = timed(runf)
 print(f"B={B} K={K} sizes={sizes}: fwd {us:.1f} us = {byts/us*1e6/1e9:.0f} GB/s")

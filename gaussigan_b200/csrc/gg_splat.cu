@@ -26,6 +26,7 @@
 // bit-reproducible; the O(T) sum over slots happens in float64 in the projection adjoint.
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 #include "gg_common.cuh"
 #include "gg_strip.cuh"
 #include "gg_launch.h"
@@ -459,26 +460,47 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_quadg_kernel(const __grid_
       ptr[j] = s.maps + ((size_t)b * n + row_begin) * n * s.cstride + 4 * kq + (size_t)(on[j] ? col : c0) * s.cstride;
     }
     const size_t row_stride = (size_t)n * s.cstride;
-    for (int row = row_begin; row < row_end; ++row) {
-      const float y = grid_coord(row, s.step);
-      float sh[4], e[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float dy = y - muy[i];
-        sh[i] = fmaf(nr[i], dy, mux[i]);
-        e[i] = (nE[i] * dy) * dy;
-      }
-#pragma unroll
-      for (int j = 0; j < kColsPerThread; ++j) {
-        float g[4];
+    // one copy of the row loop per number of columns the WARP uses (fewer on the coarse scales of a pyramid launch and
+    // in the warps behind the last column of a row): no branches inside, stores predicated per lane
+    auto rows = [&](auto mc) {
+      constexpr int M = decltype(mc)::value;
+      for (int row = row_begin; row < row_end; ++row) {
+        const float y = grid_coord(row, s.step);
+        float sh[4], e[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float t = xs[j] - sh[i];
-          g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+          const float dy = y - muy[i];
+          sh[i] = fmaf(nr[i], dy, mux[i]);
+          e[i] = (nE[i] * dy) * dy;
         }
-        if (on[j]) st_f4(ptr[j], g[0], g[1], g[2], g[3]);
-        ptr[j] += row_stride;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          float g[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float t = xs[j] - sh[i];
+            g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+          }
+          if (on[j]) st_f4(ptr[j], g[0], g[1], g[2], g[3]);
+          ptr[j] += row_stride;
+        }
       }
+    };
+    int used = 0;
+#pragma unroll
+    for (int j = 0; j < kColsPerThread; ++j) used += on[j] ? 1 : 0;
+    used = __reduce_max_sync(__activemask(), used);   // warp-uniform: the lanes of a warp run the same copy of the loop
+                                                      // (the lanes past the last unit of a pass have left already)
+    switch (used) {
+      case 1: rows(std::integral_constant<int, 1>{}); break;
+      case 2: rows(std::integral_constant<int, 2>{}); break;
+      case 3: rows(std::integral_constant<int, 3>{}); break;
+      case 4: rows(std::integral_constant<int, 4>{}); break;
+      case 5: rows(std::integral_constant<int, (kColsPerThread >= 5 ? 5 : 1)>{}); break;
+      case 6: rows(std::integral_constant<int, (kColsPerThread >= 6 ? 6 : 1)>{}); break;
+      case 7: rows(std::integral_constant<int, (kColsPerThread >= 7 ? 7 : 1)>{}); break;
+      case 8: rows(std::integral_constant<int, (kColsPerThread >= 8 ? 8 : 1)>{}); break;
+      default: break;
     }
     return;
   }
@@ -543,26 +565,45 @@ __global__ void __launch_bounds__(kThreads) splat_fwd_pair_kernel(const __grid_c
       ptr[j] = s.maps + ((size_t)b * n + row_begin) * n * s.cstride + 2 * kp + (size_t)(on[j] ? col : c0) * s.cstride;
     }
     const size_t row_stride = (size_t)n * s.cstride;
-    for (int row = row_begin; row < row_end; ++row) {
-      const float y = grid_coord(row, s.step);
-      float sh[2], e[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float dy = y - muy[i];
-        sh[i] = fmaf(nr[i], dy, mux[i]);
-        e[i] = (nE[i] * dy) * dy;
-      }
-#pragma unroll
-      for (int j = 0; j < kColsPerThread; ++j) {
-        float g[2];
+    auto rows = [&](auto mc) {
+      constexpr int M = decltype(mc)::value;
+      for (int row = row_begin; row < row_end; ++row) {
+        const float y = grid_coord(row, s.step);
+        float sh[2], e[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const float t = xs[j] - sh[i];
-          g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+          const float dy = y - muy[i];
+          sh[i] = fmaf(nr[i], dy, mux[i]);
+          e[i] = (nE[i] * dy) * dy;
         }
-        if (on[j]) *reinterpret_cast<float2 *>(ptr[j]) = make_float2(g[0], g[1]);
-        ptr[j] += row_stride;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          float g[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float t = xs[j] - sh[i];
+            g[i] = ex2_approx(fmaf(nA[i] * t, t, e[i]));
+          }
+          if (on[j]) *reinterpret_cast<float2 *>(ptr[j]) = make_float2(g[0], g[1]);
+          ptr[j] += row_stride;
+        }
       }
+    };
+    int used = 0;
+#pragma unroll
+    for (int j = 0; j < kColsPerThread; ++j) used += on[j] ? 1 : 0;
+    used = __reduce_max_sync(__activemask(), used);   // warp-uniform: the lanes of a warp run the same copy of the loop
+                                                      // (the lanes past the last unit of a pass have left already)
+    switch (used) {
+      case 1: rows(std::integral_constant<int, 1>{}); break;
+      case 2: rows(std::integral_constant<int, 2>{}); break;
+      case 3: rows(std::integral_constant<int, 3>{}); break;
+      case 4: rows(std::integral_constant<int, 4>{}); break;
+      case 5: rows(std::integral_constant<int, (kColsPerThread >= 5 ? 5 : 1)>{}); break;
+      case 6: rows(std::integral_constant<int, (kColsPerThread >= 6 ? 6 : 1)>{}); break;
+      case 7: rows(std::integral_constant<int, (kColsPerThread >= 7 ? 7 : 1)>{}); break;
+      case 8: rows(std::integral_constant<int, (kColsPerThread >= 8 ? 8 : 1)>{}); break;
+      default: break;
     }
     return;
   }

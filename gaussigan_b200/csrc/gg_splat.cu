@@ -1115,12 +1115,16 @@ cudaError_t launch_splat_fwd(const float *params, int B, int K, int nscales, con
   if (pl.maps.nscales) {
     SplatArgs &a = pl.maps;
     a.params = params; a.B = B; a.K = K; a.T = pl.tiles_maps; a.layout = layout;
-    if (pl.maps_kind == MAPS_QUAD) {
+    static const bool quad_hoist = env_int("GG_QUAD_HOIST", 1) != 0;
+    // (K = 4 / 8 without a fused silhouette: the column-hoisted kernel below, 14.3 -> 11.3 us at K = 4, B = 64, 256 x 256;
+    // K >= 16 is bound by the HBM writes in either kernel)
+    if (pl.maps_kind == MAPS_QUAD && (pl.maps_any_mask || !quad_hoist || K > 8 || fwd_cols_per_thread(a, kThreads / (K >> 2)) > 8)) {
       dim3 grid((unsigned)((size_t)B * a.T));
       if (pl.maps_any_mask) launch_pdl(splat_fwd_quad_kernel<true>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
       else launch_pdl(splat_fwd_quad_kernel<false>, dim3(grid), dim3(kThreads), 0, st, a, pl.kq_shift);
       err = cudaGetLastError();
-    } else if (pl.maps_kind == MAPS_FLAT && (K & 3) == 0 && (K >> 2) <= kThreads) {
+    } else if ((pl.maps_kind == MAPS_QUAD || pl.maps_kind == MAPS_FLAT) && (K & 3) == 0 && (K >> 2) <= kThreads) {
+      // (maps without a fused silhouette at K = 4 * 2^m take the column-hoisted kernel as well)
       const int cols = fwd_cols_per_thread(a, kThreads / (K >> 2));
       const dim3 grid((unsigned)((size_t)B * a.T));
       if (cols <= 4) launch_pdl(splat_fwd_quadg_kernel<4>, grid, dim3(kThreads), 0, st, a, K >> 2);

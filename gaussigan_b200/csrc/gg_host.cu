@@ -206,7 +206,16 @@ int gg_silhouette_step_host(const float *mus_host, const double *sigma_host, con
     k_rz = mapped_or_null(rotz_host, (size_t)B * 4);
   }
   const bool in_place_in = k_mus && k_sigma && k_rx && k_ry && k_rz;
-  if (!in_place_in) {
+  // one block on the host with the workspace's own spacing (mus, sigma and rotx each at the next multiple of 256 bytes,
+  // roty and rotz right behind rotx -- gaussigan_b200.host.HostSilhouetteStep.make_host_inputs builds it): one copy
+  const char *hb = reinterpret_cast<const char *>(mus_host);
+  const bool packed_in = reinterpret_cast<const char *>(sigma_host) == hb + (L.sigma - L.mus) &&
+                         reinterpret_cast<const char *>(rotx_host) == hb + (L.rot - L.mus) &&
+                         roty_host == rotx_host + B && rotz_host == roty_host + B;
+  if (!in_place_in && packed_in) {
+    GG_TRY(cudaMemcpyAsync(d_mus, mus_host, (L.rot - L.mus) + (size_t)3 * B * 4, cudaMemcpyHostToDevice, st), "H2D inputs");
+    k_mus = d_mus; k_sigma = d_sigma; k_rx = d_rot; k_ry = d_rot + B; k_rz = d_rot + 2 * (size_t)B;
+  } else if (!in_place_in) {
     GG_TRY(cudaMemcpyAsync(d_mus, mus_host, (size_t)B * K * 3 * 4, cudaMemcpyHostToDevice, st), "H2D mus");
     GG_TRY(cudaMemcpyAsync(d_sigma, sigma_host, (size_t)B * K * 9 * 8, cudaMemcpyHostToDevice, st), "H2D sigma");
     GG_TRY(cudaMemcpyAsync(d_rot, rotx_host, (size_t)B * 4, cudaMemcpyHostToDevice, st), "H2D rotx");

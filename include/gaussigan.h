@@ -298,7 +298,9 @@ GG_API int gg_shared_grad_allreduce_p2p(const float *dmus, const double *dsigma,
  * copied back).  sigma_host is float64 [B,K,3,3].  loss_partials_host (capacity loss_partials_capacity floats,
  * checked) receives gg_silhouette_step_loss_count(B, K, n) floats; loss = sum(partials) / (B*n*n).  For K <= 64 the step is three
  * launches (projection, fused splat+loss+backward, projection adjoint), otherwise five.  The inputs (Gaussians, camera,
- * target mask) go through the copy engine.  When the GRADIENT buffers (dmus, dsigma, drot) are pinned, the projection
+ * target mask) go through the copy engine; when mus_host, sigma_host and rotx_host lie in ONE host block, each at the
+ * next multiple of 256 bytes behind the previous array, with roty and rotz right behind rotx, the five arrays are
+ * copied with one call.  When the GRADIENT buffers (dmus, dsigma, drot) are pinned, the projection
  * adjoint writes them in place over PCIe instead of into the workspace followed by three copies (a buffer is used in
  * place only if its WHOLE extent is pinned).  GG_ZEROCOPY selects what is accessed in place: "out" (default) the
  * gradients, "in" the Gaussians and the camera, "1" both, "0" nothing.  Measured on B200 / PCIe 5 (batch 64, K = 16,

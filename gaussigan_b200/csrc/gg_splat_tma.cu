@@ -359,10 +359,12 @@ struct FastTile {
   int nstrips;               // 8-pixel strips in the tile
 };
 
-__device__ __forceinline__ FastTile fast_tile(const SplatArgs &a, const ScaleDesc &s, int b, int tile) {
+// `span` consecutive tiles of one scale of one image: they are contiguous in memory, and a CTA whose range holds several
+// of them walks them as ONE span (the per-item bookkeeping is paid once)
+__device__ __forceinline__ FastTile fast_tile(const SplatArgs &a, const ScaleDesc &s, int b, int tile, int span = 1) {
   FastTile t;
   t.row_begin = (tile - s.tile_begin) * s.rows_per_tile;
-  const int row_end = min(s.n, t.row_begin + s.rows_per_tile);
+  const int row_end = min(s.n, t.row_begin + span * s.rows_per_tile);
   t.gtile = s.maps + ((size_t)b * s.n + t.row_begin) * s.n * a.K;
   t.nstrips = (row_end - t.row_begin) * (s.n >> 3);
   return t;
@@ -429,10 +431,12 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
   // ---- issue cursor: runs kFastStages slices ahead of the consume cursor, across item boundaries.  Byte offsets
   // inside the item's tile: this warp's slices start at warp * slice_bytes and are 8 slices apart.
   int iss_b = w_begin / a.T, iss_tile = w_begin - iss_b * a.T, iss_left = w_end - w_begin;
-  int iss_off = 0, iss_total = 0, iss_stage = 0;
+  int iss_off = 0, iss_total = 0, iss_stage = 0, iss_span = 1;
   const char *iss_src = nullptr;
-  auto iss_open = [&]() {   // the tile of item (iss_b, iss_tile)
-    const FastTile t = fast_tile(a, a.sc[find_scale(a, iss_tile)], iss_b, iss_tile);
+  auto iss_open = [&]() {   // the span of tiles that starts at item (iss_b, iss_tile): to the end of its scale or of the range
+    const ScaleDesc &is = a.sc[find_scale(a, iss_tile)];
+    iss_span = min(iss_left, is.tile_begin + is.tiles - iss_tile);
+    const FastTile t = fast_tile(a, is, iss_b, iss_tile, iss_span);
     iss_src = reinterpret_cast<const char *>(t.gtile);
     iss_total = t.nstrips * 32 * K;
     iss_off = warp * slice_bytes;
@@ -440,8 +444,9 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
   if (iss_left > 0) iss_open();
   auto issue_next = [&]() {
     while (iss_left > 0 && iss_off >= iss_total) {
-      --iss_left;
-      if (++iss_tile == a.T) { iss_tile = 0; ++iss_b; }
+      iss_left -= iss_span;
+      iss_tile += iss_span;
+      if (iss_tile == a.T) { iss_tile = 0; ++iss_b; }
       if (iss_left > 0) iss_open();
     }
     if (iss_left <= 0) return;
@@ -471,11 +476,12 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
   unsigned phase = 0;
   int seg_par = 0, prev_b = -1, prev_si = -1;
 
-  for (int work = w_begin; work < w_end; ++work) {
+  for (int work = w_begin; work < w_end;) {
     const int si = find_scale(a, tile);
     const ScaleDesc &s = a.sc[si];
     const int n = s.n;
     const float h = s.step;
+    const int span = min(w_end - work, s.tile_begin + s.tiles - tile);      // tiles of this image and scale walked as one
     if (b != prev_b || si != prev_si) {   // new (image, scale) segment: its constants were staged one segment ago
       prev_b = b; prev_si = si;
       __syncthreads();
@@ -504,12 +510,13 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
       if (nb * a.T + ntile < w_end)
         stage_segment_consts(a, a.sc[find_scale(a, ntile)], nb, sc_base + (size_t)seg_par * fast_consts_floats(K));
     }
-    const bool flush = work == w_end - 1 || tile == a.T - 1;   // last item of this image in this CTA's range
-    float *out = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K) * GG_MOMENTS;
-    if (!flush)
-      for (int c = threadIdx.x; c < K * GG_MOMENTS; c += kThreads) out[c] = 0.f;
+    const bool flush = work + span == w_end || tile + span == a.T;   // last tiles of this image in this CTA's range
+    // the sums go into the slot of the span's last tile when the image ends here; every other slot of the span is zero
+    float *slot0 = a.partials + (((size_t)b * a.slots + a.tile_offset + tile) * K) * GG_MOMENTS;
+    float *out = slot0 + (size_t)(span - 1) * K * GG_MOMENTS;
+    for (int c = threadIdx.x; c < (span - (flush ? 1 : 0)) * K * GG_MOMENTS; c += kThreads) slot0[c] = 0.f;
 
-    const FastTile cur = fast_tile(a, s, b, tile);
+    const FastTile cur = fast_tile(a, s, b, tile, span);
     const int strips_per_row = n >> 3;
     const bool use_gmask = WITH_GMASK && s.mask != nullptr;
     const float hs = flip ? -h : h;                // signed step of this thread's traversal
@@ -632,7 +639,9 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
         out[c] = acc;
       }
     }
-    if (++tile == a.T) { tile = 0; ++b; }
+    work += span;
+    tile += span;
+    if (tile == a.T) { tile = 0; ++b; }
   }
 }
 

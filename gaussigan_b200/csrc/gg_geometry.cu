@@ -10,6 +10,7 @@
 //
 // In the reference each is ~25 tiny TF ops (pure launch latency); here each direction is one launch, one thread
 // per Gaussian.  The reverse passes are hand-derived adjoints evaluated in float64.
+#include <type_traits>
 #include "gg_common.cuh"
 #include "gg_launch.h"
 
@@ -307,7 +308,9 @@ __global__ void __launch_bounds__(128) svd3_fwd_kernel(const double *__restrict_
         be += Bm[r * 3 + q] * Bm[r * 3 + q];
         ga += Bm[r * 3 + p] * Bm[r * 3 + q];
       }
-      if (ga * ga <= 1e-34 * al * be) continue;            // columns orthogonal to ~1e-17
+      // columns orthogonal to 1e-15 (a threshold below the float64 round-off of ga itself is never met, and the loop
+      // ran all 16 sweeps: 19.5 us for 16 matrices; Jacobi converges quadratically, so this stops after 4-6 sweeps)
+      if (ga * ga <= 1e-30 * al * be) continue;
       rotated = true;
       const double zeta = (be - al) / (2.0 * ga);
       const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -327,19 +330,31 @@ __global__ void __launch_bounds__(128) svd3_fwd_kernel(const double *__restrict_
   double sv[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) sv[c] = sqrt(Bm[c] * Bm[c] + Bm[3 + c] * Bm[3 + c] + Bm[6 + c] * Bm[6 + c]);
-  int ord[3] = {0, 1, 2};
-  if (sv[ord[0]] < sv[ord[1]]) { int t = ord[0]; ord[0] = ord[1]; ord[1] = t; }
-  if (sv[ord[1]] < sv[ord[2]]) { int t = ord[1]; ord[1] = ord[2]; ord[2] = t; }
-  if (sv[ord[0]] < sv[ord[1]]) { int t = ord[0]; ord[0] = ord[1]; ord[1] = t; }
+  // singular values in descending order: three compare-and-swap steps on whole columns with compile-time indices (a
+  // run-time permutation index would push Bm and V -- and with them the whole Jacobi loop -- into local memory)
+  auto cswap = [&](auto ca, auto cb) {
+    constexpr int a_ = decltype(ca)::value, b_ = decltype(cb)::value;
+    if (sv[a_] < sv[b_]) {
+      double t = sv[a_]; sv[a_] = sv[b_]; sv[b_] = t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        t = Bm[r * 3 + a_]; Bm[r * 3 + a_] = Bm[r * 3 + b_]; Bm[r * 3 + b_] = t;
+        t = V[r * 3 + a_]; V[r * 3 + a_] = V[r * 3 + b_]; V[r * 3 + b_] = t;
+      }
+    }
+  };
+  cswap(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
+  cswap(std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{});
+  cswap(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double sc = sv[ord[c]];
+    const double sc = sv[c];
     const double inv = sc > 0.0 ? 1.0 / sc : 0.0;
     S[(size_t)i * 3 + c] = sc;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      U[(size_t)i * 9 + r * 3 + c] = Bm[r * 3 + ord[c]] * inv;
-      if (Vout) Vout[(size_t)i * 9 + r * 3 + c] = V[r * 3 + ord[c]];
+      U[(size_t)i * 9 + r * 3 + c] = Bm[r * 3 + c] * inv;
+      if (Vout) Vout[(size_t)i * 9 + r * 3 + c] = V[r * 3 + c];
     }
   }
 }

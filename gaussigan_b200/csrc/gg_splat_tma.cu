@@ -527,8 +527,77 @@ __global__ void __launch_bounds__(kThreads, 2) splat_bwd_nhwc_fast_kernel(const 
     int rrel = 0, cs = g;                          // its row inside the tile and its position inside the row
     while (cs >= strips_per_row) { cs -= strips_per_row; ++rrel; }
     for (int i = 0; i < my_slices; ++i) {
+      bool joint_done = false;
+      if (NP == 1 && __all_sync(0xffffffffu, !lane_ok || (!steep && g + spw < cur.nstrips))) {      // warp-uniform
+        // pair units: the thread's TWO strips of the slice (g and g + spw) as two interleaved recurrences -- same
+        // constants, different rows / columns / shared-memory addresses.  The straight-line code gives the scheduler two
+        // independent dependency chains (the one-strip-after-the-other form below ran at half its issue slots in `wait`).
+        int rs1 = rrel, cq1 = cs + spw;
+        while (cq1 >= strips_per_row) { cq1 -= strips_per_row; ++rs1; }
+        const int colA = cs * 8, colB = cq1 * 8;
+        const int rowA = cur.row_begin + rrel, rowB = cur.row_begin + rs1;
+        float gmA[8], gmB[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gmA[j] = gmB[j] = 0.f;
+        if (use_gmask && lane_ok) {
+          const float4 *mpA = reinterpret_cast<const float4 *>(s.mask + ((size_t)b * n + rowA) * n + colA);
+          const float4 *mpB = reinterpret_cast<const float4 *>(s.mask + ((size_t)b * n + rowB) * n + colB);
+          const float4 a0 = __ldg(mpA), a1 = __ldg(mpA + 1), b0 = __ldg(mpB), b1 = __ldg(mpB + 1);
+          gmA[0] = a0.x; gmA[1] = a0.y; gmA[2] = a0.z; gmA[3] = a0.w; gmA[4] = a1.x; gmA[5] = a1.y; gmA[6] = a1.z; gmA[7] = a1.w;
+          gmB[0] = b0.x; gmB[1] = b0.y; gmB[2] = b0.z; gmB[3] = b0.w; gmB[4] = b1.x; gmB[5] = b1.y; gmB[6] = b1.z; gmB[7] = b1.w;
+        }
+        const f32x2 dyA = sub2(bc(grid_coord(rowA, h)), muy[0]), dyB = sub2(bc(grid_coord(rowB, h)), muy[0]);
+        f32x2 trA = fma2(nnr[0], dyA, sub2(bc(grid_coord(colA, h)), mux[0]));
+        f32x2 trB = fma2(nnr[0], dyB, sub2(bc(grid_coord(colB, h)), mux[0]));
+        f32x2 ggA = ex2_2(fma2(mul2(nA[0], trA), trA, mul2(mul2(nE[0], dyA), dyA)));
+        f32x2 ggB = ex2_2(fma2(mul2(nA[0], trB), trB, mul2(mul2(nE[0], dyB), dyB)));
+        f32x2 rrA = ex2_2(fma2(rb[0], trA, rc[0])), rrB = ex2_2(fma2(rb[0], trB, rc[0]));
+        mbar_wait_u32(bar_u32 + (uint32_t)stage * 8u, phase);
+        // (idle lanes behind the last unit of a slice read the head of the stage: in bounds, result discarded)
+        const uint32_t spA = (lane_ok ? sp_u32 : ring_u32) + (uint32_t)stage * kFastStageBytes;
+        const uint32_t spB = spA + (lane_ok ? (uint32_t)(spw * 32 * K) : 0u);
+        f32x2 A0, B0, C0, A1, B1, C1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f32x2 GA[1], GB[1];
+          load_unit<1>(spA + (uint32_t)(j * dstride), kodd, vm, GA);
+          load_unit<1>(spB + (uint32_t)(j * dstride), kodd, vm, GB);
+          if (WITH_GMASK) { GA[0] = add2(GA[0], bc(gmA[j])); GB[0] = add2(GB[0], bc(gmB[j])); }
+          const f32x2 uA = mul2(ggA, GA[0]), uB = mul2(ggB, GB[0]);
+          if (j == 0) {
+            A0 = B0 = C0 = uA; A1 = B1 = C1 = uB;
+          } else {
+            A0 = add2(A0, uA); A1 = add2(A1, uB);
+            B0 = add2(B0, A0); B1 = add2(B1, A1);
+            C0 = add2(C0, B0); C1 = add2(C1, B1);
+          }
+          if (j < 7) {
+            ggA = mul2(ggA, rrA); ggB = mul2(ggB, rrB);
+            if (j < 6) { rrA = mul2(rrA, cc[0]); rrB = mul2(rrB, cc[0]); }
+          }
+        }
+        __syncwarp();                                  // every lane is done with the stage
+        issue_next();
+        trA = add2(trA, h8); trB = add2(trB, h8);
+        const f32x2 M1A = mul2(B0, nhs), M1B = mul2(B1, nhs);
+        const f32x2 M2A = mul2(sub2(add2(C0, C0), B0), hh), M2B = mul2(sub2(add2(C1, C1), B1), hh);
+        const f32x2 m1A = fma2(trA, A0, M1A), m1B = fma2(trB, A1, M1B);
+        const f32x2 m2A = fma2(trA, add2(M1A, m1A), M2A), m2B = fma2(trB, add2(M1B, m1B), M2B);
+        const f32x2 d0A = mul2(dyA, A0), d0B = mul2(dyB, A1);
+        // (the same order of additions as the one-strip form: strip g first, then g + spw; the idle lanes behind the
+        // last unit of a slice have read stale but in-bounds shared memory: they keep their zero sums)
+        if (lane_ok) {
+          T[0][0] = add2(add2(T[0][0], m2A), m2B);
+          T[0][3] = add2(add2(T[0][3], m1A), m1B);
+          T[0][1] = fma2(dyB, m1B, fma2(dyA, m1A, T[0][1]));
+          T[0][4] = add2(add2(T[0][4], d0A), d0B);
+          T[0][2] = fma2(dyB, d0B, fma2(dyA, d0A, T[0][2]));
+        }
+        joint_done = true;
+      }
 #pragma unroll
       for (int ss = 0; ss < SPT; ++ss) {           // the thread's strips of this slice: g, g + spw
+        if (joint_done) break;
         int rs = rrel, cq = cs;
         if (ss > 0) {
           cq += ss * spw;
